@@ -1,0 +1,165 @@
+"""Pins the CPU oracle (oracle/) — the real natten is absent offline, so the oracle is pinned by
+(a) agreement of two independently written index formulations (C sub-sequence/clamp vs the
+closed-form rules quoted in SURVEY.md §8 c3), (b) analytic backward vs autograd, and
+(c) known-answer properties published with the algorithm (NAT / DiNAT papers)."""
+import itertools
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import na2d_ref as R
+
+torch.manual_seed(0)
+
+CASES = [
+    # (B, heads, H, W, D, K, d)
+    (2, 3, 7, 9, 4, 3, 1),
+    (1, 2, 3, 3, 1, 3, 1),      # minimum size H == W == K
+    (1, 2, 6, 11, 2, 3, 2),     # H == K*d
+    (2, 1, 13, 10, 3, 5, 2),
+    (1, 2, 14, 15, 8, 7, 1),
+    (1, 1, 14, 17, 2, 7, 2),    # H == K*d, ragged residues on W
+    (1, 2, 12, 10, 1, 3, 3),    # W: residue classes of unequal length
+]
+
+
+def _rand(*shape):
+    return torch.randn(*shape, dtype=torch.float64)
+
+
+@pytest.mark.parametrize("B,Hd,H,W,D,K,d", CASES)
+@pytest.mark.parametrize("use_rpb", [True, False])
+def test_c_oracle_matches_closed_form_gather(B, Hd, H, W, D, K, d, use_rpb):
+    o = R.c_oracle()
+    q, k, v = _rand(B, Hd, H, W, D), _rand(B, Hd, H, W, D), _rand(B, Hd, H, W, D)
+    rpb = _rand(Hd, 2 * K - 1, 2 * K - 1) if use_rpb else None
+    attn_c = o.qk_fwd(q, k, rpb, K, d)
+    attn_g = R.na2d_qk_gather(q, k, rpb, K, d)
+    torch.testing.assert_close(attn_c, attn_g, rtol=1e-12, atol=1e-12)
+    p = attn_g.softmax(-1)
+    torch.testing.assert_close(o.av_fwd(p.contiguous(), v, K, d), R.na2d_av_gather(p, v, K, d),
+                               rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize("B,Hd,H,W,D,K,d", CASES)
+def test_c_oracle_backward_matches_autograd(B, Hd, H, W, D, K, d):
+    o = R.c_oracle()
+    q, k, v = (_rand(B, Hd, H, W, D).requires_grad_() for _ in range(3))
+    rpb = _rand(Hd, 2 * K - 1, 2 * K - 1).requires_grad_()
+    attn = R.na2d_qk_gather(q, k, rpb, K, d)
+    g = _rand(*attn.shape)
+    dq, dk, drpb = torch.autograd.grad(attn, (q, k, rpb), g)
+    cdq, cdk, cdrpb = o.qk_bwd(q.detach(), k.detach(), g, K, d)
+    for a, b in ((dq, cdq), (dk, cdk), (drpb, cdrpb)):
+        torch.testing.assert_close(a, b, rtol=1e-11, atol=1e-11)
+    p = attn.detach().softmax(-1).requires_grad_()
+    out = R.na2d_av_gather(p, v, K, d)
+    go = _rand(*out.shape)
+    dp, dv = torch.autograd.grad(out, (p, v), go)
+    cdp, cdv = o.av_bwd(p.detach().contiguous(), v.detach(), go, K, d)
+    torch.testing.assert_close(dp, cdp, rtol=1e-11, atol=1e-11)
+    torch.testing.assert_close(dv, cdv, rtol=1e-11, atol=1e-11)
+
+
+@pytest.mark.parametrize("B,Hd,H,W,D,K,d", CASES)
+@pytest.mark.parametrize("use_rpb", [True, False])
+def test_fused_oracle_fwd_bwd(B, Hd, H, W, D, K, d, use_rpb):
+    """Fused C oracle == composition of the unfused ops == autograd of the gather form."""
+    o = R.c_oracle()
+    q, k, v = (_rand(B, H, W, Hd, D).requires_grad_() for _ in range(3))
+    rpb = _rand(Hd, 2 * K - 1, 2 * K - 1).requires_grad_() if use_rpb else None
+    out = R.na2d_gather(q, k, v, K, d, rpb)
+    go = _rand(*out.shape)
+    grads = torch.autograd.grad(out, (q, k, v) + ((rpb,) if use_rpb else ()), go)
+    rp = rpb.detach() if use_rpb else None
+    cout, lse = o.fused_fwd(q.detach(), k.detach(), v.detach(), rp, K, d, want_lse=True)
+    torch.testing.assert_close(out.detach().contiguous(), cout, rtol=1e-11, atol=1e-11)
+    cg = o.fused_bwd(q.detach(), k.detach(), v.detach(), rp, go, K, d)
+    for a, b in zip(grads, cg):
+        torch.testing.assert_close(a, b, rtol=1e-10, atol=1e-10)
+    # lse really is the log-sum-exp of the scaled scores
+    attn = R.na2d_qk_gather(q.detach().permute(0, 3, 1, 2, 4) * D ** -0.5, k.detach().permute(0, 3, 1, 2, 4), rp, K, d)
+    torch.testing.assert_close(lse, attn.logsumexp(-1).permute(0, 2, 3, 1).contiguous(), rtol=1e-11, atol=1e-11)
+
+
+def test_fp32_oracle_close_to_fp64():
+    o = R.c_oracle()
+    q, k, v = (_rand(2, 9, 8, 12, 4) for _ in range(3))
+    rpb = _rand(12, 5, 5) * 0.02
+    ref = o.fused_fwd(q, k, v, rpb, 3, 1)
+    out = o.fused_fwd(q.float(), k.float(), v.float(), rpb.float(), 3, 1)
+    torch.testing.assert_close(out.double(), ref, rtol=1e-5, atol=1e-5)
+
+
+# ----------------------------- known-answer properties ----------------------------- #
+@pytest.mark.parametrize("L", [3, 5, 7])
+def test_kat_full_window_equals_global_attention_with_swin_bias(L):
+    """NAT paper: with the neighbourhood as large as the feature map NA *is* self-attention.
+    With rpb it is self-attention + Swin's relative position bias B[h, (ki-i)+K-1, (kj-j)+K-1]."""
+    K = L
+    Hd, D = 2, 4
+    q, k, v = (_rand(1, L, L, Hd, D) for _ in range(3))
+    rpb = _rand(Hd, 2 * K - 1, 2 * K - 1)
+    ii, jj = torch.meshgrid(torch.arange(L), torch.arange(L), indexing="ij")
+    ii, jj = ii.reshape(-1), jj.reshape(-1)
+    bias = rpb[:, (ii[None, :] - ii[:, None]) + K - 1, (jj[None, :] - jj[:, None]) + K - 1]  # [Hd, Nq, Nk]
+    qf, kf, vf = (t.reshape(1, L * L, Hd, D).transpose(1, 2) for t in (q, k, v))
+    ref = F.scaled_dot_product_attention(qf, kf, vf, attn_mask=bias[None]).transpose(1, 2).reshape(1, L, L, Hd, D)
+    out = R.c_oracle().fused_fwd(q, k, v, rpb, K, 1)
+    torch.testing.assert_close(out, ref.contiguous(), rtol=1e-10, atol=1e-10)
+
+
+@pytest.mark.parametrize("K", [3, 5])
+def test_kat_interior_equals_unfold_sliding_window(K):
+    """Away from the borders NA is plain sliding-window attention (F.unfold gives the windows)."""
+    B, Hd, H, W, D = 1, 2, 9, 10, 3
+    ns = K // 2
+    q, k, v = (_rand(B, Hd, H, W, D) for _ in range(3))
+    attn = R.c_oracle().qk_fwd(q, k, None, K, 1)
+    # unfold k: [B*Hd, D, H, W] -> [B*Hd, D*K*K, Hi*Wi]
+    ku = F.unfold(k.reshape(B * Hd, H, W, D).permute(0, 3, 1, 2), K).reshape(B, Hd, D, K * K, H - 2 * ns, W - 2 * ns)
+    ref = torch.einsum("bhijd,bhdnij->bhijn", q[:, :, ns:H - ns, ns:W - ns], ku)
+    torch.testing.assert_close(attn[:, :, ns:H - ns, ns:W - ns], ref, rtol=1e-12, atol=1e-12)
+    # central rpb entry sits at the query itself
+    keys, pbs = R.neighbour_table(H, K, 1)
+    assert all(pbs[i, ns] == K - 1 for i in range(ns, H - ns))
+
+
+def test_kat_corner_window_is_shifted_not_padded():
+    """NAT paper fig. 2: a corner query attends the K x K block in that corner (no zero padding)."""
+    for K, d, L in [(3, 1, 8), (7, 1, 9), (3, 2, 9), (5, 3, 17)]:
+        keys, pbs = R.neighbour_table(L, K, d)
+        assert keys[0].tolist() == [m * d for m in range(K)]
+        last_r = (L - 1) % d
+        sub = list(range(last_r, L, d))
+        assert keys[L - 1].tolist() == sub[-K:]
+        # every window has exactly K distinct in-range keys in the query's residue class
+        for i in range(L):
+            assert len(set(keys[i])) == K and keys[i].min() >= 0 and keys[i].max() < L
+            assert all(kk % d == i % d for kk in keys[i])
+            assert (keys[i] - i).tolist() == ((pbs[i] - (K - 1)) * d).tolist()
+
+
+@pytest.mark.parametrize("K,d", [(3, 2), (3, 3), (5, 2)])
+def test_kat_dilation_is_independent_subgrids(K, d):
+    """DiNAT: dilation d == running undilated NA on each of the d*d interleaved sub-grids."""
+    B, H, W, Hd, D = 1, K * d + 3, K * d + 2, 2, 2
+    q, k, v = (_rand(B, H, W, Hd, D) for _ in range(3))
+    rpb = _rand(Hd, 2 * K - 1, 2 * K - 1)
+    o = R.c_oracle()
+    out = o.fused_fwd(q, k, v, rpb, K, d)
+    for ri, rj in itertools.product(range(d), range(d)):
+        sub = [t[:, ri::d, rj::d].contiguous() for t in (q, k, v)]
+        torch.testing.assert_close(out[:, ri::d, rj::d].contiguous(), o.fused_fwd(*sub, rpb, K, 1),
+                                   rtol=1e-12, atol=1e-12)
+
+
+def test_oracle_module_state_dict_keys():
+    m = R.OracleNeighborhoodAttention2D(dim=24, num_heads=12, kernel_size=3)
+    assert list(m.state_dict().keys()) == ["rpb", "qkv.weight", "qkv.bias", "proj.weight", "proj.bias"]
+    x = torch.randn(1, 5, 6, 24)
+    y = m(x)
+    assert y.shape == x.shape
+    y.sum().backward()
+    assert m.rpb.grad is not None and m.rpb.grad.abs().sum() > 0
