@@ -1,0 +1,162 @@
+/*
+ * lmnet_b200.h — C ABI of the B200 (sm_100a) hot-path library for LM-Net.
+ *
+ * This is the drop-in boundary.  The reference has no native
+ * code of its own: it borrows this arithmetic from the external `natten` package
+ * (/root/reference/core/modules.py:18,509,517) and from cuDNN/ATen library kernels
+ * under ReparamConv (/root/reference/core/modules.py:586-600).  Each entry point
+ * names the reference interface it replaces.
+ *
+ * Conventions
+ *  - extern "C", plain C types only.  Device pointers + sizes + a CUDA stream
+ *    (passed as void* so that this header needs no CUDA include).
+ *  - The caller owns every buffer (inputs, outputs, workspaces).  The library never
+ *    allocates, frees or retains pointers, never synchronises the device, and
+ *    enqueues all work on the given stream.
+ *  - Return value: 0 on success, negative lmnet_status on failure.  Nothing throws
+ *    or exits.  No CPU fallback exists: without a CUDA device every compute call
+ *    returns LMNET_ERR_LAUNCH.
+ *  - Thread-safe / re-entrant per stream (no mutable global state).
+ *  - dtype is the element type of activations (q,k,v,out,attn,x,...).  Parameters
+ *    (rpb, conv weights, BN affine and running statistics) and statistics are fp32.
+ */
+#ifndef LMNET_B200_H_
+#define LMNET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LMNET_ABI_VERSION 1
+
+typedef enum lmnet_status {
+    LMNET_OK = 0,
+    LMNET_ERR_INVALID_ARG = -1, /* null pointer, bad size, kernel_size even, H < K*dilation, ... */
+    LMNET_ERR_UNSUPPORTED = -2, /* dtype / shape outside what the kernels implement */
+    LMNET_ERR_LAUNCH = -3,      /* cudaGetLastError() after a launch, or no device */
+    LMNET_ERR_WORKSPACE = -4    /* workspace too small */
+} lmnet_status;
+
+typedef enum lmnet_dtype { LMNET_F32 = 0, LMNET_BF16 = 1, LMNET_F16 = 2 } lmnet_dtype;
+
+/* A logical [B, H, W, heads, D] view: element strides for batch, row, column and
+ * head; the head-dim stride is 1.  Covers natten's unfused layout [B,heads,H,W,D],
+ * the fused layout [B,H,W,heads,D] and slices of a packed qkv tensor [B,H,W,3,heads,D]. */
+typedef struct lmnet_view5 {
+    void* ptr;
+    int64_t sb, sh, sw, sn;
+} lmnet_view5;
+
+typedef struct lmnet_na2d_dims {
+    int32_t B, H, W, heads, D;
+    int32_t kernel_size; /* odd, 3..13 */
+    int32_t dilation;    /* >= 1, H and W must be >= kernel_size*dilation */
+} lmnet_na2d_dims;
+
+int lmnet_abi_version(void);
+const char* lmnet_status_string(int status);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+uint64_t lmnet_launch_count(void);
+
+/* ---- fused neighbourhood attention -------------------------------------------------
+ * Replaces: natten.functional.na2d and the inner sequence of natten's
+ * NeighborhoodAttention2D.forward (q*scale -> na2d_qk+rpb -> softmax -> na2d_av),
+ * called from /root/reference/core/modules.py:517.  No attention map is materialised.
+ *   out[b,i,j,h,:] = sum_n softmax_n(scale*q.k_n + rpb[h,pi,pj]) * v_n
+ * rpb: fp32 [heads, 2K-1, 2K-1] or NULL.  lse: fp32 [B,H,W,heads] (natural log) or NULL. */
+int lmnet_na2d_fwd(const lmnet_view5* q, const lmnet_view5* k, const lmnet_view5* v,
+                   const float* rpb, const lmnet_view5* out, float* lse,
+                   const lmnet_na2d_dims* dims, float scale, int dtype, void* stream);
+
+/* Backward of the fused op with recomputation (replaces the autograd of natten's
+ * na2d_qk / softmax / na2d_av chain).  drpb: fp32 [heads,2K-1,2K-1]
+ * (overwritten) or NULL.  workspace: lmnet_na2d_bwd_workspace_bytes(). */
+size_t lmnet_na2d_bwd_workspace_bytes(const lmnet_na2d_dims* dims);
+int lmnet_na2d_bwd(const lmnet_view5* q, const lmnet_view5* k, const lmnet_view5* v,
+                   const float* rpb, const lmnet_view5* dout,
+                   const lmnet_view5* dq, const lmnet_view5* dk, const lmnet_view5* dv,
+                   float* drpb, void* workspace, size_t workspace_bytes,
+                   const lmnet_na2d_dims* dims, float scale, int dtype, void* stream);
+
+/* ---- unfused ops (natten.functional.na2d_qk / na2d_av, 0.14 names natten2dqkrpb /
+ * natten2dav).  attn / dattn are contiguous [B,heads,H,W,K*K]. */
+int lmnet_na2d_qk_fwd(const lmnet_view5* q, const lmnet_view5* k, const float* rpb, void* attn,
+                      const lmnet_na2d_dims* dims, int dtype, void* stream);
+size_t lmnet_na2d_qk_bwd_workspace_bytes(const lmnet_na2d_dims* dims);
+int lmnet_na2d_qk_bwd(const lmnet_view5* q, const lmnet_view5* k, const void* dattn,
+                      const lmnet_view5* dq, const lmnet_view5* dk, float* drpb,
+                      void* workspace, size_t workspace_bytes,
+                      const lmnet_na2d_dims* dims, int dtype, void* stream);
+int lmnet_na2d_av_fwd(const void* attn, const lmnet_view5* v, const lmnet_view5* out,
+                      const lmnet_na2d_dims* dims, int dtype, void* stream);
+int lmnet_na2d_av_bwd(const void* attn, const lmnet_view5* v, const lmnet_view5* dout,
+                      void* dattn, const lmnet_view5* dv,
+                      const lmnet_na2d_dims* dims, int dtype, void* stream);
+
+/* ---- fused depthwise multi-branch conv + BatchNorm + sum + GELU (+ SE pooling) ------
+ * Replaces the middle section of ReparamConv.forward,
+ * /root/reference/core/modules.py:592-597 (four depthwise branches 5x5, 3x3, 3x1, 1x3
+ * each followed by BatchNorm2d, summed, exact-erf GELU; SE's global average pool rides
+ * on the writer, /root/reference/core/modules.py:1030-1031).
+ * Branch order everywhere: 0 = large (5x5), 1 = square (3x3), 2 = ver (3x1), 3 = hor (1x3).
+ * x, u, z: [B,E,H,W] contiguous NCHW of `dtype`.  Weights fp32: w5 [E,25], w3 [E,9],
+ * w31 [E,3], w13 [E,3]. */
+typedef struct lmnet_dw_params {
+    const float* w[4];         /* w5, w3, w31, w13 */
+    const float* gamma[4];     /* BN weight  [E] per branch */
+    const float* beta[4];      /* BN bias    [E] per branch */
+    float* running_mean[4];    /* [E] per branch; updated in training when non-NULL */
+    float* running_var[4];     /* [E] per branch */
+} lmnet_dw_params;
+
+typedef struct lmnet_dw_grads {
+    float* dw[4];              /* same shapes as lmnet_dw_params.w */
+    float* dgamma[4];
+    float* dbeta[4];
+} lmnet_dw_grads;
+
+typedef struct lmnet_dw_dims {
+    int32_t B, E, H, W;
+} lmnet_dw_dims;
+
+/* One workspace size serves all three entry points below (the backward keeps a [B,E,H,W]
+ * scratch tensor of `dtype` in it). */
+size_t lmnet_reparam_dw_workspace_bytes(const lmnet_dw_dims* dims, int dtype);
+
+/* Training forward: batch statistics (biased variance for normalisation, unbiased for the
+ * running update: running = (1-momentum)*running + momentum*batch), writes
+ *   u = sum_br BN_br(dwconv_br(x))  (pre-activation, saved for backward; may be NULL),
+ *   z = GELU(u), pool[b,e] = mean_hw z (fp32 [B,E], may be NULL),
+ *   save_mean / save_rstd: fp32 [4,E].
+ * num_batches_tracked: NULL, or 4 device pointers (NULL entries allowed) to the BatchNorm
+ * counters (int64), each incremented by one on the stream. */
+int lmnet_reparam_dw_train_fwd(const void* x, const lmnet_dw_params* p, void* u, void* z, float* pool,
+                               float* save_mean, float* save_rstd, float eps, float momentum,
+                               int64_t* const* num_batches_tracked,
+                               void* workspace, size_t workspace_bytes,
+                               const lmnet_dw_dims* dims, int dtype, void* stream);
+
+/* Training backward.  dz: gradient w.r.t. z; dpool: fp32 [B,E] gradient w.r.t. pool or NULL.
+ * Outputs dx [B,E,H,W] and all parameter gradients (overwritten). */
+int lmnet_reparam_dw_train_bwd(const void* x, const void* u, const void* dz, const float* dpool,
+                               const lmnet_dw_params* p, const float* save_mean, const float* save_rstd,
+                               void* dx, const lmnet_dw_grads* g,
+                               void* workspace, size_t workspace_bytes,
+                               const lmnet_dw_dims* dims, int dtype, void* stream);
+
+/* Inference forward with running statistics folded in (the algebra of
+ * ReparamConv.get_equivalent_kernel_bias, /root/reference/core/modules.py:622-642):
+ * one 5x5 depthwise conv + bias + GELU (+ pool).  If p->gamma[0] is NULL the weights in
+ * p->w[0] are taken as an already-fused 5x5 kernel and `bias` as its bias (deploy mode,
+ * /root/reference/core/modules.py:644-657); otherwise `bias` is ignored. */
+int lmnet_reparam_dw_eval_fwd(const void* x, const lmnet_dw_params* p, const float* bias, float eps,
+                              void* z, float* pool, void* workspace, size_t workspace_bytes,
+                              const lmnet_dw_dims* dims, int dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LMNET_B200_H_ */

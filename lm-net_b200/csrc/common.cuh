@@ -1,0 +1,124 @@
+// common.cuh — device helpers shared by the sm_100a kernels of liblmnet_b200.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/lmnet_b200.h"
+
+namespace lmnet {
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+// process-wide launch counter (bench.py reports it as gpu_launches)
+extern unsigned long long g_launch_count;
+inline void count_launch(int n = 1) { __atomic_fetch_add(&g_launch_count, (unsigned long long)n, __ATOMIC_RELAXED); }
+
+#define LMNET_CHECK_LAUNCH()                                   \
+    do {                                                       \
+        lmnet::count_launch();                                 \
+        if (cudaGetLastError() != cudaSuccess) return LMNET_ERR_LAUNCH; \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------
+// element <-> float conversion
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float to_f(float x) { return x; }
+__device__ __forceinline__ float to_f(__nv_bfloat16 x) { return __bfloat162float(x); }
+__device__ __forceinline__ float to_f(__half x) { return __half2float(x); }
+template <typename T> __device__ __forceinline__ T from_f(float x);
+template <> __device__ __forceinline__ float from_f<float>(float x) { return x; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float x) { return __float2bfloat16_rn(x); }
+template <> __device__ __forceinline__ __half from_f<__half>(float x) { return __float2half_rn(x); }
+
+// Load / store N contiguous elements as floats, using the widest vector access (<= 16 B) that
+// N*sizeof(T) allows when `aligned` (pointer known to be aligned to that width).
+template <int BYTES> struct VecOf;
+template <> struct VecOf<16> { using type = uint4; };
+template <> struct VecOf<8> { using type = uint2; };
+template <> struct VecOf<4> { using type = uint32_t; };
+template <> struct VecOf<2> { using type = uint16_t; };
+
+template <int N, typename T> __host__ __device__ constexpr int vec_bytes() {
+    constexpr int total = N * (int)sizeof(T);
+    return (total % 16 == 0) ? 16 : (total % 8 == 0) ? 8 : (total % 4 == 0) ? 4 : (int)sizeof(T) == 2 ? 2 : 4;
+}
+
+template <int N, typename T, bool ALIGNED>
+__device__ __forceinline__ void load_f(const T* __restrict__ p, float (&dst)[N]) {
+    if constexpr (ALIGNED && (vec_bytes<N, T>() > (int)sizeof(T))) {
+        constexpr int VB = vec_bytes<N, T>();
+        using V = typename VecOf<VB>::type;
+        constexpr int PER = VB / (int)sizeof(T);
+        constexpr int NV = N / PER;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            V raw = __ldg(reinterpret_cast<const V*>(p) + i);
+            const T* e = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+            for (int j = 0; j < PER; ++j) dst[i * PER + j] = to_f(e[j]);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) dst[i] = to_f(p[i]);
+    }
+}
+
+template <int N, typename T, bool ALIGNED>
+__device__ __forceinline__ void store_f(T* __restrict__ p, const float (&src)[N]) {
+    if constexpr (ALIGNED && (vec_bytes<N, T>() > (int)sizeof(T))) {
+        constexpr int VB = vec_bytes<N, T>();
+        using V = typename VecOf<VB>::type;
+        constexpr int PER = VB / (int)sizeof(T);
+        constexpr int NV = N / PER;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            V raw;
+            T* e = reinterpret_cast<T*>(&raw);
+#pragma unroll
+            for (int j = 0; j < PER; ++j) e[j] = from_f<T>(src[i * PER + j]);
+            reinterpret_cast<V*>(p)[i] = raw;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) p[i] = from_f<T>(src[i]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// neighbourhood window along one axis, in sub-sequence coordinates (dilation handled by the
+// caller as d*d interleaved sub-grids): start = clamp(t - K/2, 0, L - K); rpb index of the
+// first neighbour = start - t + K - 1.   
+// ---------------------------------------------------------------------------------------
+struct AxisWin {
+    int start;
+    int pb;
+};
+__device__ __forceinline__ AxisWin axis_window(int t, int L, int K) {
+    int st = t - (K >> 1);
+    st = max(st, 0);
+    st = min(st, L - K);
+    return {st, st - t + K - 1};
+}
+// Inverse neighbourhood: the queries t' whose window contains key t form the contiguous range
+// [lo, hi]:  lo = t <= K-1 ? 0 : t - K/2,  hi = t >= L-K ? L-1 : t + K/2.
+__device__ __forceinline__ void inverse_window(int t, int L, int K, int& lo, int& hi) {
+    lo = (t <= K - 1) ? 0 : t - (K >> 1);
+    hi = (t >= L - K) ? L - 1 : t + (K >> 1);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+}  // namespace lmnet

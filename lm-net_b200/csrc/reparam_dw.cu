@@ -1,0 +1,896 @@
+// reparam_dw.cu — fused depthwise multi-branch conv + BatchNorm + sum + GELU (+ SE pooling), sm_100a.
+//
+// Replaces the middle of ReparamConv.forward, /root/reference/core/modules.py:592-597:
+//     out  = BN(dw5x5(x)) + BN(dw3x3(x)) + BN(dw3x1(x)) + BN(dw1x3(x));  z = GELU(out)
+// plus the global average pool that opens SE.forward (/root/reference/core/modules.py:1030-1031),
+// forward and backward, training (batch statistics) and inference (running statistics, i.e. the
+// algebra of get_equivalent_kernel_bias, /root/reference/core/modules.py:622-642).
+//
+// Design.  The four branches are linear in x, so once the batch statistics are
+// known the whole sum collapses to ONE 5x5 depthwise kernel + bias per channel:
+//     u = (sum_br a_br * embed5x5(w_br)) (*) x + sum_br (beta_br - a_br*mean_br),  a_br = gamma_br*rstd_br
+// Training forward = stats pass (4 branch outputs in registers, only sum / sum-of-squares leave the
+// SM) -> per-channel finalize (mean, rstd, running update, merged kernel) -> apply pass (25-tap
+// stencil + exact-erf GELU, writes u and z once, pool partial sums ride on the writer).
+// Backward: R pass (du = dz*gelu'(u); P[t] = sum du(p) x(p+t), 25 lags shared by all branches)
+// -> finalize (dgamma, dbeta, per-branch coefficients) -> A1 pass (dx) -> A2 pass (weight grads).
+//
+// Arithmetic: fp32 throughout, packed as FFMA2 (fma.rn.f32x2, new on sm_100): a thread owns two
+// adjacent output columns as one f32x2 lane pair; the scalar tap weight is the broadcast operand.
+// The input tile is staged in shared memory twice (natural and shifted by one element) so that
+// every (col, col+1) pair is an aligned 64-bit shared load.  A CTA owns one channel, one column
+// stripe and one band of rows, and loops over the batch, so per-channel reductions need no atomics:
+// per-CTA partials are reduced by the finalize kernels in a fixed order (deterministic).
+#include "common.cuh"
+
+namespace lmnet {
+
+struct f2 {
+    float x, y;
+};
+__device__ __forceinline__ f2 mk2(float a, float b) { return f2{a, b}; }
+__device__ __forceinline__ f2 ffma2(f2 a, f2 b, f2 c) {
+    f2 d;
+    asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\t"
+        "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+        "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
+        "mov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d.x), "=f"(d.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+}
+__device__ __forceinline__ f2 ffma2(f2 a, float w, f2 c) { return ffma2(a, mk2(w, w), c); }
+__device__ __forceinline__ f2 ld2(const float* p) {
+    float2 v = *reinterpret_cast<const float2*>(p);
+    return f2{v.x, v.y};
+}
+
+constexpr int kDwThreads = 128;
+constexpr int kDwWarps = 4;
+constexpr int kPitch = 72;  // floats per shared-memory tile row (64 + up to 8 halo columns)
+
+struct DwGeom {
+    int B, E, H, W;
+    int stripes, bands, rows_per_band;  // CTA grid = (stripes, bands, E)
+};
+
+// Stage a tile of one plane into shared memory as floats: sA[r][i] = x(r0+r, c0+i) (0 outside the
+// image), sB[r][i] = sA[r][i+1].
+template <typename T>
+__device__ __forceinline__ void load_tile(const T* __restrict__ plane, int H, int W, int r0, int c0, int rows,
+                                          float* sA, float* sB) {
+    for (int idx = threadIdx.x; idx < rows * kPitch; idx += kDwThreads) {
+        const int r = idx / kPitch, i = idx - r * kPitch;
+        const int gr = r0 + r, gc = c0 + i;
+        float v = 0.f;
+        if (gr >= 0 && gr < H && gc >= 0 && gc < W) v = to_f(plane[(int64_t)gr * W + gc]);
+        sA[idx] = v;
+        if (i > 0) sB[idx - 1] = v;
+    }
+}
+
+// 5x5 window walk.  The thread owns output columns (2*lane, 2*lane+1) of the tile and RT consecutive
+// rows starting at tile row `row0`; shared row `row0 + o + a`, pair offset b holds the inputs for
+// tap (a, b) of output row o.  fn(o, win) is called once per output row with win[a][b] in registers.
+template <int RT, typename Fn>
+__device__ __forceinline__ void walk5(const float* sA, const float* sB, int row0, int col0, Fn&& fn) {
+    f2 rows[5][5];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const float* a = sA + (row0 + r) * kPitch + col0;
+        const float* b = sB + (row0 + r) * kPitch + col0;
+        rows[r][0] = ld2(a); rows[r][1] = ld2(b); rows[r][2] = ld2(a + 2); rows[r][3] = ld2(b + 2); rows[r][4] = ld2(a + 4);
+    }
+#pragma unroll
+    for (int o = 0; o < RT; ++o) {
+        {
+            const int r = o + 4;
+            const float* a = sA + (row0 + r) * kPitch + col0;
+            const float* b = sB + (row0 + r) * kPitch + col0;
+            f2(&dst)[5] = rows[r % 5];
+            dst[0] = ld2(a); dst[1] = ld2(b); dst[2] = ld2(a + 2); dst[3] = ld2(b + 2); dst[4] = ld2(a + 4);
+        }
+        f2 win[5][5];
+#pragma unroll
+        for (int a = 0; a < 5; ++a)
+#pragma unroll
+            for (int b = 0; b < 5; ++b) win[a][b] = rows[(o + a) % 5][b];
+        fn(o, win);
+    }
+}
+
+// 3x3 window walk over the centre of the same geometry: win[a][b] = input at (row o+a-1, col +b-1)
+// relative to the output pixel; `row0` is the tile row of the first output row MINUS 1 and col0 the
+// same even column index as walk5 uses (the 3-wide window starts at col0+1).
+template <int RT, typename Fn>
+__device__ __forceinline__ void walk3(const float* sA, const float* sB, int row0, int col0, Fn&& fn) {
+    f2 rows[3][3];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const float* a = sA + (row0 + r) * kPitch + col0;
+        const float* b = sB + (row0 + r) * kPitch + col0;
+        rows[r][0] = ld2(b); rows[r][1] = ld2(a + 2); rows[r][2] = ld2(b + 2);
+    }
+#pragma unroll
+    for (int o = 0; o < RT; ++o) {
+        {
+            const int r = o + 2;
+            const float* a = sA + (row0 + r) * kPitch + col0;
+            const float* b = sB + (row0 + r) * kPitch + col0;
+            f2(&dst)[3] = rows[r % 3];
+            dst[0] = ld2(b); dst[1] = ld2(a + 2); dst[2] = ld2(b + 2);
+        }
+        f2 win[3][3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int b = 0; b < 3; ++b) win[a][b] = rows[(o + a) % 3][b];
+        fn(o, win);
+    }
+}
+
+struct BranchW {
+    float w5[25], w3[9], w31[3], w13[3];
+};
+__device__ __forceinline__ void load_branch_weights(const lmnet_dw_params& p, int e, BranchW& w) {
+#pragma unroll
+    for (int t = 0; t < 25; ++t) w.w5[t] = __ldg(p.w[0] + e * 25 + t);
+#pragma unroll
+    for (int t = 0; t < 9; ++t) w.w3[t] = __ldg(p.w[1] + e * 9 + t);
+#pragma unroll
+    for (int t = 0; t < 3; ++t) w.w31[t] = __ldg(p.w[2] + e * 3 + t);
+#pragma unroll
+    for (int t = 0; t < 3; ++t) w.w13[t] = __ldg(p.w[3] + e * 3 + t);
+}
+
+// the four branch outputs of one output pixel pair from its 5x5 window
+__device__ __forceinline__ void branches_from_window(const f2 (&win)[5][5], const BranchW& w, f2 (&y)[4]) {
+    y[0] = y[1] = y[2] = y[3] = mk2(0.f, 0.f);
+#pragma unroll
+    for (int a = 0; a < 5; ++a)
+#pragma unroll
+        for (int b = 0; b < 5; ++b) y[0] = ffma2(win[a][b], w.w5[a * 5 + b], y[0]);
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) y[1] = ffma2(win[a + 1][b + 1], w.w3[a * 3 + b], y[1]);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) y[2] = ffma2(win[a + 1][2], w.w31[a], y[2]);
+#pragma unroll
+    for (int b = 0; b < 3; ++b) y[3] = ffma2(win[2][b + 1], w.w13[b], y[3]);
+}
+
+// Sum N per-thread floats over the CTA; thread k < N ends up with the total in the return slot.
+template <int N>
+__device__ __forceinline__ void block_sum(float (&v)[N], float* s_red /* [kDwWarps][N] */, float* out /* [N] or null */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < N; ++k) v[k] = warp_sum(v[k]);
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < N; ++k) s_red[warp * N + k] = v[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < N && out != nullptr) {
+        float a = 0.f;
+#pragma unroll
+        for (int w = 0; w < kDwWarps; ++w) a += s_red[w * N + threadIdx.x];
+        out[threadIdx.x] = a;
+    }
+}
+
+__device__ __forceinline__ float gelu_f(float u) { return 0.5f * u * (1.f + erff(u * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_grad_f(float u) {
+    return 0.5f * (1.f + erff(u * 0.70710678118654752f)) + u * 0.3989422804014327f * __expf(-0.5f * u * u);
+}
+
+template <typename T>
+__device__ __forceinline__ f2 load_pair(const T* __restrict__ p, bool v0, bool v1, bool vec) {
+    if (vec && v1) {
+        if constexpr (sizeof(T) == 4) {
+            float2 r = *reinterpret_cast<const float2*>(p);
+            return f2{r.x, r.y};
+        } else {
+            uint32_t raw = *reinterpret_cast<const uint32_t*>(p);
+            const T* e = reinterpret_cast<const T*>(&raw);
+            return f2{to_f(e[0]), to_f(e[1])};
+        }
+    }
+    return f2{v0 ? to_f(p[0]) : 0.f, v1 ? to_f(p[1]) : 0.f};
+}
+template <typename T>
+__device__ __forceinline__ void store_pair(T* __restrict__ p, f2 v, bool v0, bool v1, bool vec) {
+    if (vec && v1) {
+        if constexpr (sizeof(T) == 4) {
+            *reinterpret_cast<float2*>(p) = make_float2(v.x, v.y);
+        } else {
+            uint32_t raw;
+            T* e = reinterpret_cast<T*>(&raw);
+            e[0] = from_f<T>(v.x);
+            e[1] = from_f<T>(v.y);
+            *reinterpret_cast<uint32_t*>(p) = raw;
+        }
+        return;
+    }
+    if (v0) p[0] = from_f<T>(v.x);
+    if (v1) p[1] = from_f<T>(v.y);
+}
+
+// =================================================================================================
+// forward: statistics pass
+// =================================================================================================
+constexpr int kFwdRT = 8;                       // output rows per thread
+constexpr int kFwdTH = kFwdRT * kDwWarps;       // 32 output rows per tile
+constexpr int kFwdTW = 64;                      // output columns per tile
+constexpr int kFwdTileRows = kFwdTH + 4;
+
+template <typename T>
+__global__ void __launch_bounds__(kDwThreads)
+dw_stats_kernel(const T* __restrict__ x, lmnet_dw_params p, float* __restrict__ part /* [E][ncta][8] */, DwGeom g) {
+    __shared__ __align__(16) float sA[kFwdTileRows * kPitch];
+    __shared__ __align__(16) float sB[kFwdTileRows * kPitch];
+    __shared__ float s_red[kDwWarps * 8];
+    const int e = blockIdx.z, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c0 = blockIdx.x * kFwdTW;
+    const int band0 = blockIdx.y * g.rows_per_band, band1 = min(band0 + g.rows_per_band, g.H);
+    BranchW w;
+    load_branch_weights(p, e, w);
+    f2 s[4], ss[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s[k] = ss[k] = mk2(0.f, 0.f);
+    const int col = c0 + 2 * lane;
+    const f2 cmask = mk2(col < g.W ? 1.f : 0.f, col + 1 < g.W ? 1.f : 0.f);
+    for (int b = 0; b < g.B; ++b) {
+        const T* plane = x + ((int64_t)b * g.E + e) * g.H * g.W;
+        for (int tr = band0; tr < band1; tr += kFwdTH) {
+            __syncthreads();
+            load_tile(plane, g.H, g.W, tr - 2, c0 - 2, kFwdTileRows, sA, sB);
+            __syncthreads();
+            walk5<kFwdRT>(sA, sB, warp * kFwdRT, 2 * lane, [&](int o, const f2(&win)[5][5]) {
+                const int row = tr + warp * kFwdRT + o;
+                f2 y[4];
+                branches_from_window(win, w, y);
+                const float rm = row < band1 ? 1.f : 0.f;
+                const f2 m = mk2(cmask.x * rm, cmask.y * rm);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const f2 ym = mk2(y[k].x * m.x, y[k].y * m.y);
+                    s[k].x += ym.x; s[k].y += ym.y;
+                    ss[k] = ffma2(ym, y[k], ss[k]);
+                }
+            });
+        }
+    }
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { v[k] = s[k].x + s[k].y; v[4 + k] = ss[k].x + ss[k].y; }
+    const int ncta = gridDim.x * gridDim.y, cta = blockIdx.y * gridDim.x + blockIdx.x;
+    block_sum<8>(v, s_red, part + ((int64_t)e * ncta + cta) * 8);
+}
+
+// per-channel finalize of the forward statistics: mean / rstd, running-stat update, merged 5x5 kernel
+// coef[e][0..24] = merged taps, coef[e][25] = bias
+__global__ void dw_fin_fwd_kernel(const float* __restrict__ part, int ncta, lmnet_dw_params p, float* __restrict__ save_mean,
+                                  float* __restrict__ save_rstd, float* __restrict__ coef, float eps, float momentum,
+                                  int64_t* nbt0, int64_t* nbt1, int64_t* nbt2, int64_t* nbt3, DwGeom g) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= g.E) return;
+    const double n = (double)g.B * g.H * g.W;
+    double sum[4] = {0, 0, 0, 0}, sq[4] = {0, 0, 0, 0};
+    for (int c = 0; c < ncta; ++c)
+        for (int k = 0; k < 4; ++k) {
+            sum[k] += part[((int64_t)e * ncta + c) * 8 + k];
+            sq[k] += part[((int64_t)e * ncta + c) * 8 + 4 + k];
+        }
+    float m5[25];
+    for (int t = 0; t < 25; ++t) m5[t] = 0.f;
+    float bias = 0.f;
+    for (int k = 0; k < 4; ++k) {
+        const double mean = sum[k] / n;
+        double var = sq[k] / n - mean * mean;
+        if (var < 0) var = 0;
+        const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+        save_mean[k * g.E + e] = (float)mean;
+        save_rstd[k * g.E + e] = rstd;
+        if (p.running_mean[k] != nullptr) {
+            const double unbiased = n > 1 ? var * n / (n - 1) : var;
+            p.running_mean[k][e] = (1.f - momentum) * p.running_mean[k][e] + momentum * (float)mean;
+            p.running_var[k][e] = (1.f - momentum) * p.running_var[k][e] + momentum * (float)unbiased;
+        }
+        const float a = p.gamma[k][e] * rstd;
+        bias += p.beta[k][e] - a * (float)mean;
+        if (k == 0) for (int t = 0; t < 25; ++t) m5[t] += a * p.w[0][e * 25 + t];
+        if (k == 1) for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) m5[(i + 1) * 5 + j + 1] += a * p.w[1][e * 9 + i * 3 + j];
+        if (k == 2) for (int i = 0; i < 3; ++i) m5[(i + 1) * 5 + 2] += a * p.w[2][e * 3 + i];
+        if (k == 3) for (int j = 0; j < 3; ++j) m5[2 * 5 + j + 1] += a * p.w[3][e * 3 + j];
+    }
+    for (int t = 0; t < 25; ++t) coef[e * 26 + t] = m5[t];
+    coef[e * 26 + 25] = bias;
+    if (e == 0) {
+        if (nbt0) *nbt0 += 1;
+        if (nbt1) *nbt1 += 1;
+        if (nbt2) *nbt2 += 1;
+        if (nbt3) *nbt3 += 1;
+    }
+}
+
+// inference coefficients: running statistics folded into one 5x5 kernel + bias (or deploy weights)
+__global__ void dw_coef_eval_kernel(lmnet_dw_params p, const float* __restrict__ deploy_bias, float eps,
+                                    float* __restrict__ coef, int E) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    if (p.gamma[0] == nullptr) {  // deploy mode: p.w[0] is the fused kernel
+        for (int t = 0; t < 25; ++t) coef[e * 26 + t] = p.w[0][e * 25 + t];
+        coef[e * 26 + 25] = deploy_bias != nullptr ? deploy_bias[e] : 0.f;
+        return;
+    }
+    float m5[25];
+    for (int t = 0; t < 25; ++t) m5[t] = 0.f;
+    float bias = 0.f;
+    for (int k = 0; k < 4; ++k) {
+        const float a = p.gamma[k][e] / sqrtf(p.running_var[k][e] + eps);
+        bias += p.beta[k][e] - a * p.running_mean[k][e];
+        if (k == 0) for (int t = 0; t < 25; ++t) m5[t] += a * p.w[0][e * 25 + t];
+        if (k == 1) for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) m5[(i + 1) * 5 + j + 1] += a * p.w[1][e * 9 + i * 3 + j];
+        if (k == 2) for (int i = 0; i < 3; ++i) m5[(i + 1) * 5 + 2] += a * p.w[2][e * 3 + i];
+        if (k == 3) for (int j = 0; j < 3; ++j) m5[2 * 5 + j + 1] += a * p.w[3][e * 3 + j];
+    }
+    for (int t = 0; t < 25; ++t) coef[e * 26 + t] = m5[t];
+    coef[e * 26 + 25] = bias;
+}
+
+// =================================================================================================
+// forward: apply pass  u = merged5x5(x) + bias;  z = GELU(u);  pool partial sums
+// =================================================================================================
+template <typename T>
+__global__ void __launch_bounds__(kDwThreads)
+dw_apply_kernel(const T* __restrict__ x, const float* __restrict__ coef, T* __restrict__ u_out, T* __restrict__ z_out,
+                float* __restrict__ pool_part /* [B*E][ncta] or null */, DwGeom g) {
+    __shared__ __align__(16) float sA[kFwdTileRows * kPitch];
+    __shared__ __align__(16) float sB[kFwdTileRows * kPitch];
+    __shared__ float s_red[kDwWarps];
+    const int e = blockIdx.z, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c0 = blockIdx.x * kFwdTW;
+    const int band0 = blockIdx.y * g.rows_per_band, band1 = min(band0 + g.rows_per_band, g.H);
+    float wm[25];
+#pragma unroll
+    for (int t = 0; t < 25; ++t) wm[t] = __ldg(coef + e * 26 + t);
+    const float bias = __ldg(coef + e * 26 + 25);
+    const int col = c0 + 2 * lane;
+    const bool v0 = col < g.W, v1 = col + 1 < g.W;
+    const bool vec = (g.W & 1) == 0;
+    const int ncta = gridDim.x * gridDim.y, cta = blockIdx.y * gridDim.x + blockIdx.x;
+    for (int b = 0; b < g.B; ++b) {
+        const int64_t poff = ((int64_t)b * g.E + e) * g.H * g.W;
+        const T* plane = x + poff;
+        float psum = 0.f;
+        for (int tr = band0; tr < band1; tr += kFwdTH) {
+            __syncthreads();
+            load_tile(plane, g.H, g.W, tr - 2, c0 - 2, kFwdTileRows, sA, sB);
+            __syncthreads();
+            walk5<kFwdRT>(sA, sB, warp * kFwdRT, 2 * lane, [&](int o, const f2(&win)[5][5]) {
+                const int row = tr + warp * kFwdRT + o;
+                f2 acc = mk2(bias, bias);
+#pragma unroll
+                for (int a = 0; a < 5; ++a)
+#pragma unroll
+                    for (int bb = 0; bb < 5; ++bb) acc = ffma2(win[a][bb], wm[a * 5 + bb], acc);
+                if (row < band1 && v0) {
+                    const int64_t off = poff + (int64_t)row * g.W + col;
+                    if (u_out != nullptr) store_pair(u_out + off, acc, v0, v1, vec);
+                    // GELU of the value as stored (what the reference's next op would read)
+                    f2 ur = mk2(to_f(from_f<T>(acc.x)), to_f(from_f<T>(acc.y)));
+                    f2 z = mk2(gelu_f(ur.x), gelu_f(ur.y));
+                    store_pair(z_out + off, z, v0, v1, vec);
+                    psum += to_f(from_f<T>(z.x)) + (v1 ? to_f(from_f<T>(z.y)) : 0.f);
+                }
+            });
+        }
+        if (pool_part != nullptr) {
+            psum = warp_sum(psum);
+            __syncthreads();
+            if (lane == 0) s_red[warp] = psum;
+            __syncthreads();
+            if (threadIdx.x == 0)
+                pool_part[((int64_t)b * g.E + e) * ncta + cta] = s_red[0] + s_red[1] + s_red[2] + s_red[3];
+        }
+    }
+}
+
+__global__ void dw_pool_fin_kernel(const float* __restrict__ pool_part, int ncta, float inv_hw, float* __restrict__ pool, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float a = 0.f;
+    for (int c = 0; c < ncta; ++c) a += pool_part[(int64_t)i * ncta + c];
+    pool[i] = a * inv_hw;
+}
+
+// =================================================================================================
+// backward R pass: du = (dz + dpool/HW) * gelu'(u);  P[t] = sum_p du(p) x(p+t) (25 lags);  sum du
+// =================================================================================================
+template <typename T>
+__global__ void __launch_bounds__(kDwThreads)
+dw_bwd_reduce_kernel(const T* __restrict__ x, const T* __restrict__ u, const T* __restrict__ dz,
+                     const float* __restrict__ dpool, T* __restrict__ du_out, float* __restrict__ part /* [E][ncta][26] */,
+                     DwGeom g) {
+    __shared__ __align__(16) float sA[kFwdTileRows * kPitch];
+    __shared__ __align__(16) float sB[kFwdTileRows * kPitch];
+    __shared__ float s_red[kDwWarps * 26];
+    const int e = blockIdx.z, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c0 = blockIdx.x * kFwdTW;
+    const int band0 = blockIdx.y * g.rows_per_band, band1 = min(band0 + g.rows_per_band, g.H);
+    const int col = c0 + 2 * lane;
+    const bool v0 = col < g.W, v1 = col + 1 < g.W;
+    const bool vec = (g.W & 1) == 0;
+    const float inv_hw = 1.f / ((float)g.H * (float)g.W);
+    f2 P[25];
+#pragma unroll
+    for (int t = 0; t < 25; ++t) P[t] = mk2(0.f, 0.f);
+    f2 sdu = mk2(0.f, 0.f);
+    for (int b = 0; b < g.B; ++b) {
+        const int64_t poff = ((int64_t)b * g.E + e) * g.H * g.W;
+        const float dp = dpool != nullptr ? __ldg(dpool + b * g.E + e) * inv_hw : 0.f;
+        for (int tr = band0; tr < band1; tr += kFwdTH) {
+            __syncthreads();
+            load_tile(x + poff, g.H, g.W, tr - 2, c0 - 2, kFwdTileRows, sA, sB);
+            __syncthreads();
+            walk5<kFwdRT>(sA, sB, warp * kFwdRT, 2 * lane, [&](int o, const f2(&win)[5][5]) {
+                const int row = tr + warp * kFwdRT + o;
+                f2 du = mk2(0.f, 0.f);
+                if (row < band1 && v0) {
+                    const int64_t off = poff + (int64_t)row * g.W + col;
+                    const f2 uu = load_pair(u + off, v0, v1, vec);
+                    const f2 gz = load_pair(dz + off, v0, v1, vec);
+                    du = mk2((gz.x + dp) * gelu_grad_f(uu.x), v1 ? (gz.y + dp) * gelu_grad_f(uu.y) : 0.f);
+                    store_pair(du_out + off, du, v0, v1, vec);
+                    // keep exactly what later passes will read back
+                    du = mk2(to_f(from_f<T>(du.x)), to_f(from_f<T>(du.y)));
+                }
+                sdu.x += du.x; sdu.y += du.y;
+#pragma unroll
+                for (int a = 0; a < 5; ++a)
+#pragma unroll
+                    for (int bb = 0; bb < 5; ++bb) P[a * 5 + bb] = ffma2(win[a][bb], du, P[a * 5 + bb]);
+            });
+        }
+    }
+    float v[26];
+#pragma unroll
+    for (int t = 0; t < 25; ++t) v[t] = P[t].x + P[t].y;
+    v[25] = sdu.x + sdu.y;
+    const int ncta = gridDim.x * gridDim.y, cta = blockIdx.y * gridDim.x + blockIdx.x;
+    block_sum<26>(v, s_red, part + ((int64_t)e * ncta + cta) * 26);
+}
+
+// Per-channel finalize of the backward reductions.
+//   Pfin[e][26]   : P[t] summed over CTAs, [25] = sum du
+//   dgamma_br = rstd_br * (sum_t w_br[t] P[t] - mean_br * sum du),  dbeta_br = sum du
+//   cb[e][br*3 + {0,1,2}] = c1, c2, c0 with dy_br = c1*du - c2*y_br - c0
+__global__ void dw_fin_bwd_kernel(const float* __restrict__ part, int ncta, lmnet_dw_params p,
+                                  const float* __restrict__ save_mean, const float* __restrict__ save_rstd,
+                                  lmnet_dw_grads gr, float* __restrict__ Pfin, float* __restrict__ cb, DwGeom g) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= g.E) return;
+    const double n = (double)g.B * g.H * g.W;
+    double P[26];
+    for (int t = 0; t < 26; ++t) P[t] = 0;
+    for (int c = 0; c < ncta; ++c)
+        for (int t = 0; t < 26; ++t) P[t] += part[((int64_t)e * ncta + c) * 26 + t];
+    for (int t = 0; t < 26; ++t) Pfin[e * 26 + t] = (float)P[t];
+    const double sdu = P[25];
+    for (int k = 0; k < 4; ++k) {
+        double sduy = 0;
+        if (k == 0) for (int t = 0; t < 25; ++t) sduy += (double)p.w[0][e * 25 + t] * P[t];
+        if (k == 1) for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) sduy += (double)p.w[1][e * 9 + i * 3 + j] * P[(i + 1) * 5 + j + 1];
+        if (k == 2) for (int i = 0; i < 3; ++i) sduy += (double)p.w[2][e * 3 + i] * P[(i + 1) * 5 + 2];
+        if (k == 3) for (int j = 0; j < 3; ++j) sduy += (double)p.w[3][e * 3 + j] * P[2 * 5 + j + 1];
+        const double mean = save_mean[k * g.E + e], rstd = save_rstd[k * g.E + e], gamma = p.gamma[k][e];
+        const double dgamma = rstd * (sduy - mean * sdu);
+        if (gr.dgamma[k] != nullptr) gr.dgamma[k][e] = (float)dgamma;
+        if (gr.dbeta[k] != nullptr) gr.dbeta[k][e] = (float)sdu;
+        const double c1 = gamma * rstd;
+        const double c2 = gamma * rstd * rstd * dgamma / n;
+        const double c0 = c1 * sdu / n - c2 * mean;
+        cb[e * 12 + k * 3 + 0] = (float)c1;
+        cb[e * 12 + k * 3 + 1] = (float)c2;
+        cb[e * 12 + k * 3 + 2] = (float)c0;
+    }
+}
+
+// =================================================================================================
+// backward A1 pass: dx = sum_br w_br (*)^T dy_br,  dy_br = c1*du - c2*y_br - c0 inside the image
+// =================================================================================================
+constexpr int kA1RT = 4;                      // dx rows per thread
+constexpr int kA1TH = kA1RT * kDwWarps;       // 16 dx rows per tile
+constexpr int kA1TW = 60;                     // dx columns per tile (dy region = 64 columns)
+constexpr int kA1RegRows = kA1TH + 4;         // dy region rows (20)
+constexpr int kA1RegRT = kA1RegRows / kDwWarps;  // 5 region rows per warp
+constexpr int kA1XRows = kA1TH + 8;           // x tile rows (halo 4)
+
+template <typename T>
+__global__ void __launch_bounds__(kDwThreads)
+dw_bwd_dx_kernel(const T* __restrict__ x, const T* __restrict__ du, lmnet_dw_params p, const float* __restrict__ cb,
+                 T* __restrict__ dx, DwGeom g) {
+    extern __shared__ __align__(16) float smem[];
+    float* xA = smem;
+    float* xB = xA + kA1XRows * kPitch;
+    float* dyA = xB + kA1XRows * kPitch;            // [4][kA1RegRows*kPitch]
+    float* dyB = dyA + 4 * kA1RegRows * kPitch;     // [4][kA1RegRows*kPitch]
+    const int e = blockIdx.z, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c0 = blockIdx.x * kA1TW;
+    const int band0 = blockIdx.y * g.rows_per_band, band1 = min(band0 + g.rows_per_band, g.H);
+    BranchW w;
+    load_branch_weights(p, e, w);
+    float c1[4], c2[4], c0c[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        c1[k] = __ldg(cb + e * 12 + k * 3);
+        c2[k] = __ldg(cb + e * 12 + k * 3 + 1);
+        c0c[k] = __ldg(cb + e * 12 + k * 3 + 2);
+    }
+    const bool vec = (g.W & 1) == 0;
+    for (int b = 0; b < g.B; ++b) {
+        const int64_t poff = ((int64_t)b * g.E + e) * g.H * g.W;
+        for (int tr = band0; tr < band1; tr += kA1TH) {
+            __syncthreads();
+            load_tile(x + poff, g.H, g.W, tr - 4, c0 - 4, kA1XRows, xA, xB);
+            __syncthreads();
+            // phase 2: y_br and dy_br on the (TH+4) x 64 region whose origin is (tr-2, c0-2)
+            walk5<kA1RegRT>(xA, xB, warp * kA1RegRT, 2 * lane, [&](int o, const f2(&win)[5][5]) {
+                const int rr = warp * kA1RegRT + o;       // region row
+                const int row = tr - 2 + rr, col = c0 - 2 + 2 * lane;
+                f2 y[4];
+                branches_from_window(win, w, y);
+                const bool rin = row >= 0 && row < g.H;
+                const bool i0 = rin && col >= 0 && col < g.W, i1 = rin && col + 1 >= 0 && col + 1 < g.W;
+                f2 d = mk2(0.f, 0.f);
+                if (i0 || i1) {
+                    const T* dp = du + poff + (int64_t)row * g.W + col;
+                    d.x = i0 ? to_f(dp[0]) : 0.f;
+                    d.y = i1 ? to_f(dp[1]) : 0.f;
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    f2 dy = mk2(i0 ? c1[k] * d.x - c2[k] * y[k].x - c0c[k] : 0.f, i1 ? c1[k] * d.y - c2[k] * y[k].y - c0c[k] : 0.f);
+                    float* a = dyA + k * kA1RegRows * kPitch + rr * kPitch + 2 * lane;
+                    float* bsh = dyB + k * kA1RegRows * kPitch + rr * kPitch + 2 * lane;
+                    *reinterpret_cast<float2*>(a) = make_float2(dy.x, dy.y);
+                    // shifted copy: B[i] = A[i+1]
+                    if (lane > 0) bsh[-1] = dy.x;
+                    bsh[0] = dy.y;
+                }
+            });
+            __syncthreads();
+            // phase 3: dx(r,c) = sum_br sum_{a,b} w_br[a][b] * dy_br(r-(a-2), c-(b-2))  (flipped taps)
+            f2 acc[kA1RT];
+#pragma unroll
+            for (int o = 0; o < kA1RT; ++o) acc[o] = mk2(0.f, 0.f);
+            walk5<kA1RT>(dyA, dyB, warp * kA1RT, 2 * lane, [&](int o, const f2(&win)[5][5]) {
+#pragma unroll
+                for (int a = 0; a < 5; ++a)
+#pragma unroll
+                    for (int bb = 0; bb < 5; ++bb) acc[o] = ffma2(win[a][bb], w.w5[(4 - a) * 5 + (4 - bb)], acc[o]);
+            });
+            walk3<kA1RT>(dyA + kA1RegRows * kPitch, dyB + kA1RegRows * kPitch, warp * kA1RT + 1, 2 * lane,
+                         [&](int o, const f2(&win)[3][3]) {
+#pragma unroll
+                             for (int a = 0; a < 3; ++a)
+#pragma unroll
+                                 for (int bb = 0; bb < 3; ++bb) acc[o] = ffma2(win[a][bb], w.w3[(2 - a) * 3 + (2 - bb)], acc[o]);
+                         });
+            walk3<kA1RT>(dyA + 2 * kA1RegRows * kPitch, dyB + 2 * kA1RegRows * kPitch, warp * kA1RT + 1, 2 * lane,
+                         [&](int o, const f2(&win)[3][3]) {
+#pragma unroll
+                             for (int a = 0; a < 3; ++a) acc[o] = ffma2(win[a][1], w.w31[2 - a], acc[o]);
+                         });
+            walk3<kA1RT>(dyA + 3 * kA1RegRows * kPitch, dyB + 3 * kA1RegRows * kPitch, warp * kA1RT + 1, 2 * lane,
+                         [&](int o, const f2(&win)[3][3]) {
+#pragma unroll
+                             for (int bb = 0; bb < 3; ++bb) acc[o] = ffma2(win[1][bb], w.w13[2 - bb], acc[o]);
+                         });
+            const int col = c0 + 2 * lane;
+            if (2 * lane < kA1TW && col < g.W) {
+#pragma unroll
+                for (int o = 0; o < kA1RT; ++o) {
+                    const int row = tr + warp * kA1RT + o;
+                    if (row < band1) store_pair(dx + poff + (int64_t)row * g.W + col, acc[o], true, col + 1 < g.W, vec);
+                }
+            }
+        }
+    }
+}
+
+// =================================================================================================
+// backward A2 pass: Rbr[t] = sum_p (c2_br*y_br(p) + c0_br) * x(p+t);  dw_br[t] = c1_br*P[t] - Rbr[t]
+// =================================================================================================
+template <typename T>
+__global__ void __launch_bounds__(kDwThreads)
+dw_bwd_dw_kernel(const T* __restrict__ x, lmnet_dw_params p, const float* __restrict__ cb,
+                 float* __restrict__ part /* [E][ncta][40] */, DwGeom g) {
+    __shared__ __align__(16) float sA[kFwdTileRows * kPitch];
+    __shared__ __align__(16) float sB[kFwdTileRows * kPitch];
+    __shared__ float s_red[kDwWarps * 40];
+    const int e = blockIdx.z, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c0 = blockIdx.x * kFwdTW;
+    const int band0 = blockIdx.y * g.rows_per_band, band1 = min(band0 + g.rows_per_band, g.H);
+    BranchW w;
+    load_branch_weights(p, e, w);
+    float c2[4], c0c[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        c2[k] = __ldg(cb + e * 12 + k * 3 + 1);
+        c0c[k] = __ldg(cb + e * 12 + k * 3 + 2);
+    }
+    const int col = c0 + 2 * lane;
+    const f2 cmask = mk2(col < g.W ? 1.f : 0.f, col + 1 < g.W ? 1.f : 0.f);
+    f2 A5[25], A3[9], A31[3], A13[3];
+#pragma unroll
+    for (int t = 0; t < 25; ++t) A5[t] = mk2(0.f, 0.f);
+#pragma unroll
+    for (int t = 0; t < 9; ++t) A3[t] = mk2(0.f, 0.f);
+#pragma unroll
+    for (int t = 0; t < 3; ++t) A31[t] = A13[t] = mk2(0.f, 0.f);
+    for (int b = 0; b < g.B; ++b) {
+        const T* plane = x + ((int64_t)b * g.E + e) * g.H * g.W;
+        for (int tr = band0; tr < band1; tr += kFwdTH) {
+            __syncthreads();
+            load_tile(plane, g.H, g.W, tr - 2, c0 - 2, kFwdTileRows, sA, sB);
+            __syncthreads();
+            walk5<kFwdRT>(sA, sB, warp * kFwdRT, 2 * lane, [&](int o, const f2(&win)[5][5]) {
+                const int row = tr + warp * kFwdRT + o;
+                const float rm = row < band1 ? 1.f : 0.f;
+                const f2 m = mk2(cmask.x * rm, cmask.y * rm);
+                f2 y[4];
+                branches_from_window(win, w, y);
+                f2 gk[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) gk[k] = mk2((c2[k] * y[k].x + c0c[k]) * m.x, (c2[k] * y[k].y + c0c[k]) * m.y);
+#pragma unroll
+                for (int a = 0; a < 5; ++a)
+#pragma unroll
+                    for (int bb = 0; bb < 5; ++bb) A5[a * 5 + bb] = ffma2(win[a][bb], gk[0], A5[a * 5 + bb]);
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+#pragma unroll
+                    for (int bb = 0; bb < 3; ++bb) A3[a * 3 + bb] = ffma2(win[a + 1][bb + 1], gk[1], A3[a * 3 + bb]);
+#pragma unroll
+                for (int a = 0; a < 3; ++a) A31[a] = ffma2(win[a + 1][2], gk[2], A31[a]);
+#pragma unroll
+                for (int bb = 0; bb < 3; ++bb) A13[bb] = ffma2(win[2][bb + 1], gk[3], A13[bb]);
+            });
+        }
+    }
+    float v[40];
+#pragma unroll
+    for (int t = 0; t < 25; ++t) v[t] = A5[t].x + A5[t].y;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) v[25 + t] = A3[t].x + A3[t].y;
+#pragma unroll
+    for (int t = 0; t < 3; ++t) { v[34 + t] = A31[t].x + A31[t].y; v[37 + t] = A13[t].x + A13[t].y; }
+    const int ncta = gridDim.x * gridDim.y, cta = blockIdx.y * gridDim.x + blockIdx.x;
+    block_sum<40>(v, s_red, part + ((int64_t)e * ncta + cta) * 40);
+}
+
+__global__ void dw_fin_dw_kernel(const float* __restrict__ part, int ncta, const float* __restrict__ Pfin,
+                                 const float* __restrict__ cb, lmnet_dw_grads gr, int E) {
+    const int e = blockIdx.x;
+    const int t = threadIdx.x;  // 0..39
+    if (e >= E || t >= 40) return;
+    double r = 0;
+    for (int c = 0; c < ncta; ++c) r += part[((int64_t)e * ncta + c) * 40 + t];
+    int k, lag, idx;
+    if (t < 25) { k = 0; idx = t; lag = t; }
+    else if (t < 34) { k = 1; idx = t - 25; lag = (idx / 3 + 1) * 5 + idx % 3 + 1; }
+    else if (t < 37) { k = 2; idx = t - 34; lag = (idx + 1) * 5 + 2; }
+    else { k = 3; idx = t - 37; lag = 2 * 5 + idx + 1; }
+    const double c1 = cb[e * 12 + k * 3];
+    const float val = (float)(c1 * (double)Pfin[e * 26 + lag] - r);
+    const int per = k == 0 ? 25 : k == 1 ? 9 : 3;
+    if (gr.dw[k] != nullptr) gr.dw[k][e * per + idx] = val;
+}
+
+// =================================================================================================
+// host side
+// =================================================================================================
+static size_t dw_align(size_t x) { return (x + 255) / 256 * 256; }
+
+static int dw_validate(const lmnet_dw_dims* d) {
+    if (d == nullptr || d->B <= 0 || d->E <= 0 || d->H <= 0 || d->W <= 0) return LMNET_ERR_INVALID_ARG;
+    if ((int64_t)d->B * d->E * d->H * d->W >= (int64_t)1 << 40) return LMNET_ERR_INVALID_ARG;
+    return LMNET_OK;
+}
+
+// CTA grid for a kernel with tile (th x tw): enough CTAs for ~4 waves of 148 SMs, bands aligned to th
+static DwGeom dw_geom(const lmnet_dw_dims* d, int th, int tw) {
+    DwGeom g;
+    g.B = d->B; g.E = d->E; g.H = d->H; g.W = d->W;
+    g.stripes = (d->W + tw - 1) / tw;
+    const int row_tiles = (d->H + th - 1) / th;
+    int bands = (4 * 148 + g.E * g.stripes - 1) / (g.E * g.stripes);
+    bands = bands < 1 ? 1 : bands > row_tiles ? row_tiles : bands;
+    const int tiles_per_band = (row_tiles + bands - 1) / bands;
+    g.rows_per_band = tiles_per_band * th;
+    g.bands = (d->H + g.rows_per_band - 1) / g.rows_per_band;
+    return g;
+}
+
+struct DwWs {
+    size_t part, coef, pool_part, pfin, cb, du, total;
+};
+static DwWs dw_ws_layout(const lmnet_dw_dims* d, size_t esize) {
+    DwGeom gf = dw_geom(d, kFwdTH, kFwdTW);
+    const size_t ncta = (size_t)gf.stripes * gf.bands;
+    DwWs w;
+    size_t off = 0;
+    w.part = off; off = dw_align(off + (size_t)d->E * ncta * 40 * sizeof(float));
+    w.coef = off; off = dw_align(off + (size_t)d->E * 26 * sizeof(float));
+    w.pool_part = off; off = dw_align(off + (size_t)d->B * d->E * ncta * sizeof(float));
+    w.pfin = off; off = dw_align(off + (size_t)d->E * 26 * sizeof(float));
+    w.cb = off; off = dw_align(off + (size_t)d->E * 12 * sizeof(float));
+    w.du = off; off = dw_align(off + (size_t)d->B * d->E * d->H * d->W * esize);
+    w.total = off;
+    return w;
+}
+
+template <typename T>
+static int dw_train_fwd(const void* x, const lmnet_dw_params* p, void* u, void* z, float* pool, float* save_mean,
+                        float* save_rstd, float eps, float momentum, int64_t* const* nbt, char* ws,
+                        const lmnet_dw_dims* d, cudaStream_t st) {
+    DwGeom g = dw_geom(d, kFwdTH, kFwdTW);
+    DwWs L = dw_ws_layout(d, sizeof(T));
+    const int ncta = g.stripes * g.bands;
+    dim3 grid(g.stripes, g.bands, g.E);
+    float* part = (float*)(ws + L.part);
+    float* coef = (float*)(ws + L.coef);
+    float* pool_part = (float*)(ws + L.pool_part);
+    dw_stats_kernel<T><<<grid, kDwThreads, 0, st>>>((const T*)x, *p, part, g);
+    LMNET_CHECK_LAUNCH();
+    dw_fin_fwd_kernel<<<(g.E + 63) / 64, 64, 0, st>>>(part, ncta, *p, save_mean, save_rstd, coef, eps, momentum,
+                                                     nbt ? nbt[0] : nullptr, nbt ? nbt[1] : nullptr,
+                                                     nbt ? nbt[2] : nullptr, nbt ? nbt[3] : nullptr, g);
+    LMNET_CHECK_LAUNCH();
+    dw_apply_kernel<T><<<grid, kDwThreads, 0, st>>>((const T*)x, coef, (T*)u, (T*)z, pool ? pool_part : nullptr, g);
+    LMNET_CHECK_LAUNCH();
+    if (pool) {
+        const int n = g.B * g.E;
+        dw_pool_fin_kernel<<<(n + 127) / 128, 128, 0, st>>>(pool_part, ncta, 1.f / ((float)g.H * g.W), pool, n);
+        LMNET_CHECK_LAUNCH();
+    }
+    return LMNET_OK;
+}
+
+template <typename T>
+static int dw_eval_fwd(const void* x, const lmnet_dw_params* p, const float* bias, float eps, void* z, float* pool,
+                       char* ws, const lmnet_dw_dims* d, cudaStream_t st) {
+    DwGeom g = dw_geom(d, kFwdTH, kFwdTW);
+    DwWs L = dw_ws_layout(d, sizeof(T));
+    const int ncta = g.stripes * g.bands;
+    dim3 grid(g.stripes, g.bands, g.E);
+    float* coef = (float*)(ws + L.coef);
+    float* pool_part = (float*)(ws + L.pool_part);
+    dw_coef_eval_kernel<<<(g.E + 63) / 64, 64, 0, st>>>(*p, bias, eps, coef, g.E);
+    LMNET_CHECK_LAUNCH();
+    dw_apply_kernel<T><<<grid, kDwThreads, 0, st>>>((const T*)x, coef, (T*)nullptr, (T*)z, pool ? pool_part : nullptr, g);
+    LMNET_CHECK_LAUNCH();
+    if (pool) {
+        const int n = g.B * g.E;
+        dw_pool_fin_kernel<<<(n + 127) / 128, 128, 0, st>>>(pool_part, ncta, 1.f / ((float)g.H * g.W), pool, n);
+        LMNET_CHECK_LAUNCH();
+    }
+    return LMNET_OK;
+}
+
+constexpr size_t kA1SmemBytes = (size_t)(2 * kA1XRows * kPitch + 8 * kA1RegRows * kPitch) * sizeof(float);
+
+template <typename T>
+static int dw_train_bwd(const void* x, const void* u, const void* dz, const float* dpool, const lmnet_dw_params* p,
+                        const float* save_mean, const float* save_rstd, void* dx, const lmnet_dw_grads* gr, char* ws,
+                        const lmnet_dw_dims* d, cudaStream_t st) {
+    DwGeom g = dw_geom(d, kFwdTH, kFwdTW);
+    DwWs L = dw_ws_layout(d, sizeof(T));
+    const int ncta = g.stripes * g.bands;
+    dim3 grid(g.stripes, g.bands, g.E);
+    float* part = (float*)(ws + L.part);
+    float* pfin = (float*)(ws + L.pfin);
+    float* cb = (float*)(ws + L.cb);
+    T* du = (T*)(ws + L.du);
+    dw_bwd_reduce_kernel<T><<<grid, kDwThreads, 0, st>>>((const T*)x, (const T*)u, (const T*)dz, dpool, du, part, g);
+    LMNET_CHECK_LAUNCH();
+    dw_fin_bwd_kernel<<<(g.E + 63) / 64, 64, 0, st>>>(part, ncta, *p, save_mean, save_rstd, *gr, pfin, cb, g);
+    LMNET_CHECK_LAUNCH();
+    {
+        DwGeom ga = dw_geom(d, kA1TH, kA1TW);
+        static bool attr_set = false;  // benign race: the attribute is idempotent
+        if (!attr_set) {
+            if (cudaFuncSetAttribute(dw_bwd_dx_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kA1SmemBytes) != cudaSuccess)
+                return LMNET_ERR_LAUNCH;
+            attr_set = true;
+        }
+        dim3 ga_grid(ga.stripes, ga.bands, ga.E);
+        dw_bwd_dx_kernel<T><<<ga_grid, kDwThreads, kA1SmemBytes, st>>>((const T*)x, du, *p, cb, (T*)dx, ga);
+        LMNET_CHECK_LAUNCH();
+    }
+    dw_bwd_dw_kernel<T><<<grid, kDwThreads, 0, st>>>((const T*)x, *p, cb, part, g);
+    LMNET_CHECK_LAUNCH();
+    dw_fin_dw_kernel<<<g.E, 64, 0, st>>>(part, ncta, pfin, cb, *gr, g.E);
+    LMNET_CHECK_LAUNCH();
+    return LMNET_OK;
+}
+
+}  // namespace lmnet
+
+using namespace lmnet;
+
+extern "C" size_t lmnet_reparam_dw_workspace_bytes(const lmnet_dw_dims* dims, int dtype) {
+    if (dw_validate(dims) != LMNET_OK) return 0;
+    return dw_ws_layout(dims, dtype == LMNET_F32 ? 4 : 2).total;
+}
+
+static bool dw_params_ok(const lmnet_dw_params* p, bool need_bn) {
+    if (p == nullptr || p->w[0] == nullptr) return false;
+    if (!need_bn) return true;
+    for (int k = 0; k < 4; ++k)
+        if (p->w[k] == nullptr || p->gamma[k] == nullptr || p->beta[k] == nullptr) return false;
+    return true;
+}
+
+extern "C" int lmnet_reparam_dw_train_fwd(const void* x, const lmnet_dw_params* p, void* u, void* z, float* pool,
+                                          float* save_mean, float* save_rstd, float eps, float momentum,
+                                          int64_t* const* num_batches_tracked,
+                                          void* workspace, size_t workspace_bytes,
+                                          const lmnet_dw_dims* dims, int dtype, void* stream) {
+    int rc = dw_validate(dims);
+    if (rc != LMNET_OK) return rc;
+    if (!x || !z || !save_mean || !save_rstd || !workspace || !dw_params_ok(p, true)) return LMNET_ERR_INVALID_ARG;
+    for (int k = 0; k < 4; ++k)
+        if ((p->running_mean[k] == nullptr) != (p->running_var[k] == nullptr)) return LMNET_ERR_INVALID_ARG;
+    if (workspace_bytes < lmnet_reparam_dw_workspace_bytes(dims, dtype)) return LMNET_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (dtype) {
+        case LMNET_F32: return dw_train_fwd<float>(x, p, u, z, pool, save_mean, save_rstd, eps, momentum, num_batches_tracked, (char*)workspace, dims, st);
+        case LMNET_BF16: return dw_train_fwd<__nv_bfloat16>(x, p, u, z, pool, save_mean, save_rstd, eps, momentum, num_batches_tracked, (char*)workspace, dims, st);
+        case LMNET_F16: return dw_train_fwd<__half>(x, p, u, z, pool, save_mean, save_rstd, eps, momentum, num_batches_tracked, (char*)workspace, dims, st);
+        default: return LMNET_ERR_UNSUPPORTED;
+    }
+}
+
+extern "C" int lmnet_reparam_dw_train_bwd(const void* x, const void* u, const void* dz, const float* dpool,
+                                          const lmnet_dw_params* p, const float* save_mean, const float* save_rstd,
+                                          void* dx, const lmnet_dw_grads* g,
+                                          void* workspace, size_t workspace_bytes,
+                                          const lmnet_dw_dims* dims, int dtype, void* stream) {
+    int rc = dw_validate(dims);
+    if (rc != LMNET_OK) return rc;
+    if (!x || !u || !dz || !dx || !g || !save_mean || !save_rstd || !workspace || !dw_params_ok(p, true)) return LMNET_ERR_INVALID_ARG;
+    if (workspace_bytes < lmnet_reparam_dw_workspace_bytes(dims, dtype)) return LMNET_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (dtype) {
+        case LMNET_F32: return dw_train_bwd<float>(x, u, dz, dpool, p, save_mean, save_rstd, dx, g, (char*)workspace, dims, st);
+        case LMNET_BF16: return dw_train_bwd<__nv_bfloat16>(x, u, dz, dpool, p, save_mean, save_rstd, dx, g, (char*)workspace, dims, st);
+        case LMNET_F16: return dw_train_bwd<__half>(x, u, dz, dpool, p, save_mean, save_rstd, dx, g, (char*)workspace, dims, st);
+        default: return LMNET_ERR_UNSUPPORTED;
+    }
+}
+
+extern "C" int lmnet_reparam_dw_eval_fwd(const void* x, const lmnet_dw_params* p, const float* bias, float eps,
+                                         void* z, float* pool, void* workspace, size_t workspace_bytes,
+                                         const lmnet_dw_dims* dims, int dtype, void* stream) {
+    int rc = dw_validate(dims);
+    if (rc != LMNET_OK) return rc;
+    if (!x || !z || !workspace || p == nullptr || p->w[0] == nullptr) return LMNET_ERR_INVALID_ARG;
+    const bool deploy = p->gamma[0] == nullptr;
+    if (!deploy) {
+        if (!dw_params_ok(p, true)) return LMNET_ERR_INVALID_ARG;
+        for (int k = 0; k < 4; ++k)
+            if (p->running_mean[k] == nullptr || p->running_var[k] == nullptr) return LMNET_ERR_INVALID_ARG;
+    }
+    if (workspace_bytes < lmnet_reparam_dw_workspace_bytes(dims, dtype)) return LMNET_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (dtype) {
+        case LMNET_F32: return dw_eval_fwd<float>(x, p, bias, eps, z, pool, (char*)workspace, dims, st);
+        case LMNET_BF16: return dw_eval_fwd<__nv_bfloat16>(x, p, bias, eps, z, pool, (char*)workspace, dims, st);
+        case LMNET_F16: return dw_eval_fwd<__half>(x, p, bias, eps, z, pool, (char*)workspace, dims, st);
+        default: return LMNET_ERR_UNSUPPORTED;
+    }
+}

@@ -1,0 +1,302 @@
+"""LM-Net assembled on the B200 hot-path operators.
+
+A from-scratch restatement of the network of /root/reference/core/LM_Net.py:5-123 and the building
+blocks it instantiates from /root/reference/core/modules.py (ReparamConv :525-658, SE :1020-1044,
+NeighborhoodTransformer :504-521, OverlapPatchEmbed :22-40, Mlp :42-56, M3Skip :83-107,
+M2Skip :109-143, GlobalAttention :235-279, GFT :329-347, PyramidPool :454-498).
+
+Why it exists: the reference sources are not present on the benchmark machine, so the harness needs
+its own definition of the model.  Sub-module names and parameter shapes are kept identical, so a
+reference ``state_dict`` loads with ``strict=True`` and vice versa (tests/test_model_parity.py checks
+this against the real reference when it is available).  The two ★ units run on the sm_100a kernels:
+``ReparamConv`` through ``lmnet_b200.reparam`` and ``NeighborhoodTransformer.att1`` through the
+drop-in ``natten.NeighborhoodAttention2D``.  Everything else is ordinary torch.nn (cuDNN / cuBLAS),
+exactly as in the reference (out of scope).
+"""
+from __future__ import annotations
+
+import math
+from collections import OrderedDict
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from natten import NeighborhoodAttention2D
+
+from .reparam import reparam_forward
+
+
+def _conv_bn(channels: int, kernel, padding) -> nn.Sequential:
+    return nn.Sequential(OrderedDict(
+        conv=nn.Conv2d(channels, channels, kernel, stride=1, padding=padding, groups=channels, bias=False),
+        bn=nn.BatchNorm2d(channels)))
+
+
+class SE(nn.Module):
+    """Squeeze-excite gate (reference: core/modules.py:1020-1044).  In the fused block only fc1/fc2 and
+    the two activations are used; ``forward`` is kept for completeness."""
+
+    def __init__(self, channels: int, reduction: int = 4):
+        super().__init__()
+        self.avgpool = nn.AdaptiveAvgPool2d(1)
+        self.fc1 = nn.Conv2d(channels, channels // reduction, 1)
+        self.fc2 = nn.Conv2d(channels // reduction, channels, 1)
+        self.activation = nn.ReLU(inplace=True)
+        self.scale_activation = nn.Hardsigmoid(inplace=True)
+        for conv in (self.fc1, self.fc2):
+            nn.init.kaiming_normal_(conv.weight)
+
+    def forward(self, x):
+        return x * self.scale_activation(self.fc2(self.activation(self.fc1(self.avgpool(x)))))
+
+
+class ReparamConv(nn.Module):
+    """expand 1x1 + BN + Hardswish -> four depthwise branches + BN -> sum -> GELU -> SE -> 1x1, plus a
+    1x1 shortcut (reference: core/modules.py:525-658).  The branch section runs fused on the GPU."""
+
+    def __init__(self, in_channels, expand_channels, out_channels, large_kernel_size=5, kernel_size=3, stride=1,
+                 groups=1, deploy=False):
+        super().__init__()
+        if (large_kernel_size, kernel_size, stride) != (5, 3, 1):
+            raise NotImplementedError("LM-Net uses ReparamConv(…, 5, 3) with stride 1; other shapes are not built")
+        self.large_kernel_size, self.kernel_size = large_kernel_size, kernel_size
+        self.in_channels, self.expand_channels, self.stride, self.deploy = in_channels, expand_channels, stride, deploy
+        E = expand_channels
+        self.se = SE(E)
+        self.expand_conv = nn.Sequential(nn.Conv2d(in_channels, E, 1), nn.BatchNorm2d(E), nn.Hardswish(inplace=True))
+        if deploy:
+            self.fuse_conv = nn.Conv2d(E, E, 5, 1, 2, groups=E, bias=True)
+        else:
+            self.large_conv = _conv_bn(E, 5, 2)
+            self.square_conv = _conv_bn(E, 3, 1)
+            self.ver_conv = _conv_bn(E, (3, 1), (1, 0))
+            self.hor_conv = _conv_bn(E, (1, 3), (0, 1))
+        self.active = nn.GELU()
+        self.pointwise_conv = nn.Sequential(nn.Conv2d(E, out_channels, 1))
+        self.shortcut = nn.Sequential(nn.Conv2d(in_channels, out_channels, 1))
+
+    forward = reparam_forward
+
+    # ---- structural re-parameterisation (same algebra as core/modules.py:602-657) ----
+    @staticmethod
+    def _fold(branch):
+        bn = branch.bn
+        scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+        return branch.conv.weight * scale.view(-1, 1, 1, 1), bn.bias - bn.running_mean * scale
+
+    def get_equivalent_kernel_bias(self):
+        kernel, bias = self._fold(self.large_conv)
+        kernel = kernel.clone()
+        for branch in (self.square_conv, self.ver_conv, self.hor_conv):
+            k, b = self._fold(branch)
+            ph, pw = (5 - k.shape[2]) // 2, (5 - k.shape[3]) // 2
+            kernel += F.pad(k, (pw, pw, ph, ph))
+            bias = bias + b
+        return kernel, bias
+
+    def switch_to_deploy(self):
+        if self.deploy:
+            return
+        kernel, bias = self.get_equivalent_kernel_bias()
+        E = self.expand_channels
+        fused = nn.Conv2d(E, E, 5, 1, 2, groups=E, bias=True).to(kernel.device, kernel.dtype)
+        fused.weight.data, fused.bias.data = kernel.detach(), bias.detach()
+        self.fuse_conv = fused
+        self.deploy = True
+        for name in ("large_conv", "square_conv", "ver_conv", "hor_conv"):
+            delattr(self, name)
+
+
+class OverlapPatchEmbed(nn.Module):
+    def __init__(self, patch, channels_in, channels_out, stride, channels_last: bool):
+        super().__init__()
+        self.channels_last = channels_last
+        self.patch_embeddings = nn.Conv2d(channels_in, channels_out, patch, stride, patch // 2)
+
+    def forward(self, x):
+        x = self.patch_embeddings(x)
+        return x.permute(0, 2, 3, 1) if self.channels_last else x.flatten(2).transpose(1, 2)
+
+
+class Mlp(nn.Module):
+    def __init__(self, dim, hidden, out):
+        super().__init__()
+        self.fc1, self.fc2 = nn.Linear(dim, hidden), nn.Linear(hidden, out)
+        self.act_fn, self.dropout = nn.GELU(), nn.Dropout(0.1)
+
+    def forward(self, x):
+        return self.dropout(self.fc2(self.dropout(self.act_fn(self.fc1(x)))))
+
+
+class NeighborhoodTransformer(nn.Module):
+    """3x3 conv embed -> LN -> NA(kernel 3) -> +res -> LN -> MLP -> +res (reference: core/modules.py:504-521)."""
+
+    def __init__(self, channels, num_heads=12, kernel_size=3):
+        super().__init__()
+        self.patchembedding = OverlapPatchEmbed(3, channels, channels, 1, channels_last=True)
+        self.norm1 = nn.LayerNorm(channels)
+        self.att1 = NeighborhoodAttention2D(dim=channels, num_heads=num_heads, kernel_size=kernel_size)
+        self.norm2 = nn.LayerNorm(channels)
+        self.mlp = Mlp(channels, 2 * channels, channels)
+
+    def forward(self, x):
+        emb = self.patchembedding(x)
+        att = self.att1(self.norm1(emb)) + emb
+        y = self.mlp(self.norm2(att)) + att
+        return y.permute(0, 3, 1, 2).contiguous()
+
+
+def _up2():
+    return nn.Upsample(scale_factor=2, mode="bilinear", align_corners=True)
+
+
+class M3Skip(nn.Module):
+    """Fuses a larger, an equal and a smaller scale (reference: core/modules.py:83-107)."""
+
+    def __init__(self, ch):
+        super().__init__()
+        lo, mid, hi = ch
+        self.convl = nn.Sequential(nn.Conv2d(lo, mid, 3, 2, 1))
+        self.convm = nn.Sequential(nn.Conv2d(mid, mid, 3, 1, 1))
+        self.convs = nn.Sequential(_up2(), nn.Conv2d(hi, mid, 3, 1, 1))
+        self.fuse_conv = nn.Sequential(nn.Conv2d(3 * mid, mid, 3, 1, 1), nn.BatchNorm2d(mid), nn.GELU())
+
+    def forward(self, xl, xm, xs):
+        return self.fuse_conv(torch.cat([self.convl(xl), self.convm(xm), self.convs(xs)], dim=1))
+
+
+class M2Skip(nn.Module):
+    """Two-scale fusion at the ends of the pyramid (reference: core/modules.py:109-143)."""
+
+    def __init__(self, ch, model_type="bottom"):
+        super().__init__()
+        big, small = ch
+        self.model_type = model_type
+        if model_type == "bottom":
+            self.convl = nn.Sequential(nn.Conv2d(big, small, 3, 2, 1))
+            self.convs = nn.Sequential(nn.Conv2d(small, small, 3, 1, 1))
+            width = small
+        else:
+            self.convl = nn.Sequential(nn.Conv2d(big, big, 3, 1, 1))
+            self.convs = nn.Sequential(_up2(), nn.Conv2d(small, big, 3, 1, 1))
+            width = big
+        self.fuse_conv = nn.Sequential(nn.Conv2d(2 * width, width, 3, 1, 1), nn.BatchNorm2d(width), nn.GELU())
+
+    def forward(self, xl, xs):
+        return self.fuse_conv(torch.cat([self.convl(xl), self.convs(xs)], dim=1))
+
+
+class GlobalAttention(nn.Module):
+    """Plain multi-head self-attention over the 1/16-resolution tokens (reference: core/modules.py:235-279)."""
+
+    def __init__(self, dim, num_heads):
+        super().__init__()
+        self.dim, self.num_heads, self.head_dim = dim, num_heads, dim // num_heads
+        self.scale = self.head_dim ** -0.5
+        self.qkv = nn.Linear(dim, 3 * dim)
+        self.attn_drop = nn.Dropout(0.0)
+        self.proj = nn.Linear(dim, dim)
+        self.proj_drop = nn.Dropout(0.0)
+        for lin in (self.qkv, self.proj):
+            nn.init.trunc_normal_(lin.weight, std=0.02)
+            nn.init.zeros_(lin.bias)
+
+    def forward(self, x):
+        B, N, C = x.shape
+        q, k, v = self.qkv(x).reshape(B, N, 3, self.num_heads, self.head_dim).permute(2, 0, 3, 1, 4)
+        attn = self.attn_drop(((q @ k.transpose(-2, -1)) * self.scale).softmax(dim=-1))
+        return self.proj_drop(self.proj((attn @ v).transpose(1, 2).reshape(B, N, C)))
+
+
+class GFT(nn.Module):
+    """Global transformer on the pooled multi-scale stack (reference: core/modules.py:329-347)."""
+
+    def __init__(self, channels, expand_ratio, out_channels, num_heads):
+        super().__init__()
+        self.patchembedding = OverlapPatchEmbed(3, channels, channels, 1, channels_last=False)
+        self.norm1 = nn.LayerNorm(channels)
+        self.attention = GlobalAttention(channels, num_heads)
+        self.norm2 = nn.LayerNorm(channels)
+        self.mlp = Mlp(channels, expand_ratio * channels, channels)
+        self.conv = nn.Sequential(nn.Conv2d(channels, out_channels, 1))
+
+    def forward(self, x):
+        B, C, H, W = x.shape
+        emb = self.patchembedding(x)
+        att = self.attention(self.norm1(emb)) + emb
+        y = self.mlp(self.norm2(att)) + att
+        return self.conv(y.reshape(B, H, W, -1).permute(0, 3, 1, 2).contiguous())
+
+
+class PyramidPool(nn.Module):
+    """Average-pools x1..x4 to the resolution of x5 and stacks everything (reference: core/modules.py:454-498)."""
+
+    def forward(self, x1, x2, x3, x4, x5):
+        size = x5.shape[-2:]
+        return torch.cat([F.adaptive_avg_pool2d(t, size) for t in (x1, x2, x3, x4)] + [x5], dim=1)
+
+
+class LM_Net(nn.Module):
+    """U-shaped encoder/decoder: 8 x 2 ReparamConv, 4 stride-2 convs, PyramidPool + GFT bottleneck,
+    4 skip-fusion blocks, 4 NeighborhoodTransformer, 4 upsample+conv, 1x1 head
+    (reference: core/LM_Net.py:5-123)."""
+
+    def __init__(self, channel, n_classes=2, filters=(12, 24, 48, 96, 192), deep_supervision=False):
+        super().__init__()
+        f = list(filters)
+        self.filters, self.deep_supervision = f, deep_supervision
+
+        def stage(cin, width):
+            return nn.Sequential(ReparamConv(cin, 2 * width, width), ReparamConv(width, 2 * width, width))
+
+        def down(cin, cout):
+            return nn.Sequential(nn.Conv2d(cin, cout, 3, 2, 1))
+
+        def up(cin, cout):
+            return nn.Sequential(_up2(), nn.Conv2d(cin, cout, 3, 1, 1))
+
+        # registration order follows the reference so that state_dict() enumerates identically
+        self.conv1, self.down1 = stage(channel, f[0]), down(f[0], f[1])
+        self.conv2, self.down2 = stage(f[1], f[1]), down(f[1], f[2])
+        self.conv3, self.down3 = stage(f[2], f[2]), down(f[2], f[3])
+        self.conv4, self.down4 = stage(f[3], f[3]), down(f[3], f[4])
+        self.dconv1 = stage(f[3], f[3])
+        self.dconv2 = stage(f[2], f[2])
+        self.dconv3 = stage(f[1], f[1])
+        self.dconv4 = stage(f[0], f[0])
+        self.pyramidpool = PyramidPool()
+        self.gft = GFT(sum(f), 2, f[4], 12)
+        self.up1, self.up2, self.up3, self.up4 = up(f[4], f[3]), up(f[3], f[2]), up(f[2], f[1]), up(f[1], f[0])
+        self.skip1 = M2Skip([f[2], f[3]], "bottom")
+        self.skip2 = M3Skip([f[1], f[2], f[3]])
+        self.skip3 = M3Skip([f[0], f[1], f[2]])
+        self.skip4 = M2Skip([f[0], f[1]], "top")
+        self.natt1 = NeighborhoodTransformer(f[3])
+        self.natt2 = NeighborhoodTransformer(f[2])
+        self.natt3 = NeighborhoodTransformer(f[1])
+        self.natt4 = NeighborhoodTransformer(f[0])
+        self.output_layer = nn.Conv2d(f[0], n_classes, 1)
+
+    def structural_reparam(self):
+        for m in self.modules():
+            if hasattr(m, "switch_to_deploy"):
+                m.switch_to_deploy()
+
+    def forward(self, x):
+        x1 = self.conv1(x)
+        x2 = self.conv2(self.down1(x1))
+        x3 = self.conv3(self.down2(x2))
+        x4 = self.conv4(self.down3(x3))
+        bottom = self.down4(x4)
+        x5 = self.gft(self.pyramidpool(x1, x2, x3, x4, bottom))
+        s1, s2, s3, s4 = self.skip1(x3, x4), self.skip2(x2, x3, x4), self.skip3(x1, x2, x3), self.skip4(x1, x2)
+        y = self.dconv1(self.up1(x5) + self.natt1(s1))
+        y = self.dconv2(self.up2(y) + self.natt2(s2))
+        y = self.dconv3(self.up3(y) + self.natt3(s3))
+        y = self.dconv4(self.up4(y) + self.natt4(s4))
+        return self.output_layer(y)
+
+
+def count_parameters(model: nn.Module) -> int:
+    return sum(p.numel() for p in model.parameters())
