@@ -61,6 +61,16 @@ const char* lmnet_status_string(int status);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 uint64_t lmnet_launch_count(void);
 
+/* Optional per-kernel profile (used by bench.py for the roofline of the dominant kernel).
+ * While enabled, every launch is bracketed by CUDA events on its own stream and logged with the
+ * ALGORITHMIC bytes of that launch.  collect() synchronises the events and sums, per
+ * kernel id, elapsed milliseconds, launch count and algorithmic bytes into arrays of length
+ * >= lmnet_profile_num_kernels().  enable() clears the log.  Off by default; never on in a timed run. */
+int lmnet_profile_enable(int on);
+int lmnet_profile_num_kernels(void);
+const char* lmnet_profile_kernel_name(int kernel_id);
+int lmnet_profile_collect(double* ms, uint64_t* launches, double* alg_bytes, int n);
+
 /* ---- fused neighbourhood attention -------------------------------------------------
  * Replaces: natten.functional.na2d and the inner sequence of natten's
  * NeighborhoodAttention2D.forward (q*scale -> na2d_qk+rpb -> softmax -> na2d_av),

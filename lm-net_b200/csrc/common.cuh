@@ -16,10 +16,32 @@ constexpr float kLn2 = 0.6931471805599453f;
 extern unsigned long long g_launch_count;
 inline void count_launch(int n = 1) { __atomic_fetch_add(&g_launch_count, (unsigned long long)n, __ATOMIC_RELAXED); }
 
-#define LMNET_CHECK_LAUNCH()                                   \
-    do {                                                       \
-        lmnet::count_launch();                                 \
-        if (cudaGetLastError() != cudaSuccess) return LMNET_ERR_LAUNCH; \
+// Kernel ids for the optional per-kernel profile (lmnet_profile_*; bench.py's roofline leg).
+enum KernelId : int {
+    KID_NA_FWD = 0, KID_NA_BWD_QUERY, KID_NA_BWD_KEY, KID_NA_DRPB_REDUCE,
+    KID_NA_PN, KID_NA_NN, KID_NA_IN, KID_NA_RPBGRAD, KID_NA_RPBGRAD_REDUCE,
+    KID_DW_STATS, KID_DW_FIN_FWD, KID_DW_APPLY, KID_DW_POOL_FIN, KID_DW_COEF_EVAL,
+    KID_DW_BWD_REDUCE, KID_DW_FIN_BWD, KID_DW_BWD_DX, KID_DW_BWD_DW, KID_DW_FIN_DW,
+    KID_COUNT
+};
+extern bool g_profile_on;
+void profile_record(int kid, cudaStream_t st, double alg_bytes, bool begin, void** slot);
+
+// Brackets one kernel launch: counts it and, when profiling is on, records CUDA events around it on
+// the launching stream (algorithmic bytes of the launch are logged next to the events).
+struct LaunchScope {
+    int kid; cudaStream_t st; void* slot = nullptr;
+    LaunchScope(int kid_, cudaStream_t st_, double alg_bytes) : kid(kid_), st(st_) {
+        count_launch();
+        if (g_profile_on) profile_record(kid, st, alg_bytes, true, &slot);
+    }
+    ~LaunchScope() { if (slot != nullptr) profile_record(kid, st, 0.0, false, &slot); }
+};
+
+#define LMNET_LAUNCH(kid, st, alg_bytes, ...)                            \
+    do {                                                                 \
+        { lmnet::LaunchScope _scope((kid), (st), (double)(alg_bytes)); __VA_ARGS__; } \
+        if (cudaGetLastError() != cudaSuccess) return LMNET_ERR_LAUNCH;  \
     } while (0)
 
 // ---------------------------------------------------------------------------------------

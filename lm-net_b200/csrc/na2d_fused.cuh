@@ -471,25 +471,28 @@ static int launch(Op op, const FusedArgs& a) {
     const int R = 2 * g.K - 1;
     const size_t rpb_bytes = (size_t)g.heads * R * R * sizeof(float);
     const unsigned z = (unsigned)(g.B * g.d * g.d);
+    const double n_bytes = (double)g.B * g.H * g.W * g.heads * g.D * sizeof(T);  // one q-sized tensor
     if (op == Op::Fwd) {
         int64_t total = (int64_t)g.Hmax * g.Wmax * NG;
         dim3 grid((unsigned)((total + kThreads - 1) / kThreads), 1, z);
-        na2d_fwd_kernel<T, KT, D, HG><<<grid, kThreads, a.rpb ? rpb_bytes : 0, a.stream>>>(
-            as_v5<const T>(a.q), as_v5<const T>(a.k), as_v5<const T>(a.v), a.rpb, as_v5<T>(a.out), a.lse, g,
-            a.scale * kLog2e);
+        LMNET_LAUNCH(KID_NA_FWD, a.stream, 4 * n_bytes,
+            (na2d_fwd_kernel<T, KT, D, HG><<<grid, kThreads, a.rpb ? rpb_bytes : 0, a.stream>>>(
+                as_v5<const T>(a.q), as_v5<const T>(a.k), as_v5<const T>(a.v), a.rpb, as_v5<T>(a.out), a.lse, g,
+                a.scale * kLog2e)));
     } else if (op == Op::BwdQ) {
         dim3 grid((unsigned)((g.Wmax * NG + kThreads - 1) / kThreads), (unsigned)((g.Hmax + kRowChunk - 1) / kRowChunk), z);
-        na2d_bwd_query_kernel<T, KT, D, HG><<<grid, kThreads, 2 * rpb_bytes, a.stream>>>(
-            as_v5<const T>(a.q), as_v5<const T>(a.k), as_v5<const T>(a.v), as_v5<const T>(a.dout), a.rpb,
-            as_v5<T>(a.dq), a.stats, a.drpb_part, g, a.scale);
+        LMNET_LAUNCH(KID_NA_BWD_QUERY, a.stream, 5 * n_bytes,
+            (na2d_bwd_query_kernel<T, KT, D, HG><<<grid, kThreads, 2 * rpb_bytes, a.stream>>>(
+                as_v5<const T>(a.q), as_v5<const T>(a.k), as_v5<const T>(a.v), as_v5<const T>(a.dout), a.rpb,
+                as_v5<T>(a.dq), a.stats, a.drpb_part, g, a.scale)));
     } else {
         int64_t total = (int64_t)g.Hmax * g.Wmax * NG;
         dim3 grid((unsigned)((total + kThreads - 1) / kThreads), 1, z);
-        na2d_bwd_key_kernel<T, KT, D, HG><<<grid, kThreads, a.rpb ? rpb_bytes : 0, a.stream>>>(
-            as_v5<const T>(a.q), as_v5<const T>(a.k), as_v5<const T>(a.v), as_v5<const T>(a.dout), a.rpb, a.stats,
-            as_v5<T>(a.dk), as_v5<T>(a.dv), g, a.scale);
+        LMNET_LAUNCH(KID_NA_BWD_KEY, a.stream, 2 * n_bytes,
+            (na2d_bwd_key_kernel<T, KT, D, HG><<<grid, kThreads, a.rpb ? rpb_bytes : 0, a.stream>>>(
+                as_v5<const T>(a.q), as_v5<const T>(a.k), as_v5<const T>(a.v), as_v5<const T>(a.dout), a.rpb, a.stats,
+                as_v5<T>(a.dk), as_v5<T>(a.dv), g, a.scale)));
     }
-    LMNET_CHECK_LAUNCH();
     return LMNET_OK;
 }
 

@@ -107,8 +107,8 @@ extern "C" int lmnet_na2d_bwd(const lmnet_view5* q, const lmnet_view5* k, const 
         int64_t gx = ((int64_t)g.Wmax * NG + kThreads - 1) / kThreads;
         int64_t gy = (g.Hmax + kRowChunk - 1) / kRowChunk;
         int64_t n_part = gx * gy * g.B * g.d * g.d;
-        drpb_reduce_kernel<<<g.heads * R * R, 256, 0, a.stream>>>(a.drpb_part, n_part, g.heads * R * R, drpb);
-        LMNET_CHECK_LAUNCH();
+        LMNET_LAUNCH(KID_NA_DRPB_REDUCE, a.stream, 0,
+            (drpb_reduce_kernel<<<g.heads * R * R, 256, 0, a.stream>>>(a.drpb_part, n_part, g.heads * R * R, drpb)));
     }
     return LMNET_OK;
 }

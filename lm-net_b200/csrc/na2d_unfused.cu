@@ -227,25 +227,30 @@ static int ulaunch(UOp op, const UArgs& u) {
     const unsigned gx = (unsigned)(((int64_t)g.Hmax * g.Wmax + kThreads - 1) / kThreads);
     const unsigned z = (unsigned)(g.B * g.d * g.d);
     dim3 grid(gx, (unsigned)g.heads, z);
+    const double n_bytes = (double)g.B * g.H * g.W * g.heads * g.D * sizeof(T);
+    const double a_bytes = (double)g.B * g.H * g.W * g.heads * g.K * g.K * sizeof(T);
     switch (op) {
         case UOp::PN:
-            na2d_pn_kernel<T, KT><<<grid, kThreads, 0, u.stream>>>(cv<T>(u.a), cv<T>(u.b), u.rpb, (T*)u.o_attn, g);
+            LMNET_LAUNCH(KID_NA_PN, u.stream, 2 * n_bytes + a_bytes,
+                (na2d_pn_kernel<T, KT><<<grid, kThreads, 0, u.stream>>>(cv<T>(u.a), cv<T>(u.b), u.rpb, (T*)u.o_attn, g)));
             break;
         case UOp::NN:
-            na2d_nn_kernel<T, KT><<<grid, kThreads, 0, u.stream>>>((const T*)u.w, cv<T>(u.b), mv<T>(u.o), g);
+            LMNET_LAUNCH(KID_NA_NN, u.stream, 2 * n_bytes + a_bytes,
+                (na2d_nn_kernel<T, KT><<<grid, kThreads, 0, u.stream>>>((const T*)u.w, cv<T>(u.b), mv<T>(u.o), g)));
             break;
         case UOp::IN:
-            na2d_in_kernel<T, KT><<<grid, kThreads, 0, u.stream>>>((const T*)u.w, cv<T>(u.a), mv<T>(u.o), g);
+            LMNET_LAUNCH(KID_NA_IN, u.stream, 2 * n_bytes + a_bytes,
+                (na2d_in_kernel<T, KT><<<grid, kThreads, 0, u.stream>>>((const T*)u.w, cv<T>(u.a), mv<T>(u.o), g)));
             break;
         case UOp::RPB: {
             const int R = 2 * g.K - 1;
             dim3 rg((unsigned)((g.Wmax + kThreads - 1) / kThreads), (unsigned)((g.Hmax + kRowChunk - 1) / kRowChunk),
                     z * (unsigned)g.heads);
-            na2d_rpbgrad_kernel<T, KT><<<rg, kThreads, R * R * sizeof(float), u.stream>>>((const T*)u.w, u.part, g);
+            LMNET_LAUNCH(KID_NA_RPBGRAD, u.stream, a_bytes,
+                (na2d_rpbgrad_kernel<T, KT><<<rg, kThreads, R * R * sizeof(float), u.stream>>>((const T*)u.w, u.part, g)));
             break;
         }
     }
-    LMNET_CHECK_LAUNCH();
     return LMNET_OK;
 }
 
@@ -322,8 +327,8 @@ extern "C" int lmnet_na2d_qk_bwd(const lmnet_view5* q, const lmnet_view5* k, con
         rc = udispatch(UOp::RPB, u, dtype);
         if (rc != LMNET_OK) return rc;
         int R = 2 * u.g.K - 1;
-        rpbgrad_reduce_kernel<<<u.g.heads * R * R, 256, 0, u.stream>>>(u.part, rpb_parts_per_head(u.g), R * R, drpb);
-        LMNET_CHECK_LAUNCH();
+        LMNET_LAUNCH(KID_NA_RPBGRAD_REDUCE, u.stream, 0,
+            (rpbgrad_reduce_kernel<<<u.g.heads * R * R, 256, 0, u.stream>>>(u.part, rpb_parts_per_head(u.g), R * R, drpb)));
     }
     return LMNET_OK;
 }

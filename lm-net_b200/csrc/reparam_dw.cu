@@ -739,23 +739,21 @@ static int dw_train_fwd(const void* x, const lmnet_dw_params* p, void* u, void* 
                         const lmnet_dw_dims* d, cudaStream_t st) {
     DwGeom g = dw_geom(d, kFwdTH, kFwdTW);
     DwWs L = dw_ws_layout(d, sizeof(T));
+    const double t_bytes = (double)d->B * d->E * d->H * d->W * sizeof(T);  // one [B,E,H,W] tensor
+    (void)t_bytes;
     const int ncta = g.stripes * g.bands;
     dim3 grid(g.stripes, g.bands, g.E);
     float* part = (float*)(ws + L.part);
     float* coef = (float*)(ws + L.coef);
     float* pool_part = (float*)(ws + L.pool_part);
-    dw_stats_kernel<T><<<grid, kDwThreads, 0, st>>>((const T*)x, *p, part, g);
-    LMNET_CHECK_LAUNCH();
-    dw_fin_fwd_kernel<<<(g.E + 63) / 64, 64, 0, st>>>(part, ncta, *p, save_mean, save_rstd, coef, eps, momentum,
+    LMNET_LAUNCH(KID_DW_STATS, st, 1 * t_bytes, (dw_stats_kernel<T><<<grid, kDwThreads, 0, st>>>((const T*)x, *p, part, g)));
+    LMNET_LAUNCH(KID_DW_FIN_FWD, st, 0, (dw_fin_fwd_kernel<<<(g.E + 63) / 64, 64, 0, st>>>(part, ncta, *p, save_mean, save_rstd, coef, eps, momentum,
                                                      nbt ? nbt[0] : nullptr, nbt ? nbt[1] : nullptr,
-                                                     nbt ? nbt[2] : nullptr, nbt ? nbt[3] : nullptr, g);
-    LMNET_CHECK_LAUNCH();
-    dw_apply_kernel<T><<<grid, kDwThreads, 0, st>>>((const T*)x, coef, (T*)u, (T*)z, pool ? pool_part : nullptr, g);
-    LMNET_CHECK_LAUNCH();
+                                                     nbt ? nbt[2] : nullptr, nbt ? nbt[3] : nullptr, g)));
+    LMNET_LAUNCH(KID_DW_APPLY, st, 2 * t_bytes, (dw_apply_kernel<T><<<grid, kDwThreads, 0, st>>>((const T*)x, coef, (T*)u, (T*)z, pool ? pool_part : nullptr, g)));
     if (pool) {
         const int n = g.B * g.E;
-        dw_pool_fin_kernel<<<(n + 127) / 128, 128, 0, st>>>(pool_part, ncta, 1.f / ((float)g.H * g.W), pool, n);
-        LMNET_CHECK_LAUNCH();
+        LMNET_LAUNCH(KID_DW_POOL_FIN, st, 0, (dw_pool_fin_kernel<<<(n + 127) / 128, 128, 0, st>>>(pool_part, ncta, 1.f / ((float)g.H * g.W), pool, n)));
     }
     return LMNET_OK;
 }
@@ -765,18 +763,17 @@ static int dw_eval_fwd(const void* x, const lmnet_dw_params* p, const float* bia
                        char* ws, const lmnet_dw_dims* d, cudaStream_t st) {
     DwGeom g = dw_geom(d, kFwdTH, kFwdTW);
     DwWs L = dw_ws_layout(d, sizeof(T));
+    const double t_bytes = (double)d->B * d->E * d->H * d->W * sizeof(T);  // one [B,E,H,W] tensor
+    (void)t_bytes;
     const int ncta = g.stripes * g.bands;
     dim3 grid(g.stripes, g.bands, g.E);
     float* coef = (float*)(ws + L.coef);
     float* pool_part = (float*)(ws + L.pool_part);
-    dw_coef_eval_kernel<<<(g.E + 63) / 64, 64, 0, st>>>(*p, bias, eps, coef, g.E);
-    LMNET_CHECK_LAUNCH();
-    dw_apply_kernel<T><<<grid, kDwThreads, 0, st>>>((const T*)x, coef, (T*)nullptr, (T*)z, pool ? pool_part : nullptr, g);
-    LMNET_CHECK_LAUNCH();
+    LMNET_LAUNCH(KID_DW_COEF_EVAL, st, 0, (dw_coef_eval_kernel<<<(g.E + 63) / 64, 64, 0, st>>>(*p, bias, eps, coef, g.E)));
+    LMNET_LAUNCH(KID_DW_APPLY, st, 2 * t_bytes, (dw_apply_kernel<T><<<grid, kDwThreads, 0, st>>>((const T*)x, coef, (T*)nullptr, (T*)z, pool ? pool_part : nullptr, g)));
     if (pool) {
         const int n = g.B * g.E;
-        dw_pool_fin_kernel<<<(n + 127) / 128, 128, 0, st>>>(pool_part, ncta, 1.f / ((float)g.H * g.W), pool, n);
-        LMNET_CHECK_LAUNCH();
+        LMNET_LAUNCH(KID_DW_POOL_FIN, st, 0, (dw_pool_fin_kernel<<<(n + 127) / 128, 128, 0, st>>>(pool_part, ncta, 1.f / ((float)g.H * g.W), pool, n)));
     }
     return LMNET_OK;
 }
@@ -789,16 +786,16 @@ static int dw_train_bwd(const void* x, const void* u, const void* dz, const floa
                         const lmnet_dw_dims* d, cudaStream_t st) {
     DwGeom g = dw_geom(d, kFwdTH, kFwdTW);
     DwWs L = dw_ws_layout(d, sizeof(T));
+    const double t_bytes = (double)d->B * d->E * d->H * d->W * sizeof(T);  // one [B,E,H,W] tensor
+    (void)t_bytes;
     const int ncta = g.stripes * g.bands;
     dim3 grid(g.stripes, g.bands, g.E);
     float* part = (float*)(ws + L.part);
     float* pfin = (float*)(ws + L.pfin);
     float* cb = (float*)(ws + L.cb);
     T* du = (T*)(ws + L.du);
-    dw_bwd_reduce_kernel<T><<<grid, kDwThreads, 0, st>>>((const T*)x, (const T*)u, (const T*)dz, dpool, du, part, g);
-    LMNET_CHECK_LAUNCH();
-    dw_fin_bwd_kernel<<<(g.E + 63) / 64, 64, 0, st>>>(part, ncta, *p, save_mean, save_rstd, *gr, pfin, cb, g);
-    LMNET_CHECK_LAUNCH();
+    LMNET_LAUNCH(KID_DW_BWD_REDUCE, st, 2 * t_bytes, (dw_bwd_reduce_kernel<T><<<grid, kDwThreads, 0, st>>>((const T*)x, (const T*)u, (const T*)dz, dpool, du, part, g)));
+    LMNET_LAUNCH(KID_DW_FIN_BWD, st, 0, (dw_fin_bwd_kernel<<<(g.E + 63) / 64, 64, 0, st>>>(part, ncta, *p, save_mean, save_rstd, *gr, pfin, cb, g)));
     {
         DwGeom ga = dw_geom(d, kA1TH, kA1TW);
         static bool attr_set = false;  // benign race: the attribute is idempotent
@@ -808,13 +805,10 @@ static int dw_train_bwd(const void* x, const void* u, const void* dz, const floa
             attr_set = true;
         }
         dim3 ga_grid(ga.stripes, ga.bands, ga.E);
-        dw_bwd_dx_kernel<T><<<ga_grid, kDwThreads, kA1SmemBytes, st>>>((const T*)x, du, *p, cb, (T*)dx, ga);
-        LMNET_CHECK_LAUNCH();
+        LMNET_LAUNCH(KID_DW_BWD_DX, st, 3 * t_bytes, (dw_bwd_dx_kernel<T><<<ga_grid, kDwThreads, kA1SmemBytes, st>>>((const T*)x, du, *p, cb, (T*)dx, ga)));
     }
-    dw_bwd_dw_kernel<T><<<grid, kDwThreads, 0, st>>>((const T*)x, *p, cb, part, g);
-    LMNET_CHECK_LAUNCH();
-    dw_fin_dw_kernel<<<g.E, 64, 0, st>>>(part, ncta, pfin, cb, *gr, g.E);
-    LMNET_CHECK_LAUNCH();
+    LMNET_LAUNCH(KID_DW_BWD_DW, st, 0, (dw_bwd_dw_kernel<T><<<grid, kDwThreads, 0, st>>>((const T*)x, *p, cb, part, g)));
+    LMNET_LAUNCH(KID_DW_FIN_DW, st, 0, (dw_fin_dw_kernel<<<g.E, 64, 0, st>>>(part, ncta, pfin, cb, *gr, g.E)));
     return LMNET_OK;
 }
 

@@ -82,8 +82,28 @@ def lib():
                                              pg, c_void_p, c_size_t, pdd, c_int, c_void_p]
     L.lmnet_reparam_dw_eval_fwd.argtypes = [c_void_p, pp, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_size_t,
                                             pdd, c_int, c_void_p]
+    L.lmnet_profile_enable.argtypes = [c_int]
+    L.lmnet_profile_kernel_name.restype = ctypes.c_char_p
+    L.lmnet_profile_kernel_name.argtypes = [c_int]
+    L.lmnet_profile_collect.argtypes = [POINTER(ctypes.c_double), POINTER(c_uint64), POINTER(ctypes.c_double), c_int]
     _lib = L
     return L
+
+
+def profile_enable(on: bool) -> None:
+    check(lib().lmnet_profile_enable(1 if on else 0), "profile_enable")
+
+
+def profile_collect() -> dict:
+    """{kernel name: {"ms": total ms, "launches": n, "alg_bytes": total algorithmic bytes}} since enable()."""
+    n = lib().lmnet_profile_num_kernels()
+    ms, cnt, by = (ctypes.c_double * n)(), (c_uint64 * n)(), (ctypes.c_double * n)()
+    check(lib().lmnet_profile_collect(ms, cnt, by, n), "profile_collect")
+    out = {}
+    for i in range(n):
+        if cnt[i]:
+            out[lib().lmnet_profile_kernel_name(i).decode()] = {"ms": ms[i], "launches": int(cnt[i]), "alg_bytes": by[i]}
+    return out
 
 
 def launch_count() -> int:

@@ -1,0 +1,135 @@
+"""Training-loop pieces that mirror the reference's driver for the benchmark harness.
+
+* ``DiceLoss``         — same arithmetic as utils/loss.py:170-206 (softmax, one-hot, per-class soft Dice
+                         with smooth=1e-5, class weights, mean over classes) minus its ``.item()`` host syncs.
+* ``build_training``   — optimiser / criteria exactly as train.py:156-160 (AdamW lr 1e-3 wd 1e-4,
+                         CE(weight [1,4], label_smoothing 1e-3), DiceLoss(2)).
+* ``train_one_epoch``  — same signature and step order as utils/train_eval_utils.py:120-166
+                         (H2D copy, autocast forward, CE + Dice(weight [1,4]), zero_grad, backward, step,
+                         loss.item(), argmax -> CPU metric update), with bf16 autocast instead of the
+                         reference's fp16 + GradScaler (BASELINE.json configs[1]).
+* ``synthetic_batches``— Kvasir-SEG-shaped synthetic data: N(0,1) RGB images and one
+                         filled ellipse per mask covering 5-40 % of the area.
+* ``ConfusionMetrics`` — duck-typed stand-in for the torchmetrics collection (reset/update/compute/to).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+
+class DiceLoss(nn.Module):
+    def __init__(self, n_classes: int):
+        super().__init__()
+        self.n_classes = n_classes
+
+    def forward(self, inputs, target, weight=None, softmax=True):
+        if softmax:
+            inputs = torch.softmax(inputs, dim=1)
+        onehot = torch.cat([(target == c) for c in range(self.n_classes)], dim=1).float()
+        if inputs.shape != onehot.shape:
+            raise ValueError("predict & target shape do not match")
+        weight = [1.0] * self.n_classes if weight is None else weight
+        loss = 0.0
+        for c in range(self.n_classes):
+            score, tgt = inputs[:, c], onehot[:, c]
+            inter = (score * tgt).sum()
+            dice = (2 * inter + 1e-5) / ((score * score).sum() + (tgt * tgt).sum() + 1e-5)
+            loss = loss + (1 - dice) * weight[c]
+        return loss / self.n_classes
+
+
+def build_training(model: nn.Module, device, lr=1e-3, weight_decay=1e-4, smoothing=1e-3, fused=None):
+    dev = torch.device(device)
+    fused = (dev.type == "cuda") if fused is None else fused
+    optimizer = torch.optim.AdamW(model.parameters(), lr=lr, weight_decay=weight_decay, fused=fused)
+    criterion = nn.CrossEntropyLoss(weight=torch.tensor([1.0, 4.0], device=dev), label_smoothing=smoothing)
+    criterion_dice = DiceLoss(2).to(dev)
+    return optimizer, criterion, criterion_dice
+
+
+def loss_fn(output, labels, criterion, criterion_dice):
+    return criterion(output, labels) + criterion_dice(output, labels.unsqueeze(1).float(), weight=[1.0, 4.0])
+
+
+def train_step(model, optimizer, images, labels, criterion, criterion_dice, amp_dtype=torch.bfloat16):
+    """forward + loss + backward + optimiser step on device-resident tensors; returns the loss tensor."""
+    dev_type = images.device.type
+    with torch.autocast(dev_type, dtype=amp_dtype, enabled=amp_dtype is not None):
+        output = model(images)
+        loss = loss_fn(output, labels, criterion, criterion_dice)
+    optimizer.zero_grad(set_to_none=True)
+    loss.backward()
+    optimizer.step()
+    return loss, output
+
+
+class ConfusionMetrics:
+    """Accumulates a 2x2 confusion matrix on the CPU; compute() returns accuracy / Dice / IoU of class 1."""
+
+    def __init__(self, num_classes=2):
+        self.n = num_classes
+        self.reset()
+
+    def to(self, _device):
+        return self
+
+    def reset(self):
+        self.cm = torch.zeros(self.n * self.n, dtype=torch.int64)
+
+    def update(self, pred, labels):
+        self.cm += torch.bincount((labels.reshape(-1) * self.n + pred.reshape(-1)), minlength=self.n * self.n)
+
+    def compute(self):
+        cm = self.cm.view(self.n, self.n).double()
+        tp, fp, fn = cm[1, 1], cm[0, 1], cm[1, 0]
+        return {"acc": float(cm.diag().sum() / cm.sum().clamp_min(1)),
+                "dice": float(2 * tp / (2 * tp + fp + fn).clamp_min(1)),
+                "iou": float(tp / (tp + fp + fn).clamp_min(1))}
+
+
+def train_one_epoch(model, optimizer, metric_collection=None, num_classes=2, data_loader=None, device=0,
+                    criterion=None, scaler=None, criterion_dice=None, amp_dtype=torch.bfloat16):
+    """Reference-shaped epoch loop.  `scaler` is accepted for signature compatibility; a non-None value
+    selects the autocast branch exactly as in the reference, but with bf16 no loss scaling is needed."""
+    model.train()
+    if metric_collection is not None:
+        metric_collection.reset()
+    total_loss = 0.0
+    use_amp = scaler is not None
+    for images, labels in data_loader:
+        images = images.to(device, non_blocking=True)
+        labels = labels.to(device, non_blocking=True)
+        loss, output = train_step(model, optimizer, images, labels, criterion, criterion_dice,
+                                  amp_dtype if use_amp else None)
+        with torch.no_grad():
+            total_loss += loss.item()
+            if metric_collection is not None:
+                pred = output.argmax(1).detach().cpu()
+                metric_collection.update(pred, labels.detach().cpu())
+    return total_loss
+
+
+def synthetic_batches(n_batches, batch, res, seed=0, pin=True):
+    """List of (images fp32 [B,3,R,R], masks int64 [B,R,R]) host tensors, optionally pinned."""
+    g = torch.Generator().manual_seed(seed)
+    yy, xx = torch.meshgrid(torch.arange(res, dtype=torch.float32), torch.arange(res, dtype=torch.float32), indexing="ij")
+    out = []
+    for _ in range(n_batches):
+        images = torch.randn(batch, 3, res, res, generator=g)
+        masks = torch.empty(batch, res, res, dtype=torch.int64)
+        for b in range(batch):
+            frac = 0.05 + 0.35 * float(torch.rand(1, generator=g))
+            aspect = 0.6 + 0.8 * float(torch.rand(1, generator=g))
+            ry = math.sqrt(frac * res * res / math.pi * aspect)
+            rx = frac * res * res / math.pi / ry
+            cy = ry + float(torch.rand(1, generator=g)) * max(1.0, res - 2 * ry)
+            cx = rx + float(torch.rand(1, generator=g)) * max(1.0, res - 2 * rx)
+            masks[b] = ((((yy - cy) / ry) ** 2 + ((xx - cx) / rx) ** 2) <= 1.0).long()
+        if pin and torch.cuda.is_available():
+            images, masks = images.pin_memory(), masks.pin_memory()
+        out.append((images, masks))
+    return out

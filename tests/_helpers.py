@@ -76,5 +76,5 @@ def import_reference():
 
 def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
     """max |a-b| / max |b| — the relative error norm used for the parity tolerances."""
-    a, b = a.double(), b.double()
+    a, b = a.detach().double(), b.detach().double()
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
