@@ -69,9 +69,21 @@ SHAPES = [
 ]
 
 
+def _run_block(blk, x, go, dtype, forward):
+    xc = x.cuda().requires_grad_()
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=dtype == torch.bfloat16):
+        y = forward(blk, xc)
+    y.backward(go.cuda().to(y.dtype))
+    return y, xc
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "x".join(map(str, s)))
 def test_train_forward_backward_vs_oracle(shape, dtype):
+    """Whole block, training mode.  fp32: within 1e-4 of the fp64 oracle.  bf16 autocast: the block also
+    contains stock cuDNN/ATen bf16 ops (1x1 convs, BatchNorm, Hardswish) whose own rounding dominates,
+    so the bound is "no worse than the stock bf16 path": err(ours vs fp64) <= max(2e-2, 1.5 x err(stock
+    torch bf16 on the same GPU vs fp64)).  The fused op alone is held to 2e-2 in test_raw_op_outputs_and_pool."""
     from oracle.reparam_ref import reparam_forward_ref
 
     B, cin, e, cout, H, W = shape
@@ -85,21 +97,27 @@ def test_train_forward_backward_vs_oracle(shape, dtype):
     yr = reparam_forward_ref(ref, xr)
     yr.backward(go.double())
 
+    stock = copy.deepcopy(blk).cuda().train()
     blk = blk.cuda().train()
-    xc = x.cuda().requires_grad_()
-    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=dtype == torch.bfloat16):
-        y = blk(xc)
-    y.backward(go.cuda().to(y.dtype))
+    y, xc = _run_block(blk, x, go, dtype, lambda m, t: m(t))
     tol = TOL[dtype]
-    assert rel_err(y.float().cpu(), yr) < tol
-    assert rel_err(xc.grad.cpu(), xr.grad) < tol * 2
+
+    def bound(name, got, want, mult):
+        if dtype == torch.float32:
+            return tol * mult
+        return max(tol * mult, 1.5 * rel_err(got, want) + 1e-3)
+
+    ys, xs = _run_block(stock, x, go, dtype, reparam_forward_ref)
+    assert rel_err(y.float().cpu(), yr) < bound("y", ys.float().cpu(), yr, 1)
+    assert rel_err(xc.grad.cpu(), xr.grad) < bound("dx", xs.grad.cpu(), xr.grad, 2)
+    stock_params = dict(stock.named_parameters())
     for (n, p), (_, pr) in zip(blk.named_parameters(), ref.named_parameters()):
         scale = float(pr.grad.abs().max())
         if scale < 1e-12:          # e.g. biases in front of a BatchNorm have exactly zero gradient
             # exact cancellation in exact arithmetic; rounding noise grows like sqrt(#pixels)
             assert float(p.grad.abs().max()) < tol * (B * H * W) ** 0.5, n
             continue
-        assert rel_err(p.grad.cpu(), pr.grad) < tol * 3, n
+        assert rel_err(p.grad.cpu(), pr.grad) < bound(n, stock_params[n].grad.cpu(), pr.grad, 3), n
     for (n, b), (_, br) in zip(blk.named_buffers(), ref.named_buffers()):
         if n.endswith("num_batches_tracked"):
             assert int(b) == int(br) == 1, n
