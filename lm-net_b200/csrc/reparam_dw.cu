@@ -21,6 +21,8 @@
 // every (col, col+1) pair is an aligned 64-bit shared load.  A CTA owns one channel, one column
 // stripe and one band of rows, and loops over the batch, so per-channel reductions need no atomics:
 // per-CTA partials are reduced by the finalize kernels in a fixed order (deterministic).
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace lmnet {
@@ -47,49 +49,137 @@ __device__ __forceinline__ f2 ld2(const float* p) {
 
 constexpr int kDwThreads = 128;
 constexpr int kDwWarps = 4;
-constexpr int kPitch = 72;  // floats per shared-memory tile row (64 + up to 8 halo columns)
+constexpr int kPad = 8;                  // halo columns staged on each side (>= 4, multiple of the vector width)
+constexpr int kPitch = 64 + 2 * kPad;    // floats per shared-memory tile row
 
 struct DwGeom {
     int B, E, H, W;
     int stripes, bands, rows_per_band;  // CTA grid = (stripes, bands, E)
 };
 
-// Stage a tile of one plane into shared memory as floats: sA[r][i] = x(r0+r, c0+i) (0 outside the
-// image), sB[r][i] = sA[r][i+1].
-template <typename T>
-__device__ __forceinline__ void load_tile(const T* __restrict__ plane, int H, int W, int r0, int c0, int rows,
-                                          float* sA, float* sB) {
-    for (int idx = threadIdx.x; idx < rows * kPitch; idx += kDwThreads) {
-        const int r = idx / kPitch, i = idx - r * kPitch;
-        const int gr = r0 + r, gc = c0 + i;
-        float v = 0.f;
-        if (gr >= 0 && gr < H && gc >= 0 && gc < W) v = to_f(plane[(int64_t)gr * W + gc]);
-        sA[idx] = v;
-        if (i > 0) sB[idx - 1] = v;
+// Stages ROWS x kPitch elements of one plane into shared memory as floats:
+//   sA[r][i] = x(r0 + r, c0 + i)  (0 outside the image).
+// Split in two halves so that the global loads of tile t+1 are in flight while tile t is computed:
+// fetch() issues all (vectorised, VEC <= 4 elements) loads into registers, commit() converts and
+// writes one VEC-float vector per lane (consecutive lanes -> consecutive vectors: conflict-free).
+// VEC > 1 requires W % VEC == 0, c0 % VEC == 0 and a plane pointer aligned to VEC elements.
+template <typename T, int VEC, int ROWS>
+struct TileLoader {
+    static constexpr int NV = kPitch / VEC;                                  // vectors per row
+    static constexpr int N = (ROWS * NV + kDwThreads - 1) / kDwThreads;      // vectors per thread
+    using V = typename VecOf<VEC * (int)sizeof(T)>::type;
+    V raw[N];
+
+    __device__ __forceinline__ void fetch(const T* __restrict__ plane, int H, int W, int r0, int c0) {
+#pragma unroll
+        for (int u = 0; u < N; ++u) {
+            const int idx = threadIdx.x + u * kDwThreads;
+            const int r = idx / NV, v = idx - r * NV;
+            const int gr = r0 + r, gc = c0 + v * VEC;
+            V val{};
+            if (idx < ROWS * NV && gr >= 0 && gr < H && gc >= 0 && gc + VEC <= W)
+                val = __ldg(reinterpret_cast<const V*>(plane + (int64_t)gr * W + gc));
+            raw[u] = val;
+        }
+    }
+    __device__ __forceinline__ void commit(float* sA) const {
+#pragma unroll
+        for (int u = 0; u < N; ++u) {
+            const int idx = threadIdx.x + u * kDwThreads;
+            if (idx < ROWS * NV) {
+                const T* e = reinterpret_cast<const T*>(&raw[u]);
+                float f[VEC];
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) f[j] = to_f(e[j]);
+                using FV = typename VecOf<VEC * 4>::type;
+                *reinterpret_cast<FV*>(sA + idx * VEC) = *reinterpret_cast<const FV*>(f);   // idx*VEC == r*kPitch + v*VEC
+            }
+        }
+    }
+};
+
+// Same idea for an un-haloed ROWS x 64 tile kept in its storage type (u, dz, du): element (r, c) of the
+// tile lands at s[r * kRawPitch + c + shift].  Out-of-image elements are zero.
+constexpr int kRawPitch = 72;
+template <typename T, int VEC, int ROWS>
+struct RawTileLoader {
+    static constexpr int NV = 64 / VEC;
+    static constexpr int N = (ROWS * NV + kDwThreads - 1) / kDwThreads;
+    using V = typename VecOf<VEC * (int)sizeof(T)>::type;
+    V raw[N];
+    __device__ __forceinline__ void fetch(const T* __restrict__ plane, int H, int W, int r0, int c0) {
+#pragma unroll
+        for (int u = 0; u < N; ++u) {
+            const int idx = threadIdx.x + u * kDwThreads;
+            const int r = idx / NV, v = idx - r * NV;
+            const int gr = r0 + r, gc = c0 + v * VEC;
+            V val{};
+            if (idx < ROWS * NV && gr >= 0 && gr < H && gc >= 0 && gc + VEC <= W)
+                val = __ldg(reinterpret_cast<const V*>(plane + (int64_t)gr * W + gc));
+            raw[u] = val;
+        }
+    }
+    __device__ __forceinline__ void commit(T* s) const {
+#pragma unroll
+        for (int u = 0; u < N; ++u) {
+            const int idx = threadIdx.x + u * kDwThreads;
+            if (idx < ROWS * NV) {
+                const int r = idx / NV, v = idx - r * NV;
+                *reinterpret_cast<V*>(s + r * kRawPitch + v * VEC) = raw[u];
+            }
+        }
+    }
+};
+
+// Runs body(b, tr, last_tile_of_b) over every (batch item, row tile) of this CTA's band, with the
+// next tile's global loads prefetched into registers while the current tile is being computed.
+// The staged x tile starts `halo` rows above tr and kPad columns left of the stripe origin c0.
+// `extra` is an object with fetch(b, tr) / commit() for further operands staged the same way.
+struct NoExtra {
+    __device__ __forceinline__ void fetch(int, int) {}
+    __device__ __forceinline__ void commit() {}
+};
+template <typename T, int VEC, int ROWS, typename PlaneFn, typename Extra, typename Body>
+__device__ __forceinline__ void for_each_tile(const DwGeom& g, int band0, int band1, int th, int halo, int c0,
+                                              float* sA, PlaneFn&& plane_of, Extra&& extra, Body&& body) {
+    const int ntr = (band1 - band0 + th - 1) / th;
+    const int total = band1 > band0 ? g.B * ntr : 0;
+    TileLoader<T, VEC, ROWS> ld;
+    if (total > 0) {
+        ld.fetch(plane_of(0), g.H, g.W, band0 - halo, c0 - kPad);
+        extra.fetch(0, band0);
+    }
+    for (int t = 0; t < total; ++t) {
+        const int b = t / ntr, k = t - b * ntr;
+        __syncthreads();
+        ld.commit(sA);
+        extra.commit();
+        __syncthreads();
+        if (t + 1 < total) {
+            const int nb = (t + 1) / ntr, nk = (t + 1) - nb * ntr;
+            ld.fetch(plane_of(nb), g.H, g.W, band0 + nk * th - halo, c0 - kPad);
+            extra.fetch(nb, band0 + nk * th);
+        }
+        body(b, band0 + k * th, k == ntr - 1);
     }
 }
 
 // 5x5 window walk.  The thread owns output columns (2*lane, 2*lane+1) of the tile and RT consecutive
 // rows starting at tile row `row0`; shared row `row0 + o + a`, pair offset b holds the inputs for
-// tap (a, b) of output row o.  fn(o, win) is called once per output row with win[a][b] in registers.
+// tap (a, b) of output row o.  Three aligned 64-bit shared loads fetch the six inputs of a row; the
+// two odd-aligned pairs are assembled in registers.  fn(o, win) is called once per output row.
+__device__ __forceinline__ void load_row5(const float* p, f2 (&dst)[5]) {
+    const f2 a0 = ld2(p), a1 = ld2(p + 2), a2 = ld2(p + 4);
+    dst[0] = a0; dst[1] = mk2(a0.y, a1.x); dst[2] = a1; dst[3] = mk2(a1.y, a2.x); dst[4] = a2;
+}
 template <int RT, typename Fn>
-__device__ __forceinline__ void walk5(const float* sA, const float* sB, int row0, int col0, Fn&& fn) {
+__device__ __forceinline__ void walk5(const float* sA, int row0, int col0, Fn&& fn, int pitch = kPitch) {
     f2 rows[5][5];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        const float* a = sA + (row0 + r) * kPitch + col0;
-        const float* b = sB + (row0 + r) * kPitch + col0;
-        rows[r][0] = ld2(a); rows[r][1] = ld2(b); rows[r][2] = ld2(a + 2); rows[r][3] = ld2(b + 2); rows[r][4] = ld2(a + 4);
-    }
+    for (int r = 0; r < 4; ++r) load_row5(sA + (row0 + r) * pitch + col0, rows[r]);
 #pragma unroll
     for (int o = 0; o < RT; ++o) {
-        {
-            const int r = o + 4;
-            const float* a = sA + (row0 + r) * kPitch + col0;
-            const float* b = sB + (row0 + r) * kPitch + col0;
-            f2(&dst)[5] = rows[r % 5];
-            dst[0] = ld2(a); dst[1] = ld2(b); dst[2] = ld2(a + 2); dst[3] = ld2(b + 2); dst[4] = ld2(a + 4);
-        }
+        load_row5(sA + (row0 + o + 4) * pitch + col0, rows[(o + 4) % 5]);
         f2 win[5][5];
 #pragma unroll
         for (int a = 0; a < 5; ++a)
@@ -102,24 +192,18 @@ __device__ __forceinline__ void walk5(const float* sA, const float* sB, int row0
 // 3x3 window walk over the centre of the same geometry: win[a][b] = input at (row o+a-1, col +b-1)
 // relative to the output pixel; `row0` is the tile row of the first output row MINUS 1 and col0 the
 // same even column index as walk5 uses (the 3-wide window starts at col0+1).
+__device__ __forceinline__ void load_row3(const float* p, f2 (&dst)[3]) {
+    const f2 a0 = ld2(p), a1 = ld2(p + 2), a2 = ld2(p + 4);
+    dst[0] = mk2(a0.y, a1.x); dst[1] = a1; dst[2] = mk2(a1.y, a2.x);
+}
 template <int RT, typename Fn>
-__device__ __forceinline__ void walk3(const float* sA, const float* sB, int row0, int col0, Fn&& fn) {
+__device__ __forceinline__ void walk3(const float* sA, int row0, int col0, Fn&& fn, int pitch = kPitch) {
     f2 rows[3][3];
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
-        const float* a = sA + (row0 + r) * kPitch + col0;
-        const float* b = sB + (row0 + r) * kPitch + col0;
-        rows[r][0] = ld2(b); rows[r][1] = ld2(a + 2); rows[r][2] = ld2(b + 2);
-    }
+    for (int r = 0; r < 2; ++r) load_row3(sA + (row0 + r) * pitch + col0, rows[r]);
 #pragma unroll
     for (int o = 0; o < RT; ++o) {
-        {
-            const int r = o + 2;
-            const float* a = sA + (row0 + r) * kPitch + col0;
-            const float* b = sB + (row0 + r) * kPitch + col0;
-            f2(&dst)[3] = rows[r % 3];
-            dst[0] = ld2(b); dst[1] = ld2(a + 2); dst[2] = ld2(b + 2);
-        }
+        load_row3(sA + (row0 + o + 2) * pitch + col0, rows[(o + 2) % 3]);
         f2 win[3][3];
 #pragma unroll
         for (int a = 0; a < 3; ++a)
@@ -199,6 +283,24 @@ __device__ __forceinline__ f2 load_pair(const T* __restrict__ p, bool v0, bool v
     }
     return f2{v0 ? to_f(p[0]) : 0.f, v1 ? to_f(p[1]) : 0.f};
 }
+// packed (unconverted) pair: keeps prefetched operands at one register per bf16/fp16 pair
+template <typename T> struct RawPair { using type = uint32_t; };
+template <> struct RawPair<float> { using type = float2; };
+template <typename T>
+__device__ __forceinline__ typename RawPair<T>::type load_pair_raw(const T* __restrict__ p, bool v0, bool v1, bool vec) {
+    typename RawPair<T>::type raw{};
+    if (vec && v1) return *reinterpret_cast<const typename RawPair<T>::type*>(p);
+    T* e = reinterpret_cast<T*>(&raw);
+    if (v0) e[0] = p[0];
+    if (v1) e[1] = p[1];
+    return raw;
+}
+template <typename T>
+__device__ __forceinline__ f2 cvt_pair(const typename RawPair<T>::type& raw) {
+    const T* e = reinterpret_cast<const T*>(&raw);
+    return f2{to_f(e[0]), to_f(e[1])};
+}
+
 template <typename T>
 __device__ __forceinline__ void store_pair(T* __restrict__ p, f2 v, bool v0, bool v1, bool vec) {
     if (vec && v1) {
@@ -225,11 +327,10 @@ constexpr int kFwdTH = kFwdRT * kDwWarps;       // 32 output rows per tile
 constexpr int kFwdTW = 64;                      // output columns per tile
 constexpr int kFwdTileRows = kFwdTH + 4;
 
-template <typename T>
+template <typename T, int VEC>
 __global__ void __launch_bounds__(kDwThreads)
 dw_stats_kernel(const T* __restrict__ x, lmnet_dw_params p, float* __restrict__ part /* [E][ncta][8] */, DwGeom g) {
     __shared__ __align__(16) float sA[kFwdTileRows * kPitch];
-    __shared__ __align__(16) float sB[kFwdTileRows * kPitch];
     __shared__ float s_red[kDwWarps * 8];
     const int e = blockIdx.z, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int c0 = blockIdx.x * kFwdTW;
@@ -241,13 +342,11 @@ dw_stats_kernel(const T* __restrict__ x, lmnet_dw_params p, float* __restrict__ 
     for (int k = 0; k < 4; ++k) s[k] = ss[k] = mk2(0.f, 0.f);
     const int col = c0 + 2 * lane;
     const f2 cmask = mk2(col < g.W ? 1.f : 0.f, col + 1 < g.W ? 1.f : 0.f);
-    for (int b = 0; b < g.B; ++b) {
-        const T* plane = x + ((int64_t)b * g.E + e) * g.H * g.W;
-        for (int tr = band0; tr < band1; tr += kFwdTH) {
-            __syncthreads();
-            load_tile(plane, g.H, g.W, tr - 2, c0 - 2, kFwdTileRows, sA, sB);
-            __syncthreads();
-            walk5<kFwdRT>(sA, sB, warp * kFwdRT, 2 * lane, [&](int o, const f2(&win)[5][5]) {
+    for_each_tile<T, VEC, kFwdTileRows>(
+        g, band0, band1, kFwdTH, 2, c0, sA,
+        [&](int b) { return x + ((int64_t)b * g.E + e) * g.H * g.W; }, NoExtra{},
+        [&](int, int tr, bool) {
+            walk5<kFwdRT>(sA, warp * kFwdRT, 2 * lane + kPad - 2, [&](int o, const f2(&win)[5][5]) {
                 const int row = tr + warp * kFwdRT + o;
                 f2 y[4];
                 branches_from_window(win, w, y);
@@ -255,13 +354,11 @@ dw_stats_kernel(const T* __restrict__ x, lmnet_dw_params p, float* __restrict__ 
                 const f2 m = mk2(cmask.x * rm, cmask.y * rm);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const f2 ym = mk2(y[k].x * m.x, y[k].y * m.y);
-                    s[k].x += ym.x; s[k].y += ym.y;
-                    ss[k] = ffma2(ym, y[k], ss[k]);
+                    s[k] = ffma2(y[k], m, s[k]);
+                    ss[k] = ffma2(mk2(y[k].x * m.x, y[k].y * m.y), y[k], ss[k]);
                 }
             });
-        }
-    }
+        });
     float v[8];
 #pragma unroll
     for (int k = 0; k < 4; ++k) { v[k] = s[k].x + s[k].y; v[4 + k] = ss[k].x + ss[k].y; }
@@ -343,12 +440,11 @@ __global__ void dw_coef_eval_kernel(lmnet_dw_params p, const float* __restrict__
 // =================================================================================================
 // forward: apply pass  u = merged5x5(x) + bias;  z = GELU(u);  pool partial sums
 // =================================================================================================
-template <typename T>
+template <typename T, int VEC>
 __global__ void __launch_bounds__(kDwThreads)
 dw_apply_kernel(const T* __restrict__ x, const float* __restrict__ coef, T* __restrict__ u_out, T* __restrict__ z_out,
                 float* __restrict__ pool_part /* [B*E][ncta] or null */, DwGeom g) {
     __shared__ __align__(16) float sA[kFwdTileRows * kPitch];
-    __shared__ __align__(16) float sB[kFwdTileRows * kPitch];
     __shared__ float s_red[kDwWarps];
     const int e = blockIdx.z, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int c0 = blockIdx.x * kFwdTW;
@@ -361,15 +457,13 @@ dw_apply_kernel(const T* __restrict__ x, const float* __restrict__ coef, T* __re
     const bool v0 = col < g.W, v1 = col + 1 < g.W;
     const bool vec = (g.W & 1) == 0;
     const int ncta = gridDim.x * gridDim.y, cta = blockIdx.y * gridDim.x + blockIdx.x;
-    for (int b = 0; b < g.B; ++b) {
-        const int64_t poff = ((int64_t)b * g.E + e) * g.H * g.W;
-        const T* plane = x + poff;
-        float psum = 0.f;
-        for (int tr = band0; tr < band1; tr += kFwdTH) {
-            __syncthreads();
-            load_tile(plane, g.H, g.W, tr - 2, c0 - 2, kFwdTileRows, sA, sB);
-            __syncthreads();
-            walk5<kFwdRT>(sA, sB, warp * kFwdRT, 2 * lane, [&](int o, const f2(&win)[5][5]) {
+    float psum = 0.f;
+    for_each_tile<T, VEC, kFwdTileRows>(
+        g, band0, band1, kFwdTH, 2, c0, sA,
+        [&](int b) { return x + ((int64_t)b * g.E + e) * g.H * g.W; }, NoExtra{},
+        [&](int b, int tr, bool last) {
+            const int64_t poff = ((int64_t)b * g.E + e) * g.H * g.W;
+            walk5<kFwdRT>(sA, warp * kFwdRT, 2 * lane + kPad - 2, [&](int o, const f2(&win)[5][5]) {
                 const int row = tr + warp * kFwdRT + o;
                 f2 acc = mk2(bias, bias);
 #pragma unroll
@@ -386,16 +480,16 @@ dw_apply_kernel(const T* __restrict__ x, const float* __restrict__ coef, T* __re
                     psum += to_f(from_f<T>(z.x)) + (v1 ? to_f(from_f<T>(z.y)) : 0.f);
                 }
             });
-        }
-        if (pool_part != nullptr) {
-            psum = warp_sum(psum);
-            __syncthreads();
-            if (lane == 0) s_red[warp] = psum;
-            __syncthreads();
-            if (threadIdx.x == 0)
-                pool_part[((int64_t)b * g.E + e) * ncta + cta] = s_red[0] + s_red[1] + s_red[2] + s_red[3];
-        }
-    }
+            if (last && pool_part != nullptr) {   // uniform across the CTA
+                float t = warp_sum(psum);
+                psum = 0.f;
+                __syncthreads();
+                if (lane == 0) s_red[warp] = t;
+                __syncthreads();
+                if (threadIdx.x == 0)
+                    pool_part[((int64_t)b * g.E + e) * ncta + cta] = s_red[0] + s_red[1] + s_red[2] + s_red[3];
+            }
+        });
 }
 
 __global__ void dw_pool_fin_kernel(const float* __restrict__ pool_part, int ncta, float inv_hw, float* __restrict__ pool, int n) {
@@ -409,13 +503,14 @@ __global__ void dw_pool_fin_kernel(const float* __restrict__ pool_part, int ncta
 // =================================================================================================
 // backward R pass: du = (dz + dpool/HW) * gelu'(u);  P[t] = sum_p du(p) x(p+t) (25 lags);  sum du
 // =================================================================================================
-template <typename T>
+template <typename T, int VEC>
 __global__ void __launch_bounds__(kDwThreads)
 dw_bwd_reduce_kernel(const T* __restrict__ x, const T* __restrict__ u, const T* __restrict__ dz,
                      const float* __restrict__ dpool, T* __restrict__ du_out, float* __restrict__ part /* [E][ncta][26] */,
                      DwGeom g) {
     __shared__ __align__(16) float sA[kFwdTileRows * kPitch];
-    __shared__ __align__(16) float sB[kFwdTileRows * kPitch];
+    __shared__ __align__(16) T s_u[kFwdTH * kRawPitch];
+    __shared__ __align__(16) T s_dz[kFwdTH * kRawPitch];
     __shared__ float s_red[kDwWarps * 26];
     const int e = blockIdx.z, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int c0 = blockIdx.x * kFwdTW;
@@ -428,22 +523,34 @@ dw_bwd_reduce_kernel(const T* __restrict__ x, const T* __restrict__ u, const T* 
 #pragma unroll
     for (int t = 0; t < 25; ++t) P[t] = mk2(0.f, 0.f);
     f2 sdu = mk2(0.f, 0.f);
-    for (int b = 0; b < g.B; ++b) {
-        const int64_t poff = ((int64_t)b * g.E + e) * g.H * g.W;
-        const float dp = dpool != nullptr ? __ldg(dpool + b * g.E + e) * inv_hw : 0.f;
-        for (int tr = band0; tr < band1; tr += kFwdTH) {
-            __syncthreads();
-            load_tile(x + poff, g.H, g.W, tr - 2, c0 - 2, kFwdTileRows, sA, sB);
-            __syncthreads();
-            walk5<kFwdRT>(sA, sB, warp * kFwdRT, 2 * lane, [&](int o, const f2(&win)[5][5]) {
-                const int row = tr + warp * kFwdRT + o;
+    // u and dz tiles (storage type, no halo) ride the same register-prefetch pipeline as x
+    struct UDz {
+        RawTileLoader<T, VEC, kFwdTH> lu, lz;
+        const T *u, *dz;
+        T *su, *sz;
+        int e, c0;
+        const DwGeom& g;
+        __device__ __forceinline__ void fetch(int b, int tr) {
+            const int64_t poff = ((int64_t)b * g.E + e) * g.H * g.W;
+            lu.fetch(u + poff, g.H, g.W, tr, c0);
+            lz.fetch(dz + poff, g.H, g.W, tr, c0);
+        }
+        __device__ __forceinline__ void commit() { lu.commit(su); lz.commit(sz); }
+    } udz{{}, {}, u, dz, s_u, s_dz, e, c0, g};
+    for_each_tile<T, VEC, kFwdTileRows>(
+        g, band0, band1, kFwdTH, 2, c0, sA,
+        [&](int b) { return x + ((int64_t)b * g.E + e) * g.H * g.W; }, udz,
+        [&](int b, int tr, bool) {
+            const int64_t poff = ((int64_t)b * g.E + e) * g.H * g.W;
+            const float dp = dpool != nullptr ? __ldg(dpool + b * g.E + e) * inv_hw : 0.f;
+            walk5<kFwdRT>(sA, warp * kFwdRT, 2 * lane + kPad - 2, [&](int o, const f2(&win)[5][5]) {
+                const int trow = warp * kFwdRT + o, row = tr + trow;
                 f2 du = mk2(0.f, 0.f);
                 if (row < band1 && v0) {
-                    const int64_t off = poff + (int64_t)row * g.W + col;
-                    const f2 uu = load_pair(u + off, v0, v1, vec);
-                    const f2 gz = load_pair(dz + off, v0, v1, vec);
-                    du = mk2((gz.x + dp) * gelu_grad_f(uu.x), v1 ? (gz.y + dp) * gelu_grad_f(uu.y) : 0.f);
-                    store_pair(du_out + off, du, v0, v1, vec);
+                    const f2 uf = cvt_pair<T>(*reinterpret_cast<const typename RawPair<T>::type*>(s_u + trow * kRawPitch + 2 * lane));
+                    const f2 gf = cvt_pair<T>(*reinterpret_cast<const typename RawPair<T>::type*>(s_dz + trow * kRawPitch + 2 * lane));
+                    du = mk2((gf.x + dp) * gelu_grad_f(uf.x), v1 ? (gf.y + dp) * gelu_grad_f(uf.y) : 0.f);
+                    store_pair(du_out + poff + (int64_t)row * g.W + col, du, v0, v1, vec);
                     // keep exactly what later passes will read back
                     du = mk2(to_f(from_f<T>(du.x)), to_f(from_f<T>(du.y)));
                 }
@@ -453,8 +560,7 @@ dw_bwd_reduce_kernel(const T* __restrict__ x, const T* __restrict__ u, const T* 
 #pragma unroll
                     for (int bb = 0; bb < 5; ++bb) P[a * 5 + bb] = ffma2(win[a][bb], du, P[a * 5 + bb]);
             });
-        }
-    }
+        });
     float v[26];
 #pragma unroll
     for (int t = 0; t < 25; ++t) v[t] = P[t].x + P[t].y;
@@ -503,20 +609,21 @@ __global__ void dw_fin_bwd_kernel(const float* __restrict__ part, int ncta, lmne
 // =================================================================================================
 constexpr int kA1RT = 4;                      // dx rows per thread
 constexpr int kA1TH = kA1RT * kDwWarps;       // 16 dx rows per tile
-constexpr int kA1TW = 60;                     // dx columns per tile (dy region = 64 columns)
+constexpr int kA1TW = 56;                     // dx columns per tile (multiple of 8; dy region = 60 columns)
+constexpr int kA1RegPairs = (kA1TW + 4) / 2;  // 30 column pairs of the dy region
 constexpr int kA1RegRows = kA1TH + 4;         // dy region rows (20)
 constexpr int kA1RegRT = kA1RegRows / kDwWarps;  // 5 region rows per warp
 constexpr int kA1XRows = kA1TH + 8;           // x tile rows (halo 4)
+constexpr int kDyPitch = 72;                  // floats per row of the dy tiles (region col k at index k)
 
-template <typename T>
+template <typename T, int VEC>
 __global__ void __launch_bounds__(kDwThreads)
 dw_bwd_dx_kernel(const T* __restrict__ x, const T* __restrict__ du, lmnet_dw_params p, const float* __restrict__ cb,
                  T* __restrict__ dx, DwGeom g) {
     extern __shared__ __align__(16) float smem[];
-    float* xA = smem;
-    float* xB = xA + kA1XRows * kPitch;
-    float* dyA = xB + kA1XRows * kPitch;            // [4][kA1RegRows*kPitch]
-    float* dyB = dyA + 4 * kA1RegRows * kPitch;     // [4][kA1RegRows*kPitch]
+    float* xA = smem;                                   // [kA1XRows][kPitch]     x, halo 4
+    float* dyA = xA + kA1XRows * kPitch;                // [4][kA1RegRows][kDyPitch]
+    T* s_du = reinterpret_cast<T*>(dyA + 4 * kA1RegRows * kDyPitch);   // [kA1RegRows][kRawPitch]
     const int e = blockIdx.z, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int c0 = blockIdx.x * kA1TW;
     const int band0 = blockIdx.y * g.rows_per_band, band1 = min(band0 + g.rows_per_band, g.H);
@@ -530,86 +637,93 @@ dw_bwd_dx_kernel(const T* __restrict__ x, const T* __restrict__ du, lmnet_dw_par
         c0c[k] = __ldg(cb + e * 12 + k * 3 + 2);
     }
     const bool vec = (g.W & 1) == 0;
-    for (int b = 0; b < g.B; ++b) {
-        const int64_t poff = ((int64_t)b * g.E + e) * g.H * g.W;
-        for (int tr = band0; tr < band1; tr += kA1TH) {
-            __syncthreads();
-            load_tile(x + poff, g.H, g.W, tr - 4, c0 - 4, kA1XRows, xA, xB);
-            __syncthreads();
-            // phase 2: y_br and dy_br on the (TH+4) x 64 region whose origin is (tr-2, c0-2)
-            walk5<kA1RegRT>(xA, xB, warp * kA1RegRT, 2 * lane, [&](int o, const f2(&win)[5][5]) {
-                const int rr = warp * kA1RegRT + o;       // region row
-                const int row = tr - 2 + rr, col = c0 - 2 + 2 * lane;
-                f2 y[4];
-                branches_from_window(win, w, y);
-                const bool rin = row >= 0 && row < g.H;
-                const bool i0 = rin && col >= 0 && col < g.W, i1 = rin && col + 1 >= 0 && col + 1 < g.W;
-                f2 d = mk2(0.f, 0.f);
-                if (i0 || i1) {
-                    const T* dp = du + poff + (int64_t)row * g.W + col;
-                    d.x = i0 ? to_f(dp[0]) : 0.f;
-                    d.y = i1 ? to_f(dp[1]) : 0.f;
-                }
+    // dy tiles: make the never-written tail columns finite (they are read by idle lanes only)
+    for (int i = threadIdx.x; i < 4 * kA1RegRows * kDyPitch; i += kDwThreads) dyA[i] = 0.f;
+    // du region tile: rows tr-2 .. tr+TH+2, staged from column c0-4 (vector aligned); region col k -> index k+2
+    struct DuStage {
+        RawTileLoader<T, VEC, kA1RegRows> ld;
+        const T* du;
+        T* s;
+        int e, c0;
+        const DwGeom& g;
+        __device__ __forceinline__ void fetch(int b, int tr) {
+            ld.fetch(du + ((int64_t)b * g.E + e) * g.H * g.W, g.H, g.W, tr - 2, c0 - 4);
+        }
+        __device__ __forceinline__ void commit() { ld.commit(s); }
+    } dus{{}, du, s_du, e, c0, g};
+    for_each_tile<T, VEC, kA1XRows>(
+        g, band0, band1, kA1TH, 4, c0, xA,
+        [&](int b) { return x + ((int64_t)b * g.E + e) * g.H * g.W; }, dus,
+        [&](int b, int tr, bool) {
+            const int64_t poff = ((int64_t)b * g.E + e) * g.H * g.W;
+            const int rcol = c0 - 2 + 2 * lane;           // global column of the region pair
+            // phase 2: y_br and dy_br on the (TH+4) x 60 region whose origin is (tr-2, c0-2);
+            // the x tile origin is (tr-4, c0-kPad), so region column k sits at tile index k + kPad - 4
+            if (lane < kA1RegPairs) {
+                walk5<kA1RegRT>(xA, warp * kA1RegRT, 2 * lane + kPad - 4, [&](int o, const f2(&win)[5][5]) {
+                    const int rr = warp * kA1RegRT + o;       // region row
+                    const int row = tr - 2 + rr;
+                    f2 y[4];
+                    branches_from_window(win, w, y);
+                    const bool rin = row >= 0 && row < g.H;
+                    const bool i0 = rin && rcol >= 0 && rcol < g.W, i1 = rin && rcol + 1 >= 0 && rcol + 1 < g.W;
+                    const f2 d = cvt_pair<T>(*reinterpret_cast<const typename RawPair<T>::type*>(s_du + rr * kRawPitch + 2 * lane + 2));
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    f2 dy = mk2(i0 ? c1[k] * d.x - c2[k] * y[k].x - c0c[k] : 0.f, i1 ? c1[k] * d.y - c2[k] * y[k].y - c0c[k] : 0.f);
-                    float* a = dyA + k * kA1RegRows * kPitch + rr * kPitch + 2 * lane;
-                    float* bsh = dyB + k * kA1RegRows * kPitch + rr * kPitch + 2 * lane;
-                    *reinterpret_cast<float2*>(a) = make_float2(dy.x, dy.y);
-                    // shifted copy: B[i] = A[i+1]
-                    if (lane > 0) bsh[-1] = dy.x;
-                    bsh[0] = dy.y;
-                }
-            });
+                    for (int k = 0; k < 4; ++k) {
+                        f2 dy = mk2(i0 ? c1[k] * d.x - c2[k] * y[k].x - c0c[k] : 0.f, i1 ? c1[k] * d.y - c2[k] * y[k].y - c0c[k] : 0.f);
+                        *reinterpret_cast<float2*>(dyA + k * kA1RegRows * kDyPitch + rr * kDyPitch + 2 * lane) = make_float2(dy.x, dy.y);
+                    }
+                });
+            }
             __syncthreads();
             // phase 3: dx(r,c) = sum_br sum_{a,b} w_br[a][b] * dy_br(r-(a-2), c-(b-2))  (flipped taps)
-            f2 acc[kA1RT];
+            if (2 * lane < kA1TW) {
+                f2 acc[kA1RT];
 #pragma unroll
-            for (int o = 0; o < kA1RT; ++o) acc[o] = mk2(0.f, 0.f);
-            walk5<kA1RT>(dyA, dyB, warp * kA1RT, 2 * lane, [&](int o, const f2(&win)[5][5]) {
+                for (int o = 0; o < kA1RT; ++o) acc[o] = mk2(0.f, 0.f);
+                walk5<kA1RT>(dyA, warp * kA1RT, 2 * lane, [&](int o, const f2(&win)[5][5]) {
 #pragma unroll
-                for (int a = 0; a < 5; ++a)
+                    for (int a = 0; a < 5; ++a)
 #pragma unroll
-                    for (int bb = 0; bb < 5; ++bb) acc[o] = ffma2(win[a][bb], w.w5[(4 - a) * 5 + (4 - bb)], acc[o]);
-            });
-            walk3<kA1RT>(dyA + kA1RegRows * kPitch, dyB + kA1RegRows * kPitch, warp * kA1RT + 1, 2 * lane,
-                         [&](int o, const f2(&win)[3][3]) {
+                        for (int bb = 0; bb < 5; ++bb) acc[o] = ffma2(win[a][bb], w.w5[(4 - a) * 5 + (4 - bb)], acc[o]);
+                }, kDyPitch);
+                walk3<kA1RT>(dyA + kA1RegRows * kDyPitch, warp * kA1RT + 1, 2 * lane,
+                             [&](int o, const f2(&win)[3][3]) {
 #pragma unroll
-                             for (int a = 0; a < 3; ++a)
+                                 for (int a = 0; a < 3; ++a)
 #pragma unroll
-                                 for (int bb = 0; bb < 3; ++bb) acc[o] = ffma2(win[a][bb], w.w3[(2 - a) * 3 + (2 - bb)], acc[o]);
-                         });
-            walk3<kA1RT>(dyA + 2 * kA1RegRows * kPitch, dyB + 2 * kA1RegRows * kPitch, warp * kA1RT + 1, 2 * lane,
-                         [&](int o, const f2(&win)[3][3]) {
+                                     for (int bb = 0; bb < 3; ++bb) acc[o] = ffma2(win[a][bb], w.w3[(2 - a) * 3 + (2 - bb)], acc[o]);
+                             }, kDyPitch);
+                walk3<kA1RT>(dyA + 2 * kA1RegRows * kDyPitch, warp * kA1RT + 1, 2 * lane,
+                             [&](int o, const f2(&win)[3][3]) {
 #pragma unroll
-                             for (int a = 0; a < 3; ++a) acc[o] = ffma2(win[a][1], w.w31[2 - a], acc[o]);
-                         });
-            walk3<kA1RT>(dyA + 3 * kA1RegRows * kPitch, dyB + 3 * kA1RegRows * kPitch, warp * kA1RT + 1, 2 * lane,
-                         [&](int o, const f2(&win)[3][3]) {
+                                 for (int a = 0; a < 3; ++a) acc[o] = ffma2(win[a][1], w.w31[2 - a], acc[o]);
+                             }, kDyPitch);
+                walk3<kA1RT>(dyA + 3 * kA1RegRows * kDyPitch, warp * kA1RT + 1, 2 * lane,
+                             [&](int o, const f2(&win)[3][3]) {
 #pragma unroll
-                             for (int bb = 0; bb < 3; ++bb) acc[o] = ffma2(win[1][bb], w.w13[2 - bb], acc[o]);
-                         });
-            const int col = c0 + 2 * lane;
-            if (2 * lane < kA1TW && col < g.W) {
+                                 for (int bb = 0; bb < 3; ++bb) acc[o] = ffma2(win[1][bb], w.w13[2 - bb], acc[o]);
+                             }, kDyPitch);
+                const int col = c0 + 2 * lane;
+                if (col < g.W) {
 #pragma unroll
-                for (int o = 0; o < kA1RT; ++o) {
-                    const int row = tr + warp * kA1RT + o;
-                    if (row < band1) store_pair(dx + poff + (int64_t)row * g.W + col, acc[o], true, col + 1 < g.W, vec);
+                    for (int o = 0; o < kA1RT; ++o) {
+                        const int row = tr + warp * kA1RT + o;
+                        if (row < band1) store_pair(dx + poff + (int64_t)row * g.W + col, acc[o], true, col + 1 < g.W, vec);
+                    }
                 }
             }
-        }
-    }
+        });
 }
 
 // =================================================================================================
 // backward A2 pass: Rbr[t] = sum_p (c2_br*y_br(p) + c0_br) * x(p+t);  dw_br[t] = c1_br*P[t] - Rbr[t]
 // =================================================================================================
-template <typename T>
+template <typename T, int VEC>
 __global__ void __launch_bounds__(kDwThreads)
 dw_bwd_dw_kernel(const T* __restrict__ x, lmnet_dw_params p, const float* __restrict__ cb,
                  float* __restrict__ part /* [E][ncta][40] */, DwGeom g) {
     __shared__ __align__(16) float sA[kFwdTileRows * kPitch];
-    __shared__ __align__(16) float sB[kFwdTileRows * kPitch];
     __shared__ float s_red[kDwWarps * 40];
     const int e = blockIdx.z, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int c0 = blockIdx.x * kFwdTW;
@@ -631,13 +745,11 @@ dw_bwd_dw_kernel(const T* __restrict__ x, lmnet_dw_params p, const float* __rest
     for (int t = 0; t < 9; ++t) A3[t] = mk2(0.f, 0.f);
 #pragma unroll
     for (int t = 0; t < 3; ++t) A31[t] = A13[t] = mk2(0.f, 0.f);
-    for (int b = 0; b < g.B; ++b) {
-        const T* plane = x + ((int64_t)b * g.E + e) * g.H * g.W;
-        for (int tr = band0; tr < band1; tr += kFwdTH) {
-            __syncthreads();
-            load_tile(plane, g.H, g.W, tr - 2, c0 - 2, kFwdTileRows, sA, sB);
-            __syncthreads();
-            walk5<kFwdRT>(sA, sB, warp * kFwdRT, 2 * lane, [&](int o, const f2(&win)[5][5]) {
+    for_each_tile<T, VEC, kFwdTileRows>(
+        g, band0, band1, kFwdTH, 2, c0, sA,
+        [&](int b) { return x + ((int64_t)b * g.E + e) * g.H * g.W; }, NoExtra{},
+        [&](int, int tr, bool) {
+            walk5<kFwdRT>(sA, warp * kFwdRT, 2 * lane + kPad - 2, [&](int o, const f2(&win)[5][5]) {
                 const int row = tr + warp * kFwdRT + o;
                 const float rm = row < band1 ? 1.f : 0.f;
                 const f2 m = mk2(cmask.x * rm, cmask.y * rm);
@@ -659,8 +771,7 @@ dw_bwd_dw_kernel(const T* __restrict__ x, lmnet_dw_params p, const float* __rest
 #pragma unroll
                 for (int bb = 0; bb < 3; ++bb) A13[bb] = ffma2(win[2][bb + 1], gk[3], A13[bb]);
             });
-        }
-    }
+        });
     float v[40];
 #pragma unroll
     for (int t = 0; t < 25; ++t) v[t] = A5[t].x + A5[t].y;
@@ -733,6 +844,24 @@ static DwWs dw_ws_layout(const lmnet_dw_dims* d, size_t esize) {
     return w;
 }
 
+// widest vector (16 or 8 bytes, else scalar) the tile loader may use for this tensor
+static int dw_vec_bytes(const void* const* ptrs, int n, const lmnet_dw_dims* d, size_t es) {
+    for (int vb = 16; vb >= 4; vb >>= 1) {
+        bool ok = ((size_t)d->W * es) % vb == 0;
+        for (int i = 0; i < n; ++i) ok = ok && ((uintptr_t)ptrs[i] % vb == 0);
+        if (ok) return vb;
+    }
+    return 0;
+}
+template <typename T, typename F>
+static int with_vec(int vec_bytes, F&& f) {
+    // the loaders move 4, 2 or 1 elements per lane (one float4 / float2 / float shared store each)
+    const int elems = vec_bytes / (int)sizeof(T);
+    if (elems >= 4) return f(std::integral_constant<int, 4>{});
+    if (elems >= 2) return f(std::integral_constant<int, 2>{});
+    return f(std::integral_constant<int, 1>{});
+}
+
 template <typename T>
 static int dw_train_fwd(const void* x, const lmnet_dw_params* p, void* u, void* z, float* pool, float* save_mean,
                         float* save_rstd, float eps, float momentum, int64_t* const* nbt, char* ws,
@@ -746,11 +875,23 @@ static int dw_train_fwd(const void* x, const lmnet_dw_params* p, void* u, void* 
     float* part = (float*)(ws + L.part);
     float* coef = (float*)(ws + L.coef);
     float* pool_part = (float*)(ws + L.pool_part);
-    LMNET_LAUNCH(KID_DW_STATS, st, 1 * t_bytes, (dw_stats_kernel<T><<<grid, kDwThreads, 0, st>>>((const T*)x, *p, part, g)));
+    const void* vp[1] = {x};
+    const int vb = dw_vec_bytes(vp, 1, d, sizeof(T));
+    int rc = with_vec<T>(vb, [&](auto v) -> int {
+        constexpr int VEC = decltype(v)::value;
+        LMNET_LAUNCH(KID_DW_STATS, st, 1 * t_bytes, (dw_stats_kernel<T, VEC><<<grid, kDwThreads, 0, st>>>((const T*)x, *p, part, g)));
+        return LMNET_OK;
+    });
+    if (rc != LMNET_OK) return rc;
     LMNET_LAUNCH(KID_DW_FIN_FWD, st, 0, (dw_fin_fwd_kernel<<<(g.E + 63) / 64, 64, 0, st>>>(part, ncta, *p, save_mean, save_rstd, coef, eps, momentum,
                                                      nbt ? nbt[0] : nullptr, nbt ? nbt[1] : nullptr,
                                                      nbt ? nbt[2] : nullptr, nbt ? nbt[3] : nullptr, g)));
-    LMNET_LAUNCH(KID_DW_APPLY, st, 2 * t_bytes, (dw_apply_kernel<T><<<grid, kDwThreads, 0, st>>>((const T*)x, coef, (T*)u, (T*)z, pool ? pool_part : nullptr, g)));
+    rc = with_vec<T>(vb, [&](auto v) -> int {
+        constexpr int VEC = decltype(v)::value;
+        LMNET_LAUNCH(KID_DW_APPLY, st, 2 * t_bytes, (dw_apply_kernel<T, VEC><<<grid, kDwThreads, 0, st>>>((const T*)x, coef, (T*)u, (T*)z, pool ? pool_part : nullptr, g)));
+        return LMNET_OK;
+    });
+    if (rc != LMNET_OK) return rc;
     if (pool) {
         const int n = g.B * g.E;
         LMNET_LAUNCH(KID_DW_POOL_FIN, st, 0, (dw_pool_fin_kernel<<<(n + 127) / 128, 128, 0, st>>>(pool_part, ncta, 1.f / ((float)g.H * g.W), pool, n)));
@@ -770,7 +911,14 @@ static int dw_eval_fwd(const void* x, const lmnet_dw_params* p, const float* bia
     float* coef = (float*)(ws + L.coef);
     float* pool_part = (float*)(ws + L.pool_part);
     LMNET_LAUNCH(KID_DW_COEF_EVAL, st, 0, (dw_coef_eval_kernel<<<(g.E + 63) / 64, 64, 0, st>>>(*p, bias, eps, coef, g.E)));
-    LMNET_LAUNCH(KID_DW_APPLY, st, 2 * t_bytes, (dw_apply_kernel<T><<<grid, kDwThreads, 0, st>>>((const T*)x, coef, (T*)nullptr, (T*)z, pool ? pool_part : nullptr, g)));
+    const void* vp[1] = {x};
+    const int vb = dw_vec_bytes(vp, 1, d, sizeof(T));
+    int rc = with_vec<T>(vb, [&](auto v) -> int {
+        constexpr int VEC = decltype(v)::value;
+        LMNET_LAUNCH(KID_DW_APPLY, st, 2 * t_bytes, (dw_apply_kernel<T, VEC><<<grid, kDwThreads, 0, st>>>((const T*)x, coef, (T*)nullptr, (T*)z, pool ? pool_part : nullptr, g)));
+        return LMNET_OK;
+    });
+    if (rc != LMNET_OK) return rc;
     if (pool) {
         const int n = g.B * g.E;
         LMNET_LAUNCH(KID_DW_POOL_FIN, st, 0, (dw_pool_fin_kernel<<<(n + 127) / 128, 128, 0, st>>>(pool_part, ncta, 1.f / ((float)g.H * g.W), pool, n)));
@@ -778,7 +926,7 @@ static int dw_eval_fwd(const void* x, const lmnet_dw_params* p, const float* bia
     return LMNET_OK;
 }
 
-constexpr size_t kA1SmemBytes = (size_t)(2 * kA1XRows * kPitch + 8 * kA1RegRows * kPitch) * sizeof(float);
+constexpr size_t kA1SmemBytes = (size_t)(kA1XRows * kPitch + 4 * kA1RegRows * kDyPitch + kA1RegRows * kRawPitch) * sizeof(float);
 
 template <typename T>
 static int dw_train_bwd(const void* x, const void* u, const void* dz, const float* dpool, const lmnet_dw_params* p,
@@ -794,20 +942,30 @@ static int dw_train_bwd(const void* x, const void* u, const void* dz, const floa
     float* pfin = (float*)(ws + L.pfin);
     float* cb = (float*)(ws + L.cb);
     T* du = (T*)(ws + L.du);
-    LMNET_LAUNCH(KID_DW_BWD_REDUCE, st, 2 * t_bytes, (dw_bwd_reduce_kernel<T><<<grid, kDwThreads, 0, st>>>((const T*)x, (const T*)u, (const T*)dz, dpool, du, part, g)));
+    const void* vp[4] = {x, u, dz, du};
+    const int vb = dw_vec_bytes(vp, 4, d, sizeof(T));
+    int rc = with_vec<T>(vb, [&](auto v) -> int {
+        constexpr int VEC = decltype(v)::value;
+        LMNET_LAUNCH(KID_DW_BWD_REDUCE, st, 2 * t_bytes, (dw_bwd_reduce_kernel<T, VEC><<<grid, kDwThreads, 0, st>>>((const T*)x, (const T*)u, (const T*)dz, dpool, du, part, g)));
+        return LMNET_OK;
+    });
+    if (rc != LMNET_OK) return rc;
     LMNET_LAUNCH(KID_DW_FIN_BWD, st, 0, (dw_fin_bwd_kernel<<<(g.E + 63) / 64, 64, 0, st>>>(part, ncta, *p, save_mean, save_rstd, *gr, pfin, cb, g)));
-    {
+    rc = with_vec<T>(vb, [&](auto v) -> int {
+        constexpr int VEC = decltype(v)::value;
         DwGeom ga = dw_geom(d, kA1TH, kA1TW);
         static bool attr_set = false;  // benign race: the attribute is idempotent
         if (!attr_set) {
-            if (cudaFuncSetAttribute(dw_bwd_dx_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kA1SmemBytes) != cudaSuccess)
+            if (cudaFuncSetAttribute(dw_bwd_dx_kernel<T, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kA1SmemBytes) != cudaSuccess)
                 return LMNET_ERR_LAUNCH;
             attr_set = true;
         }
         dim3 ga_grid(ga.stripes, ga.bands, ga.E);
-        LMNET_LAUNCH(KID_DW_BWD_DX, st, 3 * t_bytes, (dw_bwd_dx_kernel<T><<<ga_grid, kDwThreads, kA1SmemBytes, st>>>((const T*)x, du, *p, cb, (T*)dx, ga)));
-    }
-    LMNET_LAUNCH(KID_DW_BWD_DW, st, 0, (dw_bwd_dw_kernel<T><<<grid, kDwThreads, 0, st>>>((const T*)x, *p, cb, part, g)));
+        LMNET_LAUNCH(KID_DW_BWD_DX, st, 3 * t_bytes, (dw_bwd_dx_kernel<T, VEC><<<ga_grid, kDwThreads, kA1SmemBytes, st>>>((const T*)x, du, *p, cb, (T*)dx, ga)));
+        LMNET_LAUNCH(KID_DW_BWD_DW, st, 0, (dw_bwd_dw_kernel<T, VEC><<<grid, kDwThreads, 0, st>>>((const T*)x, *p, cb, part, g)));
+        return LMNET_OK;
+    });
+    if (rc != LMNET_OK) return rc;
     LMNET_LAUNCH(KID_DW_FIN_DW, st, 0, (dw_fin_dw_kernel<<<g.E, 64, 0, st>>>(part, ncta, pfin, cb, *gr, g.E)));
     return LMNET_OK;
 }
