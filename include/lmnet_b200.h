@@ -166,6 +166,28 @@ int lmnet_reparam_dw_eval_fwd(const void* x, const lmnet_dw_params* p, const flo
                               void* z, float* pool, void* workspace, size_t workspace_bytes,
                               const lmnet_dw_dims* dims, int dtype, void* stream);
 
+/* ---- fused BatchNorm2d + activation on NCHW tensors (widening step f1/f3, SURVEY.md §8 f) -------
+ * Replaces nn.BatchNorm2d followed by an activation where the reference applies them back to back:
+ * expand_conv's BN + Hardswish (/root/reference/core/modules.py:537-539) and the skip blocks'
+ * BN + GELU (/root/reference/core/modules.py:97-100, 122-125, 134-137).  y, out, dout, dy: [B,C,HW]
+ * contiguous of `dtype`; gamma/beta may be NULL (affine off).  Training: batch statistics, running
+ * statistics and the counter updated in place when non-NULL (momentum semantics of nn.BatchNorm2d),
+ * save_mean/save_rstd [C] written.  Inference: running statistics are used. */
+typedef enum lmnet_act { LMNET_ACT_NONE = 0, LMNET_ACT_HARDSWISH = 1, LMNET_ACT_GELU = 2, LMNET_ACT_RELU = 3 } lmnet_act;
+typedef struct lmnet_bn_dims {
+    int32_t B, C;
+    int64_t HW;
+} lmnet_bn_dims;
+size_t lmnet_bn_act_workspace_bytes(const lmnet_bn_dims* dims);
+int lmnet_bn_act_fwd(const void* y, const float* gamma, const float* beta, float* running_mean,
+                     float* running_var, int64_t* num_batches_tracked, void* out, float* save_mean,
+                     float* save_rstd, float eps, float momentum, int training, int act,
+                     void* workspace, size_t workspace_bytes, const lmnet_bn_dims* dims, int dtype, void* stream);
+int lmnet_bn_act_bwd(const void* y, const void* dout, const float* gamma, const float* beta,
+                     const float* save_mean, const float* save_rstd, void* dy, float* dgamma, float* dbeta,
+                     int act, void* workspace, size_t workspace_bytes, const lmnet_bn_dims* dims, int dtype,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

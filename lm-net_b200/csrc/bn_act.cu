@@ -1,0 +1,410 @@
+// bn_act.cu — fused train/eval BatchNorm2d + activation on NCHW tensors (sm_100a), forward and backward.
+//
+// Widening step f1/f3 of SURVEY.md §8: the BatchNorm + Hardswish that follows ReparamConv's expand
+// 1x1 convolution (/root/reference/core/modules.py:537-539, 587) and the BatchNorm + GELU that closes
+// the skip-fusion blocks (/root/reference/core/modules.py:97-100, 122-125, 134-137).  In the step
+// profile of round 1 ATen's bf16 batch_norm_backward alone was 21 % of the training step
+// (profiles/r01_step_profile_a_*.txt).  These are pure bandwidth kernels:
+//   train fwd  = stats (read y) -> finalize -> apply (read y, write out)            3*T*es
+//   train bwd  = reduce (read y, dout) -> finalize -> apply (read y, dout, write dy) 5*T*es
+//   eval  fwd  = apply                                                              2*T*es
+// A CTA owns one channel and one chunk of its B*HW elements (16-byte vector loads, fp32 math);
+// per-CTA partial sums are reduced by the finalize kernels in a fixed order (deterministic).
+// The activation input is rounded to the storage type first, as the reference's separate
+// BatchNorm -> activation kernels would see it.
+#include "common.cuh"
+
+namespace lmnet {
+
+constexpr int kBnThreads = 256;
+
+struct BnGeom {
+    int B, C;
+    int64_t HW;
+    int chunks;            // CTAs per channel
+    int64_t per_chunk;     // elements of one channel handled by one CTA (multiple of the vector width)
+};
+
+template <int ACT> __device__ __forceinline__ float act_fwd(float x) {
+    if constexpr (ACT == LMNET_ACT_HARDSWISH) return x * fminf(fmaxf(x + 3.f, 0.f), 6.f) * (1.f / 6.f);
+    else if constexpr (ACT == LMNET_ACT_GELU) return 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
+    else if constexpr (ACT == LMNET_ACT_RELU) return fmaxf(x, 0.f);
+    else return x;
+}
+template <int ACT> __device__ __forceinline__ float act_bwd(float x) {
+    if constexpr (ACT == LMNET_ACT_HARDSWISH) return x < -3.f ? 0.f : (x <= 3.f ? (2.f * x + 3.f) * (1.f / 6.f) : 1.f);
+    else if constexpr (ACT == LMNET_ACT_GELU)
+        return 0.5f * (1.f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+    else if constexpr (ACT == LMNET_ACT_RELU) return x > 0.f ? 1.f : 0.f;
+    else return 1.f;
+}
+
+// elements per lane per iteration: a 16-byte vector on the aligned path, one element otherwise
+template <typename T, bool VEC> struct Lane { static constexpr int N = VEC ? 16 / (int)sizeof(T) : 1; };
+
+template <typename T, bool VEC>
+__device__ __forceinline__ void ld_elems(const T* __restrict__ p, float (&f)[Lane<T, VEC>::N], int n_valid) {
+    constexpr int N = Lane<T, VEC>::N;
+    if constexpr (VEC) {
+        uint4 raw = __ldg(reinterpret_cast<const uint4*>(p));
+        const T* e = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+        for (int j = 0; j < N; ++j) f[j] = to_f(e[j]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < N; ++j) f[j] = j < n_valid ? to_f(p[j]) : 0.f;
+    }
+}
+template <typename T, bool VEC>
+__device__ __forceinline__ void st_elems(T* __restrict__ p, const float (&f)[Lane<T, VEC>::N], int n_valid) {
+    constexpr int N = Lane<T, VEC>::N;
+    if constexpr (VEC) {
+        uint4 raw;
+        T* e = reinterpret_cast<T*>(&raw);
+#pragma unroll
+        for (int j = 0; j < N; ++j) e[j] = from_f<T>(f[j]);
+        *reinterpret_cast<uint4*>(p) = raw;
+    } else {
+#pragma unroll
+        for (int j = 0; j < N; ++j)
+            if (j < n_valid) p[j] = from_f<T>(f[j]);
+    }
+}
+
+__device__ __forceinline__ void block_sum2(float& a, float& b, float* s_red /* [2*8] */) {
+    a = warp_sum(a);
+    b = warp_sum(b);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { s_red[warp] = a; s_red[8 + warp] = b; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float x = 0.f, y = 0.f;
+        for (int w = 0; w < kBnThreads / 32; ++w) { x += s_red[w]; y += s_red[8 + w]; }
+        a = x; b = y;
+    }
+}
+
+// Iterates the vectors of channel c that belong to chunk k: fn(pointer offset, n_valid)
+template <typename T, bool VEC, typename Fn>
+__device__ __forceinline__ void for_chunk(const BnGeom& g, int c, int k, Fn&& fn) {
+    constexpr int N = Lane<T, VEC>::N;
+    const int64_t total = (int64_t)g.B * g.HW;                 // elements of this channel
+    const int64_t lo = (int64_t)k * g.per_chunk, hi = min(lo + g.per_chunk, total);
+    for (int64_t n = lo + (int64_t)threadIdx.x * N; n < hi; n += (int64_t)kBnThreads * N) {
+        const int64_t b = n / g.HW, i = n - b * g.HW;          // HW % N == 0 on the vector path => no straddle
+        const int64_t off = (b * g.C + c) * g.HW + i;
+        const int n_valid = (int)min((int64_t)N, min(hi - n, g.HW - i));
+        fn(off, n_valid);
+    }
+}
+
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(kBnThreads)
+bnact_stats_kernel(const T* __restrict__ y, float* __restrict__ part /* [C][chunks][2] */, BnGeom g) {
+    __shared__ float s_red[16];
+    const int c = blockIdx.y, k = blockIdx.x;
+    float s = 0.f, ss = 0.f;
+    for_chunk<T, VEC>(g, c, k, [&](int64_t off, int nv) {
+        float f[Lane<T, VEC>::N];
+        ld_elems<T, VEC>(y + off, f, nv);
+#pragma unroll
+        for (int j = 0; j < Lane<T, VEC>::N; ++j) { s += f[j]; ss = fmaf(f[j], f[j], ss); }
+    });
+    block_sum2(s, ss, s_red);
+    if (threadIdx.x == 0) {
+        part[((int64_t)c * g.chunks + k) * 2] = s;
+        part[((int64_t)c * g.chunks + k) * 2 + 1] = ss;
+    }
+}
+
+// coef[c] = (a, b) with out = act(a*y + b)
+__global__ void bnact_fin_fwd_kernel(const float* __restrict__ part, const float* __restrict__ gamma,
+                                     const float* __restrict__ beta, float* running_mean, float* running_var,
+                                     int64_t* nbt, float* __restrict__ save_mean, float* __restrict__ save_rstd,
+                                     float2* __restrict__ coef, float eps, float momentum, BnGeom g) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= g.C) return;
+    const double n = (double)g.B * (double)g.HW;
+    double s = 0, ss = 0;
+    for (int k = 0; k < g.chunks; ++k) {
+        s += part[((int64_t)c * g.chunks + k) * 2];
+        ss += part[((int64_t)c * g.chunks + k) * 2 + 1];
+    }
+    const double mean = s / n;
+    double var = ss / n - mean * mean;
+    if (var < 0) var = 0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    save_mean[c] = (float)mean;
+    save_rstd[c] = rstd;
+    if (running_mean != nullptr) {
+        const double unbiased = n > 1 ? var * n / (n - 1) : var;
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+    }
+    const float ga = gamma != nullptr ? gamma[c] : 1.f, be = beta != nullptr ? beta[c] : 0.f;
+    const float a = ga * rstd;
+    coef[c] = make_float2(a, be - a * (float)mean);
+    if (c == 0 && nbt != nullptr) *nbt += 1;
+}
+
+__global__ void bnact_coef_eval_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
+                                       const float* __restrict__ running_mean, const float* __restrict__ running_var,
+                                       float2* __restrict__ coef, float eps, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float ga = gamma != nullptr ? gamma[c] : 1.f, be = beta != nullptr ? beta[c] : 0.f;
+    const float a = ga / sqrtf(running_var[c] + eps);
+    coef[c] = make_float2(a, be - a * running_mean[c]);
+}
+
+template <typename T, bool VEC, int ACT>
+__global__ void __launch_bounds__(kBnThreads)
+bnact_apply_kernel(const T* __restrict__ y, const float2* __restrict__ coef, T* __restrict__ out, BnGeom g) {
+    const int c = blockIdx.y, k = blockIdx.x;
+    const float2 ab = __ldg(coef + c);
+    for_chunk<T, VEC>(g, c, k, [&](int64_t off, int nv) {
+        float f[Lane<T, VEC>::N];
+        ld_elems<T, VEC>(y + off, f, nv);
+#pragma unroll
+        for (int j = 0; j < Lane<T, VEC>::N; ++j) {
+            const float pre = to_f(from_f<T>(fmaf(f[j], ab.x, ab.y)));
+            f[j] = act_fwd<ACT>(pre);
+        }
+        st_elems<T, VEC>(out + off, f, nv);
+    });
+}
+
+// sums of dh = dout * act'(pre) and dh * yhat, yhat = (y - mean) * rstd
+template <typename T, bool VEC, int ACT>
+__global__ void __launch_bounds__(kBnThreads)
+bnact_bwd_reduce_kernel(const T* __restrict__ y, const T* __restrict__ dout, const float* __restrict__ gamma,
+                        const float* __restrict__ beta, const float* __restrict__ save_mean,
+                        const float* __restrict__ save_rstd, float* __restrict__ part, BnGeom g) {
+    __shared__ float s_red[16];
+    const int c = blockIdx.y, k = blockIdx.x;
+    const float mean = save_mean[c], rstd = save_rstd[c];
+    const float ga = gamma != nullptr ? gamma[c] : 1.f, be = beta != nullptr ? beta[c] : 0.f;
+    float s = 0.f, sy = 0.f;
+    for_chunk<T, VEC>(g, c, k, [&](int64_t off, int nv) {
+        float f[Lane<T, VEC>::N], d[Lane<T, VEC>::N];
+        ld_elems<T, VEC>(y + off, f, nv);
+        ld_elems<T, VEC>(dout + off, d, nv);
+#pragma unroll
+        for (int j = 0; j < Lane<T, VEC>::N; ++j) {
+            const float yh = (f[j] - mean) * rstd;
+            const float pre = to_f(from_f<T>(fmaf(yh, ga, be)));
+            const float dh = d[j] * act_bwd<ACT>(pre);
+            s += dh;
+            sy = fmaf(dh, yh, sy);
+        }
+    });
+    block_sum2(s, sy, s_red);
+    if (threadIdx.x == 0) {
+        part[((int64_t)c * g.chunks + k) * 2] = s;
+        part[((int64_t)c * g.chunks + k) * 2 + 1] = sy;
+    }
+}
+
+// cb[c] = (m1, m2) = (sum dh / n, sum dh*yhat / n); also writes dgamma, dbeta
+__global__ void bnact_fin_bwd_kernel(const float* __restrict__ part, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                     float2* __restrict__ cb, BnGeom g) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= g.C) return;
+    const double n = (double)g.B * (double)g.HW;
+    double s = 0, sy = 0;
+    for (int k = 0; k < g.chunks; ++k) {
+        s += part[((int64_t)c * g.chunks + k) * 2];
+        sy += part[((int64_t)c * g.chunks + k) * 2 + 1];
+    }
+    if (dgamma != nullptr) dgamma[c] = (float)sy;
+    if (dbeta != nullptr) dbeta[c] = (float)s;
+    cb[c] = make_float2((float)(s / n), (float)(sy / n));
+}
+
+template <typename T, bool VEC, int ACT>
+__global__ void __launch_bounds__(kBnThreads)
+bnact_bwd_apply_kernel(const T* __restrict__ y, const T* __restrict__ dout, const float* __restrict__ gamma,
+                       const float* __restrict__ beta, const float* __restrict__ save_mean,
+                       const float* __restrict__ save_rstd, const float2* __restrict__ cb, T* __restrict__ dy, BnGeom g) {
+    const int c = blockIdx.y, k = blockIdx.x;
+    const float mean = save_mean[c], rstd = save_rstd[c];
+    const float ga = gamma != nullptr ? gamma[c] : 1.f, be = beta != nullptr ? beta[c] : 0.f;
+    const float2 m = __ldg(cb + c);
+    const float gr = ga * rstd;
+    for_chunk<T, VEC>(g, c, k, [&](int64_t off, int nv) {
+        float f[Lane<T, VEC>::N], d[Lane<T, VEC>::N];
+        ld_elems<T, VEC>(y + off, f, nv);
+        ld_elems<T, VEC>(dout + off, d, nv);
+#pragma unroll
+        for (int j = 0; j < Lane<T, VEC>::N; ++j) {
+            const float yh = (f[j] - mean) * rstd;
+            const float pre = to_f(from_f<T>(fmaf(yh, ga, be)));
+            const float dh = d[j] * act_bwd<ACT>(pre);
+            f[j] = gr * (dh - m.x - yh * m.y);
+        }
+        st_elems<T, VEC>(dy + off, f, nv);
+    });
+}
+
+// ------------------------------------------------------------------------------------------------
+static int bn_validate(const lmnet_bn_dims* d) {
+    if (d == nullptr || d->B <= 0 || d->C <= 0 || d->HW <= 0) return LMNET_ERR_INVALID_ARG;
+    return LMNET_OK;
+}
+
+static BnGeom bn_geom(const lmnet_bn_dims* d, size_t es) {
+    BnGeom g;
+    g.B = d->B; g.C = d->C; g.HW = d->HW;
+    const int64_t total = (int64_t)d->B * d->HW;
+    const int64_t vec = 16 / (int64_t)es;
+    int chunks = (4 * 148 + d->C - 1) / d->C;                      // ~4 CTAs per SM over the whole grid
+    const int64_t min_chunk = (int64_t)kBnThreads * vec * 4;       // at least 4 vectors per thread
+    const int64_t max_chunks = (total + min_chunk - 1) / min_chunk;
+    if (chunks > max_chunks) chunks = (int)max_chunks;
+    if (chunks < 1) chunks = 1;
+    int64_t per = (total + chunks - 1) / chunks;
+    per = (per + vec - 1) / vec * vec;
+    g.per_chunk = per;
+    g.chunks = (int)((total + per - 1) / per);
+    return g;
+}
+
+static bool bn_vec_ok(const lmnet_bn_dims* d, size_t es, std::initializer_list<const void*> ptrs) {
+    if ((d->HW * (int64_t)es) % 16 != 0) return false;
+    for (auto p : ptrs)
+        if (p != nullptr && (uintptr_t)p % 16 != 0) return false;
+    return true;
+}
+
+struct BnWs {
+    size_t part, coef, total;
+};
+static BnWs bn_ws(const lmnet_bn_dims* d) {
+    BnGeom g = bn_geom(d, 2);   // the smaller element size gives the larger chunk count
+    BnGeom g4 = bn_geom(d, 4);
+    int chunks = g.chunks > g4.chunks ? g.chunks : g4.chunks;
+    BnWs w;
+    w.part = 0;
+    w.coef = ((size_t)d->C * chunks * 2 * sizeof(float) + 255) / 256 * 256;
+    w.total = w.coef + ((size_t)d->C * sizeof(float2) + 255) / 256 * 256;
+    return w;
+}
+
+template <typename T, bool VEC, int ACT>
+static int bn_launch_fwd(bool train, const void* y, const float* gamma, const float* beta, float* rm, float* rv,
+                         int64_t* nbt, void* out, float* save_mean, float* save_rstd, float eps, float momentum,
+                         char* ws, const lmnet_bn_dims* d, cudaStream_t st) {
+    BnGeom g = bn_geom(d, sizeof(T));
+    BnWs L = bn_ws(d);
+    float* part = (float*)(ws + L.part);
+    float2* coef = (float2*)(ws + L.coef);
+    dim3 grid(g.chunks, g.C);
+    const double t_bytes = (double)d->B * d->C * d->HW * sizeof(T);
+    if (train) {
+        LMNET_LAUNCH(KID_BN_STATS, st, t_bytes, (bnact_stats_kernel<T, VEC><<<grid, kBnThreads, 0, st>>>((const T*)y, part, g)));
+        LMNET_LAUNCH(KID_BN_FIN_FWD, st, 0, (bnact_fin_fwd_kernel<<<(g.C + 127) / 128, 128, 0, st>>>(
+            part, gamma, beta, rm, rv, nbt, save_mean, save_rstd, coef, eps, momentum, g)));
+    } else {
+        LMNET_LAUNCH(KID_BN_FIN_FWD, st, 0, (bnact_coef_eval_kernel<<<(g.C + 127) / 128, 128, 0, st>>>(gamma, beta, rm, rv, coef, eps, g.C)));
+    }
+    LMNET_LAUNCH(KID_BN_APPLY, st, 2 * t_bytes, (bnact_apply_kernel<T, VEC, ACT><<<grid, kBnThreads, 0, st>>>((const T*)y, coef, (T*)out, g)));
+    return LMNET_OK;
+}
+
+template <typename T, bool VEC, int ACT>
+static int bn_launch_bwd(const void* y, const void* dout, const float* gamma, const float* beta, const float* save_mean,
+                         const float* save_rstd, void* dy, float* dgamma, float* dbeta, char* ws,
+                         const lmnet_bn_dims* d, cudaStream_t st) {
+    BnGeom g = bn_geom(d, sizeof(T));
+    BnWs L = bn_ws(d);
+    float* part = (float*)(ws + L.part);
+    float2* cb = (float2*)(ws + L.coef);
+    dim3 grid(g.chunks, g.C);
+    const double t_bytes = (double)d->B * d->C * d->HW * sizeof(T);
+    LMNET_LAUNCH(KID_BN_BWD_REDUCE, st, 2 * t_bytes, (bnact_bwd_reduce_kernel<T, VEC, ACT><<<grid, kBnThreads, 0, st>>>(
+        (const T*)y, (const T*)dout, gamma, beta, save_mean, save_rstd, part, g)));
+    LMNET_LAUNCH(KID_BN_FIN_BWD, st, 0, (bnact_fin_bwd_kernel<<<(g.C + 127) / 128, 128, 0, st>>>(part, dgamma, dbeta, cb, g)));
+    LMNET_LAUNCH(KID_BN_BWD_APPLY, st, 3 * t_bytes, (bnact_bwd_apply_kernel<T, VEC, ACT><<<grid, kBnThreads, 0, st>>>(
+        (const T*)y, (const T*)dout, gamma, beta, save_mean, save_rstd, cb, (T*)dy, g)));
+    return LMNET_OK;
+}
+
+#define BN_DISPATCH_ACT(T, VEC, CALL)                                                      \
+    switch (act) {                                                                        \
+        case LMNET_ACT_NONE: return CALL<T, VEC, LMNET_ACT_NONE>;                         \
+        case LMNET_ACT_HARDSWISH: return CALL<T, VEC, LMNET_ACT_HARDSWISH>;               \
+        case LMNET_ACT_GELU: return CALL<T, VEC, LMNET_ACT_GELU>;                         \
+        case LMNET_ACT_RELU: return CALL<T, VEC, LMNET_ACT_RELU>;                         \
+        default: return nullptr;                                                          \
+    }
+
+template <typename T, bool VEC> static auto pick_fwd(int act) -> decltype(&bn_launch_fwd<T, VEC, 0>) { BN_DISPATCH_ACT(T, VEC, &bn_launch_fwd) }
+template <typename T, bool VEC> static auto pick_bwd(int act) -> decltype(&bn_launch_bwd<T, VEC, 0>) { BN_DISPATCH_ACT(T, VEC, &bn_launch_bwd) }
+
+template <typename T>
+static int bn_fwd_t(bool vec, int act, bool train, const void* y, const float* gamma, const float* beta, float* rm,
+                    float* rv, int64_t* nbt, void* out, float* sm, float* sr, float eps, float mom, char* ws,
+                    const lmnet_bn_dims* d, cudaStream_t st) {
+    auto fn = vec ? pick_fwd<T, true>(act) : pick_fwd<T, false>(act);
+    if (fn == nullptr) return LMNET_ERR_UNSUPPORTED;
+    return fn(train, y, gamma, beta, rm, rv, nbt, out, sm, sr, eps, mom, ws, d, st);
+}
+template <typename T>
+static int bn_bwd_t(bool vec, int act, const void* y, const void* dout, const float* gamma, const float* beta,
+                    const float* sm, const float* sr, void* dy, float* dgamma, float* dbeta, char* ws,
+                    const lmnet_bn_dims* d, cudaStream_t st) {
+    auto fn = vec ? pick_bwd<T, true>(act) : pick_bwd<T, false>(act);
+    if (fn == nullptr) return LMNET_ERR_UNSUPPORTED;
+    return fn(y, dout, gamma, beta, sm, sr, dy, dgamma, dbeta, ws, d, st);
+}
+
+}  // namespace lmnet
+
+using namespace lmnet;
+
+extern "C" size_t lmnet_bn_act_workspace_bytes(const lmnet_bn_dims* dims) {
+    if (bn_validate(dims) != LMNET_OK) return 0;
+    return bn_ws(dims).total;
+}
+
+extern "C" int lmnet_bn_act_fwd(const void* y, const float* gamma, const float* beta, float* running_mean,
+                                float* running_var, int64_t* num_batches_tracked, void* out, float* save_mean,
+                                float* save_rstd, float eps, float momentum, int training, int act,
+                                void* workspace, size_t workspace_bytes, const lmnet_bn_dims* dims, int dtype,
+                                void* stream) {
+    int rc = bn_validate(dims);
+    if (rc != LMNET_OK) return rc;
+    if (!y || !out || !workspace) return LMNET_ERR_INVALID_ARG;
+    if (training && (!save_mean || !save_rstd)) return LMNET_ERR_INVALID_ARG;
+    if (!training && (!running_mean || !running_var)) return LMNET_ERR_INVALID_ARG;
+    if ((running_mean == nullptr) != (running_var == nullptr)) return LMNET_ERR_INVALID_ARG;
+    if (workspace_bytes < bn_ws(dims).total) return LMNET_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t es = dtype == LMNET_F32 ? 4 : 2;
+    const bool vec = bn_vec_ok(dims, es, {y, out});
+    switch (dtype) {
+        case LMNET_F32: return bn_fwd_t<float>(vec, act, training != 0, y, gamma, beta, running_mean, running_var, num_batches_tracked, out, save_mean, save_rstd, eps, momentum, (char*)workspace, dims, st);
+        case LMNET_BF16: return bn_fwd_t<__nv_bfloat16>(vec, act, training != 0, y, gamma, beta, running_mean, running_var, num_batches_tracked, out, save_mean, save_rstd, eps, momentum, (char*)workspace, dims, st);
+        case LMNET_F16: return bn_fwd_t<__half>(vec, act, training != 0, y, gamma, beta, running_mean, running_var, num_batches_tracked, out, save_mean, save_rstd, eps, momentum, (char*)workspace, dims, st);
+        default: return LMNET_ERR_UNSUPPORTED;
+    }
+}
+
+extern "C" int lmnet_bn_act_bwd(const void* y, const void* dout, const float* gamma, const float* beta,
+                                const float* save_mean, const float* save_rstd, void* dy, float* dgamma,
+                                float* dbeta, int act, void* workspace, size_t workspace_bytes,
+                                const lmnet_bn_dims* dims, int dtype, void* stream) {
+    int rc = bn_validate(dims);
+    if (rc != LMNET_OK) return rc;
+    if (!y || !dout || !dy || !save_mean || !save_rstd || !workspace) return LMNET_ERR_INVALID_ARG;
+    if (workspace_bytes < bn_ws(dims).total) return LMNET_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t es = dtype == LMNET_F32 ? 4 : 2;
+    const bool vec = bn_vec_ok(dims, es, {y, dout, dy});
+    switch (dtype) {
+        case LMNET_F32: return bn_bwd_t<float>(vec, act, y, dout, gamma, beta, save_mean, save_rstd, dy, dgamma, dbeta, (char*)workspace, dims, st);
+        case LMNET_BF16: return bn_bwd_t<__nv_bfloat16>(vec, act, y, dout, gamma, beta, save_mean, save_rstd, dy, dgamma, dbeta, (char*)workspace, dims, st);
+        case LMNET_F16: return bn_bwd_t<__half>(vec, act, y, dout, gamma, beta, save_mean, save_rstd, dy, dgamma, dbeta, (char*)workspace, dims, st);
+        default: return LMNET_ERR_UNSUPPORTED;
+    }
+}

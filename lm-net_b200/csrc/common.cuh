@@ -22,6 +22,8 @@ enum KernelId : int {
     KID_NA_PN, KID_NA_NN, KID_NA_IN, KID_NA_RPBGRAD, KID_NA_RPBGRAD_REDUCE,
     KID_DW_STATS, KID_DW_FIN_FWD, KID_DW_APPLY, KID_DW_POOL_FIN, KID_DW_COEF_EVAL,
     KID_DW_BWD_REDUCE, KID_DW_FIN_BWD, KID_DW_BWD_DX, KID_DW_BWD_DW, KID_DW_FIN_DW,
+    KID_BN_STATS, KID_BN_FIN_FWD, KID_BN_APPLY, KID_BN_BWD_REDUCE, KID_BN_FIN_BWD, KID_BN_BWD_APPLY,
+    KID_LN_FWD, KID_LN_BWD, KID_LN_BWD_PARAMS,
     KID_COUNT
 };
 extern bool g_profile_on;

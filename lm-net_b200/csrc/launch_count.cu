@@ -34,7 +34,9 @@ static const char* kKernelNames[KID_COUNT] = {
     "na2d_fwd", "na2d_bwd_query", "na2d_bwd_key", "na2d_drpb_reduce",
     "na2d_pn", "na2d_nn", "na2d_in", "na2d_rpbgrad", "na2d_rpbgrad_reduce",
     "dw_stats", "dw_fin_fwd", "dw_apply", "dw_pool_fin", "dw_coef_eval",
-    "dw_bwd_reduce", "dw_fin_bwd", "dw_bwd_dx", "dw_bwd_dw", "dw_fin_dw"};
+    "dw_bwd_reduce", "dw_fin_bwd", "dw_bwd_dx", "dw_bwd_dw", "dw_fin_dw",
+    "bn_stats", "bn_fin_fwd", "bn_apply", "bn_bwd_reduce", "bn_fin_bwd", "bn_bwd_apply",
+    "ln_fwd", "ln_bwd", "ln_bwd_params"};
 }  // namespace lmnet
 
 extern "C" int lmnet_profile_enable(int on) {

@@ -42,6 +42,13 @@ class DwDims(Structure):
     _fields_ = [("B", c_int32), ("E", c_int32), ("H", c_int32), ("W", c_int32)]
 
 
+class BnDims(Structure):
+    _fields_ = [("B", c_int32), ("C", c_int32), ("HW", c_int64)]
+
+
+ACT_CODES = {"none": 0, "hardswish": 1, "gelu": 2, "relu": 3}
+
+
 _lib = None
 
 
@@ -82,6 +89,11 @@ def lib():
                                              pg, c_void_p, c_size_t, pdd, c_int, c_void_p]
     L.lmnet_reparam_dw_eval_fwd.argtypes = [c_void_p, pp, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_size_t,
                                             pdd, c_int, c_void_p]
+    pbd = POINTER(BnDims)
+    L.lmnet_bn_act_workspace_bytes.restype = c_size_t
+    L.lmnet_bn_act_workspace_bytes.argtypes = [pbd]
+    L.lmnet_bn_act_fwd.argtypes = [c_void_p] * 9 + [c_float, c_float, c_int, c_int, c_void_p, c_size_t, pbd, c_int, c_void_p]
+    L.lmnet_bn_act_bwd.argtypes = [c_void_p] * 9 + [c_int, c_void_p, c_size_t, pbd, c_int, c_void_p]
     L.lmnet_profile_enable.argtypes = [c_int]
     L.lmnet_profile_kernel_name.restype = ctypes.c_char_p
     L.lmnet_profile_kernel_name.argtypes = [c_int]
@@ -183,4 +195,4 @@ def dw_grads(dw, dgamma, dbeta) -> DwGrads:
 
 
 __all__ = ["lib", "check", "dtype_code", "require_cuda", "stream_ptr", "ptr", "view5", "na_dims", "dw_params",
-           "dw_grads", "View5", "NADims", "DwParams", "DwGrads", "DwDims", "byref", "launch_count", "LIB_PATH"]
+           "dw_grads", "View5", "NADims", "DwParams", "DwGrads", "DwDims", "BnDims", "ACT_CODES", "byref", "launch_count", "LIB_PATH"]

@@ -24,6 +24,7 @@ from torch import nn
 
 from natten import NeighborhoodAttention2D
 
+from .bnact import conv_bn_act
 from .reparam import reparam_forward
 
 
@@ -163,7 +164,7 @@ class M3Skip(nn.Module):
         self.fuse_conv = nn.Sequential(nn.Conv2d(3 * mid, mid, 3, 1, 1), nn.BatchNorm2d(mid), nn.GELU())
 
     def forward(self, xl, xm, xs):
-        return self.fuse_conv(torch.cat([self.convl(xl), self.convm(xm), self.convs(xs)], dim=1))
+        return conv_bn_act(self.fuse_conv, torch.cat([self.convl(xl), self.convm(xm), self.convs(xs)], dim=1))
 
 
 class M2Skip(nn.Module):
@@ -184,7 +185,7 @@ class M2Skip(nn.Module):
         self.fuse_conv = nn.Sequential(nn.Conv2d(2 * width, width, 3, 1, 1), nn.BatchNorm2d(width), nn.GELU())
 
     def forward(self, xl, xs):
-        return self.fuse_conv(torch.cat([self.convl(xl), self.convs(xs)], dim=1))
+        return conv_bn_act(self.fuse_conv, torch.cat([self.convl(xl), self.convs(xs)], dim=1))
 
 
 class GlobalAttention(nn.Module):

@@ -21,6 +21,7 @@ import torch
 from torch.amp import custom_bwd, custom_fwd
 
 from . import _lib as L
+from .bnact import conv_bn_act
 
 
 def _dims(x):
@@ -181,7 +182,7 @@ def fused_dw_deploy(mod, x1):
 
 def reparam_forward(self, x):
     """Replacement for ReparamConv.forward (/root/reference/core/modules.py:586-600)."""
-    x1 = self.expand_conv(x)
+    x1 = conv_bn_act(self.expand_conv, x)          # 1x1 conv (cuDNN) + fused BatchNorm + Hardswish
     if self.deploy:
         z, pool = fused_dw_deploy(self, x1)
     else:

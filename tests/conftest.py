@@ -80,6 +80,15 @@ def cpu_backend(monkeypatch):
     for name, fn in dict(raw_fused_fwd=fused_fwd, raw_fused_bwd=fused_bwd, raw_qk_fwd=qk_fwd, raw_qk_bwd=qk_bwd,
                          raw_av_fwd=av_fwd, raw_av_bwd=av_bwd).items():
         monkeypatch.setattr(na_ops, name, fn)
+    import torch.nn.functional as F
+
+    from lmnet_b200 import bnact, model
+
+    def bn_act_ref(bn, y, act="none"):
+        out = bn(y)
+        return {"none": lambda t: t, "hardswish": F.hardswish, "gelu": F.gelu, "relu": F.relu}[act](out)
+
+    monkeypatch.setattr(bnact, "bn_act", bn_act_ref)
     monkeypatch.setattr(reparam, "fused_dw_bn_gelu", lambda mod, x1: reparam_ref.dw_bn_gelu(mod, x1))
     monkeypatch.setattr(reparam, "fused_dw_deploy", lambda mod, x1: reparam_ref.dw_bn_gelu(mod, x1))
     return o
