@@ -188,6 +188,18 @@ int lmnet_bn_act_bwd(const void* y, const void* dout, const float* gamma, const 
                      int act, void* workspace, size_t workspace_bytes, const lmnet_bn_dims* dims, int dtype,
                      void* stream);
 
+/* ---- LayerNorm over short channels-last rows (widening step f2, SURVEY.md §8 f) ------------------
+ * Replaces nn.LayerNorm(C) as used twice per NeighborhoodTransformer
+ * (/root/reference/core/modules.py:507, 510, 515-518) for C in {12, 24, 48, 96}.  x, y, dy, dx: [rows, C]
+ * contiguous of `dtype` (16-byte aligned); gamma/beta fp32 [C] or NULL; save_mean/save_rstd fp32 [rows]. */
+int lmnet_layer_norm_supported(int C);
+size_t lmnet_layer_norm_workspace_bytes(int64_t rows, int C);
+int lmnet_layer_norm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* save_mean,
+                         float* save_rstd, int64_t rows, int C, float eps, int dtype, void* stream);
+int lmnet_layer_norm_bwd(const void* x, const void* dy, const float* gamma, const float* save_mean,
+                         const float* save_rstd, void* dx, float* dgamma, float* dbeta,
+                         void* workspace, size_t workspace_bytes, int64_t rows, int C, int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -94,6 +94,11 @@ def lib():
     L.lmnet_bn_act_workspace_bytes.argtypes = [pbd]
     L.lmnet_bn_act_fwd.argtypes = [c_void_p] * 9 + [c_float, c_float, c_int, c_int, c_void_p, c_size_t, pbd, c_int, c_void_p]
     L.lmnet_bn_act_bwd.argtypes = [c_void_p] * 9 + [c_int, c_void_p, c_size_t, pbd, c_int, c_void_p]
+    L.lmnet_layer_norm_supported.argtypes = [c_int]
+    L.lmnet_layer_norm_workspace_bytes.restype = c_size_t
+    L.lmnet_layer_norm_workspace_bytes.argtypes = [c_int64, c_int]
+    L.lmnet_layer_norm_fwd.argtypes = [c_void_p] * 6 + [c_int64, c_int, c_float, c_int, c_void_p]
+    L.lmnet_layer_norm_bwd.argtypes = [c_void_p] * 8 + [c_void_p, c_size_t, c_int64, c_int, c_int, c_void_p]
     L.lmnet_profile_enable.argtypes = [c_int]
     L.lmnet_profile_kernel_name.restype = ctypes.c_char_p
     L.lmnet_profile_kernel_name.argtypes = [c_int]

@@ -25,6 +25,7 @@ from torch import nn
 from natten import NeighborhoodAttention2D
 
 from .bnact import conv_bn_act
+from .layernorm import layer_norm
 from .reparam import reparam_forward
 
 
@@ -143,8 +144,8 @@ class NeighborhoodTransformer(nn.Module):
 
     def forward(self, x):
         emb = self.patchembedding(x)
-        att = self.att1(self.norm1(emb)) + emb
-        y = self.mlp(self.norm2(att)) + att
+        att = self.att1(layer_norm(self.norm1, emb)) + emb
+        y = self.mlp(layer_norm(self.norm2, att)) + att
         return y.permute(0, 3, 1, 2).contiguous()
 
 

@@ -68,48 +68,105 @@ def train_step(model, optimizer, images, labels, criterion, criterion_dice, amp_
 
 
 class ConfusionMetrics:
-    """Accumulates a 2x2 confusion matrix on the CPU; compute() returns accuracy / Dice / IoU of class 1."""
+    """Accumulates a confusion matrix; compute() returns accuracy / Dice / IoU of class 1.
+
+    Duck-types the torchmetrics collection the reference passes around (reset / update / compute / to).
+    update() accepts tensors on any device; with CUDA tensors the 2x2 histogram is built on the GPU and
+    stays there until compute(), so the training loop needs no per-step D2H of the [B,H,W] mask."""
 
     def __init__(self, num_classes=2):
         self.n = num_classes
+        self.cm = None
         self.reset()
 
     def to(self, _device):
         return self
 
     def reset(self):
-        self.cm = torch.zeros(self.n * self.n, dtype=torch.int64)
+        self.cm = None
 
     def update(self, pred, labels):
-        self.cm += torch.bincount((labels.reshape(-1) * self.n + pred.reshape(-1)), minlength=self.n * self.n)
+        idx = labels.reshape(-1) * self.n + pred.reshape(-1)
+        cm = torch.bincount(idx, minlength=self.n * self.n)
+        self.cm = cm if self.cm is None else self.cm + cm.to(self.cm.device)
 
     def compute(self):
-        cm = self.cm.view(self.n, self.n).double()
+        cm = torch.zeros(self.n * self.n) if self.cm is None else self.cm.cpu()
+        cm = cm.view(self.n, self.n).double()
         tp, fp, fn = cm[1, 1], cm[0, 1], cm[1, 0]
         return {"acc": float(cm.diag().sum() / cm.sum().clamp_min(1)),
                 "dice": float(2 * tp / (2 * tp + fp + fn).clamp_min(1)),
                 "iou": float(tp / (tp + fp + fn).clamp_min(1))}
 
 
+class _Prefetcher:
+    """Copies the next host batch to the device on a side stream while the current step computes."""
+
+    def __init__(self, loader, device):
+        self.it, self.device = iter(loader), torch.device(device)
+        self.stream = torch.cuda.Stream(self.device) if self.device.type == "cuda" else None
+        self.next = None
+        self._load()
+
+    def _load(self):
+        try:
+            images, labels = next(self.it)
+        except StopIteration:
+            self.next = None
+            return
+        if self.stream is None:
+            self.next = (images.to(self.device), labels.to(self.device))
+            return
+        with torch.cuda.stream(self.stream):
+            self.next = (images.to(self.device, non_blocking=True), labels.to(self.device, non_blocking=True))
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        if self.next is None:
+            raise StopIteration
+        if self.stream is not None:
+            torch.cuda.current_stream(self.device).wait_stream(self.stream)
+        batch = self.next
+        for t in batch:
+            if t.is_cuda:
+                t.record_stream(torch.cuda.current_stream(self.device))
+        self._load()
+        return batch
+
+
 def train_one_epoch(model, optimizer, metric_collection=None, num_classes=2, data_loader=None, device=0,
-                    criterion=None, scaler=None, criterion_dice=None, amp_dtype=torch.bfloat16):
-    """Reference-shaped epoch loop.  `scaler` is accepted for signature compatibility; a non-None value
-    selects the autocast branch exactly as in the reference, but with bf16 no loss scaling is needed."""
+                    criterion=None, scaler=None, criterion_dice=None, amp_dtype=torch.bfloat16,
+                    metrics_on_device=True, prefetch=True):
+    """Reference-shaped epoch loop (utils/train_eval_utils.py:120-166): H2D copy of every batch, autocast
+    forward, CE + Dice(weight [1,4]), zero_grad, backward, step, loss.item() every step, argmax ->
+    metric update.  `scaler` is accepted for signature compatibility; a non-None value selects the
+    autocast branch exactly as in the reference, but with bf16 no loss scaling is needed.
+
+    Two host-side overheads of the reference loop are removed without changing what
+    is computed: the next batch is copied on a side stream while the current step runs (`prefetch`), and
+    the confusion matrix is accumulated on the GPU instead of shipping the [B,H,W] int64 mask to the CPU
+    every step (`metrics_on_device`; set False for the reference's exact D2H behaviour)."""
     model.train()
     if metric_collection is not None:
         metric_collection.reset()
     total_loss = 0.0
     use_amp = scaler is not None
-    for images, labels in data_loader:
-        images = images.to(device, non_blocking=True)
-        labels = labels.to(device, non_blocking=True)
+    dev = torch.device(device if not isinstance(device, int) else f"cuda:{device}")
+    batches = _Prefetcher(data_loader, dev) if prefetch else (
+        (i.to(dev, non_blocking=True), l.to(dev, non_blocking=True)) for i, l in data_loader)
+    for images, labels in batches:
         loss, output = train_step(model, optimizer, images, labels, criterion, criterion_dice,
                                   amp_dtype if use_amp else None)
         with torch.no_grad():
-            total_loss += loss.item()
             if metric_collection is not None:
-                pred = output.argmax(1).detach().cpu()
-                metric_collection.update(pred, labels.detach().cpu())
+                pred = output.argmax(1).detach()
+                if metrics_on_device:
+                    metric_collection.update(pred, labels)
+                else:
+                    metric_collection.update(pred.cpu(), labels.detach().cpu())
+            total_loss += loss.item()
     return total_loss
 
 

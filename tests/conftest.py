@@ -9,7 +9,8 @@ import sys
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-for p in (ROOT, os.path.join(ROOT, "lm-net_b200")):
+TESTS = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "lm-net_b200"), TESTS):
     if p not in sys.path:
         sys.path.insert(0, p)
 
@@ -32,63 +33,8 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture
 def cpu_backend(monkeypatch):
     """TEST-ONLY: lets the *host-side* Python (modules, autograd plumbing, layout handling) run on a
-    machine without a GPU by answering the raw C-ABI launches with the CPU oracle.  The product has no
-    such path — outside this fixture CPU tensors raise."""
-    import torch
+    machine without a GPU by answering the raw C-ABI launches with the CPU oracle (tests/_cpu_backend.py).
+    The product has no such path — outside this fixture CPU tensors raise."""
+    import _cpu_backend
 
-    from lmnet_b200 import _lib, na_ops, reparam
-    from oracle import na2d_ref, reparam_ref
-
-    o = na2d_ref.c_oracle()
-    monkeypatch.setattr(_lib, "require_cuda", lambda *a: None)
-
-    def c32(t):   # oracle precision: fp64 stays fp64, everything else runs in fp32
-        t = t.detach()
-        return (t if t.dtype == torch.float64 else t.float()).contiguous()
-
-    def rp(rpb32, like):
-        if rpb32 is None:
-            return None
-        return rpb32.double() if like.dtype == torch.float64 else rpb32
-
-    def fused_fwd(q, k, v, rpb32, out, K, d, scale, order="bhwnd", lse=None):
-        assert order == "bhwnd"
-        out.copy_(o.fused_fwd(c32(q), c32(k), c32(v), rp(rpb32, q), K, d, scale).to(out.dtype))
-
-    def fused_bwd(q, k, v, rpb32, dout, dq, dk, dv, drpb, K, d, scale, order="bhwnd"):
-        gq, gk, gv, gr = o.fused_bwd(c32(q), c32(k), c32(v), rp(rpb32, q), c32(dout), K, d, scale)
-        dq.copy_(gq.to(dq.dtype)), dk.copy_(gk.to(dk.dtype)), dv.copy_(gv.to(dv.dtype))
-        if drpb is not None:
-            drpb.copy_(gr)
-
-    def qk_fwd(q, k, rpb32, attn, K, d):
-        attn.copy_(o.qk_fwd(c32(q), c32(k), rp(rpb32, q), K, d).to(attn.dtype))
-
-    def qk_bwd(q, k, dattn, dq, dk, drpb, K, d):
-        gq, gk, gr = o.qk_bwd(c32(q), c32(k), c32(dattn), K, d, drpb is not None)
-        dq.copy_(gq.to(dq.dtype)), dk.copy_(gk.to(dk.dtype))
-        if drpb is not None:
-            drpb.copy_(gr)
-
-    def av_fwd(attn, v, out, K, d):
-        out.copy_(o.av_fwd(c32(attn), c32(v), K, d).to(out.dtype))
-
-    def av_bwd(attn, v, dout, dattn, dv, K, d):
-        ga, gv = o.av_bwd(c32(attn), c32(v), c32(dout), K, d)
-        dattn.copy_(ga.to(dattn.dtype)), dv.copy_(gv.to(dv.dtype))
-
-    for name, fn in dict(raw_fused_fwd=fused_fwd, raw_fused_bwd=fused_bwd, raw_qk_fwd=qk_fwd, raw_qk_bwd=qk_bwd,
-                         raw_av_fwd=av_fwd, raw_av_bwd=av_bwd).items():
-        monkeypatch.setattr(na_ops, name, fn)
-    import torch.nn.functional as F
-
-    from lmnet_b200 import bnact, model
-
-    def bn_act_ref(bn, y, act="none"):
-        out = bn(y)
-        return {"none": lambda t: t, "hardswish": F.hardswish, "gelu": F.gelu, "relu": F.relu}[act](out)
-
-    monkeypatch.setattr(bnact, "bn_act", bn_act_ref)
-    monkeypatch.setattr(reparam, "fused_dw_bn_gelu", lambda mod, x1: reparam_ref.dw_bn_gelu(mod, x1))
-    monkeypatch.setattr(reparam, "fused_dw_deploy", lambda mod, x1: reparam_ref.dw_bn_gelu(mod, x1))
-    return o
+    return _cpu_backend.apply(monkeypatch.setattr)
