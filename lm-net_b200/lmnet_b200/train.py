@@ -138,7 +138,7 @@ class _Prefetcher:
 
 def train_one_epoch(model, optimizer, metric_collection=None, num_classes=2, data_loader=None, device=0,
                     criterion=None, scaler=None, criterion_dice=None, amp_dtype=torch.bfloat16,
-                    metrics_on_device=True, prefetch=True):
+                    metrics_on_device=True, prefetch=True, defer_loss_read=True):
     """Reference-shaped epoch loop (utils/train_eval_utils.py:120-166): H2D copy of every batch, autocast
     forward, CE + Dice(weight [1,4]), zero_grad, backward, step, loss.item() every step, argmax ->
     metric update.  `scaler` is accepted for signature compatibility; a non-None value selects the
@@ -147,7 +147,8 @@ def train_one_epoch(model, optimizer, metric_collection=None, num_classes=2, dat
     Two host-side overheads of the reference loop are removed without changing what
     is computed: the next batch is copied on a side stream while the current step runs (`prefetch`), and
     the confusion matrix is accumulated on the GPU instead of shipping the [B,H,W] int64 mask to the CPU
-    every step (`metrics_on_device`; set False for the reference's exact D2H behaviour)."""
+    every step (`metrics_on_device`; set False for the reference's exact D2H behaviour).  `defer_loss_read` reads
+    each step's loss one step late (same values, same total)."""
     model.train()
     if metric_collection is not None:
         metric_collection.reset()
@@ -156,6 +157,11 @@ def train_one_epoch(model, optimizer, metric_collection=None, num_classes=2, dat
     dev = torch.device(device if not isinstance(device, int) else f"cuda:{device}")
     batches = _Prefetcher(data_loader, dev) if prefetch else (
         (i.to(dev, non_blocking=True), l.to(dev, non_blocking=True)) for i, l in data_loader)
+    # loss.item() every step, as in the reference — but read one step late through pinned memory, so the
+    # host keeps enqueueing the next step instead of draining the GPU pipeline at every iteration
+    pipelined = dev.type == "cuda" and defer_loss_read
+    slots = [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(2)] if pipelined else None
+    pending, step = None, 0
     for images, labels in batches:
         loss, output = train_step(model, optimizer, images, labels, criterion, criterion_dice,
                                   amp_dtype if use_amp else None)
@@ -166,7 +172,21 @@ def train_one_epoch(model, optimizer, metric_collection=None, num_classes=2, dat
                     metric_collection.update(pred, labels)
                 else:
                     metric_collection.update(pred.cpu(), labels.detach().cpu())
-            total_loss += loss.item()
+            if pipelined:
+                slot = slots[step % 2]
+                slot.copy_(loss.detach().float(), non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
+                if pending is not None:
+                    pending[1].synchronize()
+                    total_loss += float(pending[0])
+                pending = (slot, ev)
+            else:
+                total_loss += loss.item()
+        step += 1
+    if pending is not None:
+        pending[1].synchronize()
+        total_loss += float(pending[0])
     return total_loss
 
 
