@@ -200,6 +200,23 @@ int lmnet_layer_norm_bwd(const void* x, const void* dy, const float* gamma, cons
                          const float* save_rstd, void* dx, float* dgamma, float* dbeta,
                          void* workspace, size_t workspace_bytes, int64_t rows, int C, int dtype, void* stream);
 
+/* ---- weight / bias gradients of 1x1 convolutions on NCHW tensors (widening step f1) -------------
+ * For the 1x1 convolutions of ReparamConv (/root/reference/core/modules.py:537, 576-584): forward and
+ * input gradients are plain GEMMs on the NCHW planes (cuBLAS via torch.bmm on the host side); this entry
+ * point is the pixel-reduction GEMM cuBLAS serves badly:
+ *     dW[b][m][n] = sum_p A[b][m][p] * Bt[b][n][p],   drow[b][m] = sum_p A[b][m][p]
+ * A = grad_output [B,M,P]; Bt = layer input, rows [0,N1) from B1 [B,N1,P] and [N1,N1+N2) from B2 [B,N2,P]
+ * (B2 may be NULL when N2 == 0).  16-bit dtypes, P % 8 == 0, 16-byte aligned tensors; outputs fp32, per batch
+ * item (dW [B,M,N1+N2], drow [B,M] or NULL).  lmnet_wgrad_1x1_supported() tells whether a shape is covered. */
+typedef struct lmnet_wgrad_dims {
+    int32_t B, M, N1, N2;
+    int64_t P;
+} lmnet_wgrad_dims;
+int lmnet_wgrad_1x1_supported(const lmnet_wgrad_dims* dims, int dtype);
+size_t lmnet_wgrad_1x1_workspace_bytes(const lmnet_wgrad_dims* dims);
+int lmnet_wgrad_1x1(const void* A, const void* B1, const void* B2, float* dW, float* drow,
+                    void* workspace, size_t workspace_bytes, const lmnet_wgrad_dims* dims, int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -36,7 +36,8 @@ static const char* kKernelNames[KID_COUNT] = {
     "dw_stats", "dw_fin_fwd", "dw_apply", "dw_pool_fin", "dw_coef_eval",
     "dw_bwd_reduce", "dw_fin_bwd", "dw_bwd_dx", "dw_bwd_dw", "dw_fin_dw",
     "bn_stats", "bn_fin_fwd", "bn_apply", "bn_bwd_reduce", "bn_fin_bwd", "bn_bwd_apply",
-    "ln_fwd", "ln_bwd", "ln_bwd_params"};
+    "ln_fwd", "ln_bwd", "ln_bwd_params",
+    "wgrad_1x1", "wgrad_reduce"};
 }  // namespace lmnet
 
 extern "C" int lmnet_profile_enable(int on) {

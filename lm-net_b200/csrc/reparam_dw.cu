@@ -21,6 +21,7 @@
 // every (col, col+1) pair is an aligned 64-bit shared load.  A CTA owns one channel, one column
 // stripe and one band of rows, and loops over the batch, so per-channel reductions need no atomics:
 // per-CTA partials are reduced by the finalize kernels in a fixed order (deterministic).
+#include <cstdlib>
 #include <type_traits>
 
 #include "common.cuh"
@@ -801,6 +802,10 @@ __global__ void dw_fin_dw_kernel(const float* __restrict__ part, int ncta, const
     if (gr.dw[k] != nullptr) gr.dw[k][e * per + idx] = val;
 }
 
+}  // namespace lmnet
+#include "reparam_dw_mma.cuh"
+namespace lmnet {
+
 // =================================================================================================
 // host side
 // =================================================================================================
@@ -853,6 +858,12 @@ static int dw_vec_bytes(const void* const* ptrs, int n, const lmnet_dw_dims* d, 
     }
     return 0;
 }
+// the tensor-core kernels need 16-bit storage, an even row length and 4-byte aligned planes
+template <typename T>
+static bool dw_mma_ok(const lmnet_dw_dims* d, const void* x) {
+    if (sizeof(T) != 2 || getenv("LMNET_DW_NO_MMA") != nullptr) return false;
+    return (d->W % 2 == 0) && ((uintptr_t)x % 4 == 0);
+}
 template <typename T, typename F>
 static int with_vec(int vec_bytes, F&& f) {
     // the loaders move 4, 2 or 1 elements per lane (one float4 / float2 / float shared store each)
@@ -877,7 +888,12 @@ static int dw_train_fwd(const void* x, const lmnet_dw_params* p, void* u, void* 
     float* pool_part = (float*)(ws + L.pool_part);
     const void* vp[1] = {x};
     const int vb = dw_vec_bytes(vp, 1, d, sizeof(T));
-    int rc = with_vec<T>(vb, [&](auto v) -> int {
+    const bool use_mma = dw_mma_ok<T>(d, x);
+    int rc = LMNET_OK;
+    if constexpr (sizeof(T) == 2) {
+        if (use_mma) LMNET_LAUNCH(KID_DW_STATS, st, 1 * t_bytes, (dw_stats_mma_kernel<T><<<grid, kDwThreads, 0, st>>>((const T*)x, *p, part, g)));
+    }
+    if (!use_mma) rc = with_vec<T>(vb, [&](auto v) -> int {
         constexpr int VEC = decltype(v)::value;
         LMNET_LAUNCH(KID_DW_STATS, st, 1 * t_bytes, (dw_stats_kernel<T, VEC><<<grid, kDwThreads, 0, st>>>((const T*)x, *p, part, g)));
         return LMNET_OK;
@@ -886,7 +902,10 @@ static int dw_train_fwd(const void* x, const lmnet_dw_params* p, void* u, void* 
     LMNET_LAUNCH(KID_DW_FIN_FWD, st, 0, (dw_fin_fwd_kernel<<<(g.E + 63) / 64, 64, 0, st>>>(part, ncta, *p, save_mean, save_rstd, coef, eps, momentum,
                                                      nbt ? nbt[0] : nullptr, nbt ? nbt[1] : nullptr,
                                                      nbt ? nbt[2] : nullptr, nbt ? nbt[3] : nullptr, g)));
-    rc = with_vec<T>(vb, [&](auto v) -> int {
+    if constexpr (sizeof(T) == 2) {
+        if (use_mma) LMNET_LAUNCH(KID_DW_APPLY, st, 2 * t_bytes, (dw_apply_mma_kernel<T><<<grid, kDwThreads, 0, st>>>((const T*)x, coef, (T*)u, (T*)z, pool ? pool_part : nullptr, g)));
+    }
+    if (!use_mma) rc = with_vec<T>(vb, [&](auto v) -> int {
         constexpr int VEC = decltype(v)::value;
         LMNET_LAUNCH(KID_DW_APPLY, st, 2 * t_bytes, (dw_apply_kernel<T, VEC><<<grid, kDwThreads, 0, st>>>((const T*)x, coef, (T*)u, (T*)z, pool ? pool_part : nullptr, g)));
         return LMNET_OK;
@@ -913,7 +932,12 @@ static int dw_eval_fwd(const void* x, const lmnet_dw_params* p, const float* bia
     LMNET_LAUNCH(KID_DW_COEF_EVAL, st, 0, (dw_coef_eval_kernel<<<(g.E + 63) / 64, 64, 0, st>>>(*p, bias, eps, coef, g.E)));
     const void* vp[1] = {x};
     const int vb = dw_vec_bytes(vp, 1, d, sizeof(T));
-    int rc = with_vec<T>(vb, [&](auto v) -> int {
+    const bool use_mma = dw_mma_ok<T>(d, x);
+    int rc = LMNET_OK;
+    if constexpr (sizeof(T) == 2) {
+        if (use_mma) LMNET_LAUNCH(KID_DW_APPLY, st, 2 * t_bytes, (dw_apply_mma_kernel<T><<<grid, kDwThreads, 0, st>>>((const T*)x, coef, (T*)nullptr, (T*)z, pool ? pool_part : nullptr, g)));
+    }
+    if (!use_mma) rc = with_vec<T>(vb, [&](auto v) -> int {
         constexpr int VEC = decltype(v)::value;
         LMNET_LAUNCH(KID_DW_APPLY, st, 2 * t_bytes, (dw_apply_kernel<T, VEC><<<grid, kDwThreads, 0, st>>>((const T*)x, coef, (T*)nullptr, (T*)z, pool ? pool_part : nullptr, g)));
         return LMNET_OK;

@@ -1,0 +1,285 @@
+// reparam_dw_mma.cuh — tensor-core (HMMA) versions of the depthwise branch kernels for 16-bit storage.
+//
+// Why: per 2-byte element the branch section needs 40 taps (statistics) / 25 taps + erf (apply); on the
+// fp32 pipe that is >= 40 FLOP/B, far above its ~11 FLOP/B ridge, so the FFMA2 kernels of
+// reparam_dw.cu are FP32-issue bound at < 10 % of HBM peak (profiles/r01_ncu_dw_*).  A depthwise
+// stencil is a product with a banded Toeplitz matrix: for each row offset a,
+//     Y[r][c] += sum_k X[r+a][k] * T_a[k][c],   T_a[k][c] = w[a][k-c] for 0 <= k-c <= 4, else 0,
+// which is an m16n8k16 MMA with M = 16 image rows, K = 16 input columns, N = 8 output columns.
+// 5 MMAs give the 5x5 branch of a 16x8 output block (12 MMAs give all four branches), the
+// accumulators stay fp32, the operands are exactly what the reference's bf16 cuDNN path uses (bf16
+// activations, bf16-rounded weights, fp32 accumulate).  The A fragments come straight out of the bf16
+// image tile in shared memory via ldmatrix (no fp32 staging, half the shared-memory traffic); the B
+// fragments (Toeplitz bands) are built once per CTA in registers.
+//
+// Scope note (tier rules): this is NOT a reshaping of a bandwidth-bound kernel into a GEMM to "reach
+// tensor cores" — it moves a compute-bound stencil off the saturated fp32 pipe so that it can become
+// bandwidth-bound at all.  mma.sync is used (per-warp 16x8 blocks with halo reuse fit it naturally;
+// tcgen05's 128-row TMEM tiles do not help a 5-tap band).
+#pragma once
+#include "common.cuh"
+
+namespace lmnet {
+
+constexpr int kMmaPitch = 72;                 // bf16 elements per shared row (144 B: conflict-free ldmatrix)
+constexpr int kMmaTH = 32, kMmaTW = 64;       // output tile
+constexpr int kMmaTileRows = kMmaTH + 4;
+constexpr int kMmaPairs = kMmaPitch / 2;      // 32-bit pairs per row
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* p) {
+    const uint32_t addr = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+template <typename T> struct MmaOp;
+template <> struct MmaOp<__nv_bfloat16> {
+    __device__ __forceinline__ static void run(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                     : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+    }
+    __device__ __forceinline__ static uint32_t pack(float lo, float hi) {
+        __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+        return *reinterpret_cast<uint32_t*>(&v);
+    }
+    __device__ __forceinline__ static float round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+};
+template <> struct MmaOp<__half> {
+    __device__ __forceinline__ static void run(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                     : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+    }
+    __device__ __forceinline__ static uint32_t pack(float lo, float hi) {
+        __half2 v = __floats2half2_rn(lo, hi);
+        return *reinterpret_cast<uint32_t*>(&v);
+    }
+    __device__ __forceinline__ static float round(float x) { return __half2float(__float2half_rn(x)); }
+};
+
+// B fragment of the Toeplitz band of one kernel row: taps[j] multiplies input column (c + j + shift).
+// For lane (g = lane/4, t = lane%4): b0 = T[2t][g], b1 = T[2t+1][g], b2 = T[2t+8][g], b3 = T[2t+9][g],
+// T[k][c] = taps[k - c - shift] when 0 <= k-c-shift < ntaps.
+template <typename T>
+__device__ __forceinline__ void toeplitz_frag(const float* taps, int ntaps, int shift, int lane, uint32_t (&b)[2]) {
+    const int g = lane >> 2, t = lane & 3;
+    auto tap = [&](int k) -> float {
+        const int j = k - g - shift;
+        return (j >= 0 && j < ntaps) ? taps[j] : 0.f;
+    };
+    b[0] = MmaOp<T>::pack(tap(2 * t), tap(2 * t + 1));
+    b[1] = MmaOp<T>::pack(tap(2 * t + 8), tap(2 * t + 9));
+}
+
+// Raw 16-bit tile (rows x kMmaPitch) staged with 32-bit accesses: index i of a row <-> image column c0 + i.
+template <typename T, int ROWS>
+struct MmaTileLoader {
+    static constexpr int N = (ROWS * kMmaPairs + kDwThreads - 1) / kDwThreads;
+    uint32_t raw[N];
+    __device__ __forceinline__ void fetch(const T* __restrict__ plane, int H, int W, int r0, int c0) {
+#pragma unroll
+        for (int u = 0; u < N; ++u) {
+            const int idx = threadIdx.x + u * kDwThreads;
+            const int r = idx / kMmaPairs, v = idx - r * kMmaPairs;
+            const int gr = r0 + r, gc = c0 + 2 * v;
+            uint32_t val = 0u;
+            if (idx < ROWS * kMmaPairs && gr >= 0 && gr < H && gc >= 0 && gc + 2 <= W)
+                val = __ldg(reinterpret_cast<const uint32_t*>(plane + (int64_t)gr * W + gc));
+            raw[u] = val;
+        }
+    }
+    __device__ __forceinline__ void commit(T* s) const {
+#pragma unroll
+        for (int u = 0; u < N; ++u) {
+            const int idx = threadIdx.x + u * kDwThreads;
+            if (idx < ROWS * kMmaPairs) reinterpret_cast<uint32_t*>(s)[idx] = raw[u];
+        }
+    }
+};
+
+template <typename T, int ROWS, typename PlaneFn, typename Body>
+__device__ __forceinline__ void mma_for_each_tile(const DwGeom& g, int band0, int band1, int th, int halo, int c0,
+                                                  T* s_tile, PlaneFn&& plane_of, Body&& body) {
+    const int ntr = (band1 - band0 + th - 1) / th;
+    const int total = band1 > band0 ? g.B * ntr : 0;
+    MmaTileLoader<T, ROWS> ld;
+    if (total > 0) ld.fetch(plane_of(0), g.H, g.W, band0 - halo, c0 - halo);
+    for (int t = 0; t < total; ++t) {
+        const int b = t / ntr, k = t - b * ntr;
+        __syncthreads();
+        ld.commit(s_tile);
+        __syncthreads();
+        if (t + 1 < total) {
+            const int nb = (t + 1) / ntr, nk = (t + 1) - nb * ntr;
+            ld.fetch(plane_of(nb), g.H, g.W, band0 + nk * th - halo, c0 - halo);
+        }
+        body(b, band0 + k * th, k == ntr - 1);
+    }
+}
+
+// A fragment: 16 rows starting at tile row `row`, 16 input columns starting at tile index `col`
+template <typename T>
+__device__ __forceinline__ void load_a(const T* s_tile, int row, int col, int lane, uint32_t (&a)[4]) {
+    const int m = lane >> 3, rr = lane & 7;
+    ldmatrix_x4(a, s_tile + (row + (m & 1) * 8 + rr) * kMmaPitch + col + (m >> 1) * 8);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// statistics pass: per-channel sum / sum of squares of the four branch outputs
+// ---------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kDwThreads)
+dw_stats_mma_kernel(const T* __restrict__ x, lmnet_dw_params p, float* __restrict__ part /* [E][ncta][8] */, DwGeom g) {
+    __shared__ __align__(16) T s_tile[kMmaTileRows * kMmaPitch];
+    __shared__ float s_red[kDwWarps * 8];
+    const int e = blockIdx.z, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wr = warp >> 1, wc = warp & 1;               // warp owns rows 16*wr.., columns 32*wc..
+    const int c0 = blockIdx.x * kMmaTW;
+    const int band0 = blockIdx.y * g.rows_per_band, band1 = min(band0 + g.rows_per_band, g.H);
+    // Toeplitz fragments: 5x5 rows a=0..4; 3x3 / 3x1 rows a=1..3; 1x3 row a=2
+    uint32_t B5[5][2], B3[3][2], B31[3][2], B13[2];
+    {
+        float w5[25], w3[9], w31[3], w13[3];
+#pragma unroll
+        for (int t = 0; t < 25; ++t) w5[t] = __ldg(p.w[0] + e * 25 + t);
+#pragma unroll
+        for (int t = 0; t < 9; ++t) w3[t] = __ldg(p.w[1] + e * 9 + t);
+#pragma unroll
+        for (int t = 0; t < 3; ++t) { w31[t] = __ldg(p.w[2] + e * 3 + t); w13[t] = __ldg(p.w[3] + e * 3 + t); }
+#pragma unroll
+        for (int a = 0; a < 5; ++a) toeplitz_frag<T>(w5 + a * 5, 5, 0, lane, B5[a]);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            toeplitz_frag<T>(w3 + a * 3, 3, 1, lane, B3[a]);
+            toeplitz_frag<T>(w31 + a, 1, 2, lane, B31[a]);
+        }
+        toeplitz_frag<T>(w13, 3, 1, lane, B13);
+    }
+    float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
+    const int gq = lane >> 2, tq = lane & 3;
+    mma_for_each_tile<T, kMmaTileRows>(
+        g, band0, band1, kMmaTH, 2, c0, s_tile,
+        [&](int b) { return x + ((int64_t)b * g.E + e) * g.H * g.W; },
+        [&](int, int tr, bool) {
+            const int row_lo = tr + 16 * wr + gq;            // image rows of c0/c1 and (+8) c2/c3
+            const float rm0 = row_lo < band1 ? 1.f : 0.f, rm1 = row_lo + 8 < band1 ? 1.f : 0.f;
+#pragma unroll
+            for (int cb = 0; cb < 4; ++cb) {
+                float acc[4][4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) acc[k][0] = acc[k][1] = acc[k][2] = acc[k][3] = 0.f;
+                const int tcol = 32 * wc + 8 * cb;           // tile index of input column (cb_col - 2)
+#pragma unroll
+                for (int a = 0; a < 5; ++a) {
+                    uint32_t A[4];
+                    load_a(s_tile, 16 * wr + a, tcol, lane, A);
+                    MmaOp<T>::run(acc[0], A, B5[a]);
+                    if (a >= 1 && a <= 3) {
+                        MmaOp<T>::run(acc[1], A, B3[a - 1]);
+                        MmaOp<T>::run(acc[2], A, B31[a - 1]);
+                    }
+                    if (a == 2) MmaOp<T>::run(acc[3], A, B13);
+                }
+                const int col = c0 + tcol + 2 * tq;
+                const float cm0 = col < g.W ? 1.f : 0.f, cm1 = col + 1 < g.W ? 1.f : 0.f;
+                const float m[4] = {rm0 * cm0, rm0 * cm1, rm1 * cm0, rm1 * cm1};
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float y = acc[k][i] * m[i];
+                        s[k] += y;
+                        ss[k] = fmaf(y, acc[k][i], ss[k]);
+                    }
+            }
+        });
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { v[k] = s[k]; v[4 + k] = ss[k]; }
+    const int ncta = gridDim.x * gridDim.y, cta = blockIdx.y * gridDim.x + blockIdx.x;
+    block_sum<8>(v, s_red, part + ((int64_t)e * ncta + cta) * 8);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// apply pass: u = merged5x5(x) + bias; z = GELU(u); pool partial sums.  The merged fp32 taps are split
+// into hi + lo 16-bit parts (two MMAs per kernel row) so that folding the BatchNorm scales adds no
+// rounding beyond fp32.
+// ---------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kDwThreads)
+dw_apply_mma_kernel(const T* __restrict__ x, const float* __restrict__ coef, T* __restrict__ u_out, T* __restrict__ z_out,
+                    float* __restrict__ pool_part, DwGeom g) {
+    __shared__ __align__(16) T s_tile[kMmaTileRows * kMmaPitch];
+    __shared__ float s_red[kDwWarps];
+    const int e = blockIdx.z, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wr = warp >> 1, wc = warp & 1;
+    const int c0 = blockIdx.x * kMmaTW;
+    const int band0 = blockIdx.y * g.rows_per_band, band1 = min(band0 + g.rows_per_band, g.H);
+    uint32_t Bhi[5][2], Blo[5][2];
+    {
+        float wm[25], hi[5], lo[5];
+#pragma unroll
+        for (int t = 0; t < 25; ++t) wm[t] = __ldg(coef + e * 26 + t);
+#pragma unroll
+        for (int a = 0; a < 5; ++a) {
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+                hi[j] = MmaOp<T>::round(wm[a * 5 + j]);
+                lo[j] = wm[a * 5 + j] - hi[j];
+            }
+            toeplitz_frag<T>(hi, 5, 0, lane, Bhi[a]);
+            toeplitz_frag<T>(lo, 5, 0, lane, Blo[a]);
+        }
+    }
+    const float bias = __ldg(coef + e * 26 + 25);
+    const int gq = lane >> 2, tq = lane & 3;
+    const int ncta = gridDim.x * gridDim.y, cta = blockIdx.y * gridDim.x + blockIdx.x;
+    float psum = 0.f;
+    mma_for_each_tile<T, kMmaTileRows>(
+        g, band0, band1, kMmaTH, 2, c0, s_tile,
+        [&](int b) { return x + ((int64_t)b * g.E + e) * g.H * g.W; },
+        [&](int b, int tr, bool last) {
+            const int64_t poff = ((int64_t)b * g.E + e) * g.H * g.W;
+            const int row_lo = tr + 16 * wr + gq;
+#pragma unroll
+            for (int cb = 0; cb < 4; ++cb) {
+                float acc[4] = {bias, bias, bias, bias};
+                const int tcol = 32 * wc + 8 * cb;
+#pragma unroll
+                for (int a = 0; a < 5; ++a) {
+                    uint32_t A[4];
+                    load_a(s_tile, 16 * wr + a, tcol, lane, A);
+                    MmaOp<T>::run(acc, A, Bhi[a]);
+                    MmaOp<T>::run(acc, A, Blo[a]);
+                }
+                const int col = c0 + tcol + 2 * tq;
+                if (col < g.W) {                          // W is even on this path: the pair is all in or all out
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int row = row_lo + 8 * h;
+                        if (row < band1) {
+                            const int64_t off = poff + (int64_t)row * g.W + col;
+                            const uint32_t up = MmaOp<T>::pack(acc[2 * h], acc[2 * h + 1]);
+                            if (u_out != nullptr) *reinterpret_cast<uint32_t*>(u_out + off) = up;
+                            const T* ur = reinterpret_cast<const T*>(&up);
+                            const uint32_t zp = MmaOp<T>::pack(gelu_f(to_f(ur[0])), gelu_f(to_f(ur[1])));
+                            *reinterpret_cast<uint32_t*>(z_out + off) = zp;
+                            const T* zr = reinterpret_cast<const T*>(&zp);
+                            psum += to_f(zr[0]) + to_f(zr[1]);
+                        }
+                    }
+                }
+            }
+            if (last && pool_part != nullptr) {
+                float t = warp_sum(psum);
+                psum = 0.f;
+                __syncthreads();
+                if (lane == 0) s_red[warp] = t;
+                __syncthreads();
+                if (threadIdx.x == 0)
+                    pool_part[((int64_t)b * g.E + e) * ncta + cta] = s_red[0] + s_red[1] + s_red[2] + s_red[3];
+            }
+        });
+}
+
+}  // namespace lmnet

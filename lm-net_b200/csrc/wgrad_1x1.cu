@@ -1,0 +1,296 @@
+// wgrad_1x1.cu — weight / bias gradients of 1x1 convolutions on NCHW tensors (sm_100a, 16-bit storage).
+//
+// Widening step f1 of SURVEY.md §8 (rest of ReparamConv: expand 1x1, pointwise 1x1, shortcut 1x1,
+// /root/reference/core/modules.py:537, 576-584, 587, 598-599).  Forward and input gradients of a 1x1
+// convolution on NCHW data are plain GEMMs whose big operand is already laid out right (cuBLAS via
+// torch.bmm).  The WEIGHT gradient is the awkward one:
+//     dW[b][m][n] = sum_p A[b][m][p] * Bt[b][n][p]          (A = grad_output, Bt = layer input)
+// — a tiny M x N result reduced over K = H*W up to 124k pixels.  cuBLAS has no good kernel for it (7 ms
+// of a 70 ms step in profiles/r01_step_profile_c_*).  Here both operands are K-contiguous, i.e. exactly
+// the row/col fragment layouts of mma.sync m16n8k16, so the kernel streams pixel chunks through a
+// 2-stage cp.async pipeline, every warp keeps a block of M-tiles x N-tiles of fp32 accumulators in
+// registers, and the pixel range is split over CTAs whose partials are summed in a fixed order.
+// An extra all-ones row appended to Bt makes the bias gradient (row sums of A) fall out of the same MMAs.
+// Bt may come from two tensors (rows [0,N1) from B1, [N1,N1+N2) from B2) so that pointwise+shortcut,
+// which share grad_output, read it once.
+#include "common.cuh"
+
+namespace lmnet {
+
+constexpr int kWgThreads = 256;
+constexpr int kWgWarps = 8;
+constexpr int kWgKP = 64;              // pixels per pipeline stage
+constexpr int kWgPitch = kWgKP + 8;    // 144-byte rows: conflict-free ldmatrix
+
+struct WgGeom {
+    int B, M, N1, N2, NT;              // NT = number of 8-wide N tiles incl. the ones row
+    int64_t P;
+    int splits, chunks_per_split;      // pixel chunks of kWgKP handled by one CTA
+};
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+    const int sz = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+
+__device__ __forceinline__ void wg_ldmatrix_x4(uint32_t (&r)[4], const void* p) {
+    const uint32_t addr = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void wg_ldmatrix_x2(uint32_t (&r)[2], const void* p) {
+    const uint32_t addr = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
+}
+template <typename T> __device__ __forceinline__ void wg_mma(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]);
+template <> __device__ __forceinline__ void wg_mma<__nv_bfloat16>(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+template <> __device__ __forceinline__ void wg_mma<__half>(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+template <typename T> __device__ __forceinline__ T wg_one();
+template <> __device__ __forceinline__ __nv_bfloat16 wg_one<__nv_bfloat16>() { return __float2bfloat16_rn(1.f); }
+template <> __device__ __forceinline__ __half wg_one<__half>() { return __float2half_rn(1.f); }
+
+// part[b][split][M][NT*8] (fp32).  MT = M tiles per CTA (all of them), NTW = N tiles per warp.
+template <typename T, int MT, int NTW>
+__global__ void __launch_bounds__(kWgThreads)
+wgrad_1x1_kernel(const T* __restrict__ A, const T* __restrict__ B1, const T* __restrict__ B2,
+                 float* __restrict__ part, WgGeom g) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int a_rows = MT * 16, b_rows = g.NT * 8;
+    const int stage_elems = (a_rows + b_rows) * kWgPitch;
+    T* smem = reinterpret_cast<T*>(smem_raw);
+    const int b = blockIdx.y, split = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int Ntot = g.N1 + g.N2;                      // real input channels; row Ntot is the ones row
+    const int64_t chunk0 = (int64_t)split * g.chunks_per_split;
+    const int64_t nchunks_total = (g.P + kWgKP - 1) / kWgKP;
+    const int nchunks = (int)max((int64_t)0, min((int64_t)g.chunks_per_split, nchunks_total - chunk0));
+
+    // rows that no copy ever touches: zero padding rows of A / Bt, and the ones row (both stages)
+    for (int st = 0; st < 2; ++st) {
+        T* sa = smem + st * stage_elems;
+        T* sb = sa + a_rows * kWgPitch;
+        for (int i = threadIdx.x; i < (a_rows - g.M) * kWgPitch; i += kWgThreads) sa[g.M * kWgPitch + i] = from_f<T>(0.f);
+        for (int i = threadIdx.x; i < (b_rows - Ntot) * kWgPitch; i += kWgThreads)
+            sb[Ntot * kWgPitch + i] = (i < kWgPitch) ? wg_one<T>() : from_f<T>(0.f);
+    }
+
+    auto issue = [&](int c, int st) {
+        T* sa = smem + st * stage_elems;
+        T* sb = sa + a_rows * kWgPitch;
+        const int64_t p0 = (chunk0 + c) * kWgKP;
+        constexpr int VPR = kWgKP / 8;                  // 16-byte vectors per row
+        const int rows = g.M + Ntot;
+        for (int i = threadIdx.x; i < rows * VPR; i += kWgThreads) {
+            const int r = i / VPR, v = i - r * VPR;
+            const int64_t p = p0 + v * 8;
+            const bool ok = p < g.P;                    // P % 8 == 0: a vector is all in or all out
+            const T* src;
+            T* dst;
+            if (r < g.M) {
+                src = A + ((int64_t)b * g.M + r) * g.P + p;
+                dst = sa + r * kWgPitch + v * 8;
+            } else {
+                const int n = r - g.M;
+                src = n < g.N1 ? B1 + ((int64_t)b * g.N1 + n) * g.P + p : B2 + ((int64_t)b * g.N2 + (n - g.N1)) * g.P + p;
+                dst = sb + n * kWgPitch + v * 8;
+            }
+            cp_async16(dst, ok ? src : A, ok);
+        }
+        cp_async_commit();
+    };
+
+    float acc[MT][NTW][4];
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < NTW; ++j) acc[i][j][0] = acc[i][j][1] = acc[i][j][2] = acc[i][j][3] = 0.f;
+    const int nt0 = warp * NTW;                        // this warp's first N tile
+
+    if (nchunks > 0) issue(0, 0);
+    for (int c = 0; c < nchunks; ++c) {
+        const int st = c & 1;
+        if (c + 1 < nchunks) {
+            issue(c + 1, st ^ 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        const T* sa = smem + st * stage_elems;
+        const T* sb = sa + a_rows * kWgPitch;
+        // the ones row must only count real pixels of the tail chunk
+        if ((chunk0 + c + 1) * kWgKP > g.P) {
+            const int valid = (int)(g.P - (chunk0 + c) * kWgKP);
+            T* ones = const_cast<T*>(sb) + Ntot * kWgPitch;
+            for (int i = threadIdx.x; i < kWgKP; i += kWgThreads) ones[i] = i < valid ? wg_one<T>() : from_f<T>(0.f);
+            __syncthreads();
+        }
+#pragma unroll
+        for (int kt = 0; kt < kWgKP / 16; ++kt) {
+            uint32_t bf[NTW][2];
+#pragma unroll
+            for (int j = 0; j < NTW; ++j) {
+                const int nt = nt0 + j;
+                if (nt < g.NT) {
+                    // matrix 0: rows n 0..7, k 0..7 ; matrix 1: k 8..15   (lanes 0-15 give the addresses)
+                    const int l = lane & 15;
+                    wg_ldmatrix_x2(bf[j], sb + (nt * 8 + (l & 7)) * kWgPitch + kt * 16 + (l >> 3) * 8);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < MT; ++i) {
+                uint32_t af[4];
+                const int m = lane >> 3, rr = lane & 7;
+                wg_ldmatrix_x4(af, sa + (i * 16 + (m & 1) * 8 + rr) * kWgPitch + kt * 16 + (m >> 1) * 8);
+#pragma unroll
+                for (int j = 0; j < NTW; ++j)
+                    if (nt0 + j < g.NT) wg_mma<T>(acc[i][j], af, bf[j]);
+            }
+        }
+        __syncthreads();
+        if ((chunk0 + c + 1) * kWgKP > g.P) {           // restore the ones row for the next use of this stage
+            T* ones = const_cast<T*>(sb) + Ntot * kWgPitch;
+            for (int i = threadIdx.x; i < kWgKP; i += kWgThreads) ones[i] = wg_one<T>();
+        }
+    }
+    // write this CTA's partial: part[((b*splits + split)*M + m) * (NT*8) + n]
+    const int ldn = g.NT * 8;
+    float* out = part + ((int64_t)b * g.splits + split) * g.M * ldn;
+    const int gq = lane >> 2, tq = lane & 3;
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < NTW; ++j) {
+            const int nt = nt0 + j;
+            if (nt < g.NT) {
+                const int n = nt * 8 + 2 * tq;
+                const int m0 = i * 16 + gq, m1 = m0 + 8;
+                if (m0 < g.M) *reinterpret_cast<float2*>(out + (int64_t)m0 * ldn + n) = make_float2(acc[i][j][0], acc[i][j][1]);
+                if (m1 < g.M) *reinterpret_cast<float2*>(out + (int64_t)m1 * ldn + n) = make_float2(acc[i][j][2], acc[i][j][3]);
+            }
+        }
+}
+
+// dW[b][m][n] (n < N1+N2) and drow[b][m] (the ones column) = sum over splits, fixed order
+__global__ void wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ dW, float* __restrict__ drow,
+                                    int B, int splits, int M, int Ntot, int ldn) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t total = (int64_t)B * M * (Ntot + 1);
+    if (idx >= total) return;
+    const int n = (int)(idx % (Ntot + 1));
+    const int m = (int)((idx / (Ntot + 1)) % M);
+    const int b = (int)(idx / ((int64_t)(Ntot + 1) * M));
+    float a = 0.f;
+    for (int s = 0; s < splits; ++s) a += part[(((int64_t)b * splits + s) * M + m) * ldn + n];
+    if (n < Ntot) dW[((int64_t)b * M + m) * Ntot + n] = a;
+    else if (drow != nullptr) drow[(int64_t)b * M + m] = a;
+}
+
+static bool wg_shape(int M, int N, int& MT, int& NTW, int& NT) {
+    MT = (M + 15) / 16;
+    NT = (N + 1 + 7) / 8;
+    NTW = (NT + kWgWarps - 1) / kWgWarps;
+    const bool mt_ok = MT == 1 || MT == 2 || MT == 3 || MT == 6 || MT == 12;
+    const bool nt_ok = NTW == 1 || NTW == 2 || NTW == 3 || NTW == 5;
+    return mt_ok && nt_ok && MT * NTW <= 30;
+}
+
+static WgGeom wg_geom(const lmnet_wgrad_dims* d, int NT) {
+    WgGeom g;
+    g.B = d->B; g.M = d->M; g.N1 = d->N1; g.N2 = d->N2; g.NT = NT; g.P = d->P;
+    const int64_t nchunks = (d->P + kWgKP - 1) / kWgKP;
+    int64_t splits = (4 * 148 + d->B - 1) / d->B;
+    if (splits > nchunks) splits = nchunks;
+    if (splits < 1) splits = 1;
+    g.chunks_per_split = (int)((nchunks + splits - 1) / splits);
+    g.splits = (int)((nchunks + g.chunks_per_split - 1) / g.chunks_per_split);
+    return g;
+}
+
+template <typename T, int MT, int NTW>
+static int wg_launch(const void* A, const void* B1, const void* B2, float* part, const WgGeom& g, cudaStream_t st) {
+    const size_t smem = 2 * (size_t)(MT * 16 + g.NT * 8) * kWgPitch * sizeof(T);
+    static size_t attr_bytes = 0;
+    if (smem > 48 * 1024 && smem > attr_bytes) {
+        if (cudaFuncSetAttribute(wgrad_1x1_kernel<T, MT, NTW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return LMNET_ERR_LAUNCH;
+        attr_bytes = smem;
+    }
+    const double bytes = (double)g.B * (g.M + g.N1 + g.N2) * g.P * sizeof(T);
+    dim3 grid(g.splits, g.B);
+    LMNET_LAUNCH(KID_WGRAD_1X1, st, bytes, (wgrad_1x1_kernel<T, MT, NTW><<<grid, kWgThreads, smem, st>>>(
+        (const T*)A, (const T*)B1, (const T*)B2, part, g)));
+    return LMNET_OK;
+}
+
+template <typename T, int MT>
+static int wg_dispatch_n(int NTW, const void* A, const void* B1, const void* B2, float* part, const WgGeom& g, cudaStream_t st) {
+    switch (NTW) {
+        case 1: return wg_launch<T, MT, 1>(A, B1, B2, part, g, st);
+        case 2: return wg_launch<T, MT, 2>(A, B1, B2, part, g, st);
+        case 3: if constexpr (MT <= 6) return wg_launch<T, MT, 3>(A, B1, B2, part, g, st); else return LMNET_ERR_UNSUPPORTED;
+        case 5: if constexpr (MT <= 6) return wg_launch<T, MT, 5>(A, B1, B2, part, g, st); else return LMNET_ERR_UNSUPPORTED;
+        default: return LMNET_ERR_UNSUPPORTED;
+    }
+}
+template <typename T>
+static int wg_dispatch(int MT, int NTW, const void* A, const void* B1, const void* B2, float* part, const WgGeom& g, cudaStream_t st) {
+    switch (MT) {
+        case 1: return wg_dispatch_n<T, 1>(NTW, A, B1, B2, part, g, st);
+        case 2: return wg_dispatch_n<T, 2>(NTW, A, B1, B2, part, g, st);
+        case 3: return wg_dispatch_n<T, 3>(NTW, A, B1, B2, part, g, st);
+        case 6: return wg_dispatch_n<T, 6>(NTW, A, B1, B2, part, g, st);
+        case 12: return wg_dispatch_n<T, 12>(NTW, A, B1, B2, part, g, st);
+        default: return LMNET_ERR_UNSUPPORTED;
+    }
+}
+
+}  // namespace lmnet
+
+using namespace lmnet;
+
+extern "C" int lmnet_wgrad_1x1_supported(const lmnet_wgrad_dims* d, int dtype) {
+    if (d == nullptr || d->B <= 0 || d->M <= 0 || d->N1 <= 0 || d->N2 < 0 || d->P <= 0) return 0;
+    if (dtype != LMNET_BF16 && dtype != LMNET_F16) return 0;
+    if (d->P % 8 != 0) return 0;
+    int MT, NTW, NT;
+    return wg_shape(d->M, d->N1 + d->N2, MT, NTW, NT) ? 1 : 0;
+}
+
+extern "C" size_t lmnet_wgrad_1x1_workspace_bytes(const lmnet_wgrad_dims* d) {
+    int MT, NTW, NT;
+    if (d == nullptr || d->B <= 0 || d->M <= 0 || d->P <= 0 || !wg_shape(d->M, d->N1 + d->N2, MT, NTW, NT)) return 0;
+    WgGeom g = wg_geom(d, NT);
+    return (size_t)g.B * g.splits * g.M * (NT * 8) * sizeof(float);
+}
+
+extern "C" int lmnet_wgrad_1x1(const void* A, const void* B1, const void* B2, float* dW, float* drow,
+                               void* workspace, size_t workspace_bytes, const lmnet_wgrad_dims* d, int dtype,
+                               void* stream) {
+    if (!lmnet_wgrad_1x1_supported(d, dtype)) return LMNET_ERR_UNSUPPORTED;
+    if (!A || !B1 || (d->N2 > 0 && !B2) || !dW || !workspace) return LMNET_ERR_INVALID_ARG;
+    if (workspace_bytes < lmnet_wgrad_1x1_workspace_bytes(d)) return LMNET_ERR_WORKSPACE;
+    if ((uintptr_t)A % 16 || (uintptr_t)B1 % 16 || (uintptr_t)B2 % 16) return LMNET_ERR_UNSUPPORTED;
+    int MT, NTW, NT;
+    wg_shape(d->M, d->N1 + d->N2, MT, NTW, NT);
+    WgGeom g = wg_geom(d, NT);
+    cudaStream_t st = (cudaStream_t)stream;
+    float* part = (float*)workspace;
+    int rc = dtype == LMNET_BF16 ? wg_dispatch<__nv_bfloat16>(MT, NTW, A, B1, d->N2 > 0 ? B2 : B1, part, g, st)
+                                 : wg_dispatch<__half>(MT, NTW, A, B1, d->N2 > 0 ? B2 : B1, part, g, st);
+    if (rc != LMNET_OK) return rc;
+    const int Ntot = d->N1 + d->N2;
+    const int64_t total = (int64_t)d->B * d->M * (Ntot + 1);
+    LMNET_LAUNCH(KID_WGRAD_REDUCE, st, 0, (wgrad_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+        part, dW, drow, d->B, g.splits, d->M, Ntot, NT * 8)));
+    return LMNET_OK;
+}

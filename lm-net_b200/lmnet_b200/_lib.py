@@ -49,6 +49,10 @@ class BnDims(Structure):
 ACT_CODES = {"none": 0, "hardswish": 1, "gelu": 2, "relu": 3}
 
 
+class WgradDims(Structure):
+    _fields_ = [("B", c_int32), ("M", c_int32), ("N1", c_int32), ("N2", c_int32), ("P", c_int64)]
+
+
 _lib = None
 
 
@@ -99,6 +103,11 @@ def lib():
     L.lmnet_layer_norm_workspace_bytes.argtypes = [c_int64, c_int]
     L.lmnet_layer_norm_fwd.argtypes = [c_void_p] * 6 + [c_int64, c_int, c_float, c_int, c_void_p]
     L.lmnet_layer_norm_bwd.argtypes = [c_void_p] * 8 + [c_void_p, c_size_t, c_int64, c_int, c_int, c_void_p]
+    pwd = POINTER(WgradDims)
+    L.lmnet_wgrad_1x1_supported.argtypes = [pwd, c_int]
+    L.lmnet_wgrad_1x1_workspace_bytes.restype = c_size_t
+    L.lmnet_wgrad_1x1_workspace_bytes.argtypes = [pwd]
+    L.lmnet_wgrad_1x1.argtypes = [c_void_p] * 5 + [c_void_p, c_size_t, pwd, c_int, c_void_p]
     L.lmnet_profile_enable.argtypes = [c_int]
     L.lmnet_profile_kernel_name.restype = ctypes.c_char_p
     L.lmnet_profile_kernel_name.argtypes = [c_int]
@@ -200,4 +209,4 @@ def dw_grads(dw, dgamma, dbeta) -> DwGrads:
 
 
 __all__ = ["lib", "check", "dtype_code", "require_cuda", "stream_ptr", "ptr", "view5", "na_dims", "dw_params",
-           "dw_grads", "View5", "NADims", "DwParams", "DwGrads", "DwDims", "BnDims", "ACT_CODES", "byref", "launch_count", "LIB_PATH"]
+           "dw_grads", "View5", "NADims", "DwParams", "DwGrads", "DwDims", "BnDims", "ACT_CODES", "WgradDims", "byref", "launch_count", "LIB_PATH"]

@@ -1,0 +1,139 @@
+"""The three 1x1 convolutions of ReparamConv on NCHW planes (widening step f1 of SURVEY.md §8;
+reference: expand_conv[0] /root/reference/core/modules.py:537, pointwise_conv :576-579, shortcut :581-584,
+used at :587 and :598-599).
+
+Forward and input gradients are GEMMs whose large operand is already in the right layout (NCHW planes
+= the [K, N] operand), so they go to cuBLAS through torch.bmm — unlike cuDNN's bf16 path no NCHW<->NHWC
+transposes are needed.  The weight and bias gradients (a small matrix reduced over up to 124k pixels) run on
+the hand-written split-K tensor-core kernel of csrc/wgrad_1x1.cu.  The squeeze-excite gate is folded into
+the pointwise weights per sample (W_b = W * gate_b), which removes the gate multiply and its backward pass
+over [B,E,H,W]; pointwise + shortcut accumulate into one output and share one read of grad_output.
+"""
+from __future__ import annotations
+
+import torch
+from torch.amp import custom_bwd, custom_fwd
+
+from . import _lib as L
+
+
+def _wgrad(A, B1, B2):
+    """A [B,M,P], B1 [B,N1,P], B2 [B,N2,P] or None -> (dW [B,M,N1+N2] fp32, drow [B,M] fp32)."""
+    Bn, M, P = A.shape
+    N1 = B1.shape[1]
+    N2 = 0 if B2 is None else B2.shape[1]
+    dims = L.WgradDims(Bn, M, N1, N2, P)
+    dW = torch.empty(Bn, M, N1 + N2, dtype=torch.float32, device=A.device)
+    drow = torch.empty(Bn, M, dtype=torch.float32, device=A.device)
+    n = L.lib().lmnet_wgrad_1x1_workspace_bytes(L.byref(dims))
+    ws = torch.empty(max(int(n), 16), dtype=torch.uint8, device=A.device)
+    rc = L.lib().lmnet_wgrad_1x1(L.ptr(A), L.ptr(B1), L.ptr(B2), L.ptr(dW), L.ptr(drow), L.ptr(ws), ws.numel(),
+                                 L.byref(dims), L.dtype_code(A), L.stream_ptr())
+    L.check(rc, "wgrad_1x1")
+    return dW, drow
+
+
+def wgrad_supported(B, M, N1, N2, P, dtype) -> bool:
+    if dtype not in (torch.bfloat16, torch.float16):
+        return False
+    dims = L.WgradDims(B, M, N1, N2, P)
+    return bool(L.lib().lmnet_wgrad_1x1_supported(L.byref(dims), L._DTYPES[dtype]))
+
+
+class _Expand1x1(torch.autograd.Function):
+    """y[b] = W @ x[b] + bias on NCHW planes."""
+
+    @staticmethod
+    @custom_fwd(device_type="cuda")
+    def forward(ctx, x, w, bias):
+        B, K, H, Wd = x.shape
+        M = w.shape[0]
+        xf = x.reshape(B, K, H * Wd)
+        wc = w.to(x.dtype).unsqueeze(0).expand(B, M, K)
+        y = torch.baddbmm(bias.to(x.dtype).view(1, M, 1), wc, xf) if bias is not None else torch.bmm(wc, xf)
+        ctx.save_for_backward(x, w)
+        ctx.has_bias = bias is not None
+        ctx.bias_dtype = None if bias is None else bias.dtype
+        return y.view(B, M, H, Wd)
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        B, K, H, Wd = x.shape
+        M = w.shape[0]
+        dyf = dy.to(x.dtype).contiguous().view(B, M, H * Wd)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.bmm(w.to(x.dtype).t().unsqueeze(0).expand(B, K, M), dyf).view(B, K, H, Wd)
+        dW, drow = _wgrad(dyf, x.view(B, K, H * Wd), None)
+        dw = dW.sum(0).to(w.dtype)
+        db = drow.sum(0).to(ctx.bias_dtype) if ctx.has_bias else None
+        return dx, dw, db
+
+
+class _PointwiseShortcut(torch.autograd.Function):
+    """out[b] = (Wpw * gate[b]) @ z[b] + Wsc @ x[b] + bias  — pointwise(gate*z) + shortcut(x) of ReparamConv."""
+
+    @staticmethod
+    @custom_fwd(device_type="cuda")
+    def forward(ctx, z, gate, x, wpw, wsc, bias):
+        B, E, H, Wd = z.shape
+        Cin, Cout = x.shape[1], wpw.shape[0]
+        P = H * Wd
+        dt = z.dtype
+        wg = (wpw.float().unsqueeze(0) * gate.float().unsqueeze(1)).to(dt)            # [B, Cout, E]
+        out = torch.baddbmm(bias.to(dt).view(1, Cout, 1), wsc.to(dt).unsqueeze(0).expand(B, Cout, Cin), x.reshape(B, Cin, P))
+        out = torch.baddbmm(out, wg, z.reshape(B, E, P))
+        ctx.save_for_backward(z, gate, x, wpw, wsc, wg)
+        ctx.bias_dtype = bias.dtype
+        return out.view(B, Cout, H, Wd)
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, dout):
+        z, gate, x, wpw, wsc, wg = ctx.saved_tensors
+        B, E, H, Wd = z.shape
+        Cin, Cout = x.shape[1], wpw.shape[0]
+        P = H * Wd
+        dt = z.dtype
+        do = dout.to(dt).contiguous().view(B, Cout, P)
+        dz = torch.bmm(wg.transpose(1, 2), do).view(B, E, H, Wd)
+        dx = None
+        if ctx.needs_input_grad[2]:
+            dx = torch.bmm(wsc.to(dt).t().unsqueeze(0).expand(B, Cin, Cout), do).view(B, Cin, H, Wd)
+        dW, drow = _wgrad(do, z.view(B, E, P), x.reshape(B, Cin, P))                  # [B, Cout, E + Cin]
+        dWg = dW[:, :, :E]
+        dwpw = (dWg * gate.float().unsqueeze(1)).sum(0).to(wpw.dtype)
+        dgate = (dWg * wpw.float().unsqueeze(0)).sum(1).to(gate.dtype)                # [B, E]
+        dwsc = dW[:, :, E:].sum(0).to(wsc.dtype)
+        dbias = drow.sum(0).to(ctx.bias_dtype)
+        return dz, dgate, dx, dwpw, dwsc, dbias
+
+
+def _compute_dtype(x):
+    if torch.is_autocast_enabled("cuda"):
+        return torch.get_autocast_dtype("cuda")
+    return x.dtype
+
+
+def expand_1x1(conv: torch.nn.Conv2d, x: torch.Tensor) -> torch.Tensor:
+    """conv(x) for a 1x1 convolution on a CUDA NCHW tensor (falls back to the module for uncovered cases)."""
+    dt = _compute_dtype(x)
+    B, K, H, W = x.shape
+    M = conv.out_channels
+    if x.is_cuda and wgrad_supported(B, M, K, 0, H * W, dt):
+        return _Expand1x1.apply(x.to(dt).contiguous(), conv.weight.view(M, K), conv.bias)
+    return conv(x)
+
+
+def pointwise_shortcut(pw: torch.nn.Conv2d, sc: torch.nn.Conv2d, z, gate, x):
+    """pw(gate * z) + sc(x) with gate [B,E,1,1]; fused path on CUDA, module calls otherwise."""
+    dt = _compute_dtype(z)
+    B, E, H, W = z.shape
+    Cin, Cout = x.shape[1], pw.out_channels
+    if z.is_cuda and pw.bias is not None and sc.bias is not None and wgrad_supported(B, Cout, E, Cin, H * W, dt):
+        bias = pw.bias + sc.bias
+        return _PointwiseShortcut.apply(z.to(dt).contiguous(), gate.reshape(B, E), x.to(dt).contiguous(),
+                                        pw.weight.view(Cout, E), sc.weight.view(Cout, Cin), bias)
+    return pw(gate * z) + sc(x)

@@ -21,7 +21,8 @@ import torch
 from torch.amp import custom_bwd, custom_fwd
 
 from . import _lib as L
-from .bnact import conv_bn_act
+from .bnact import bn_act, conv_bn_act
+from .conv1x1 import expand_1x1, pointwise_shortcut
 
 
 def _dims(x):
@@ -180,9 +181,18 @@ def fused_dw_deploy(mod, x1):
     return _eval_call(x1, params, bias, 0.0)
 
 
+def _is_1x1(conv) -> bool:
+    return (isinstance(conv, torch.nn.Conv2d) and conv.kernel_size == (1, 1) and conv.stride == (1, 1)
+            and conv.padding == (0, 0) and conv.groups == 1 and conv.dilation == (1, 1))
+
+
 def reparam_forward(self, x):
     """Replacement for ReparamConv.forward (/root/reference/core/modules.py:586-600)."""
-    x1 = conv_bn_act(self.expand_conv, x)          # 1x1 conv (cuDNN) + fused BatchNorm + Hardswish
+    ec = self.expand_conv
+    if len(ec) == 3 and _is_1x1(ec[0]) and type(ec[1]) is torch.nn.BatchNorm2d and type(ec[2]) is torch.nn.Hardswish:
+        x1 = bn_act(ec[1], expand_1x1(ec[0], x), "hardswish")     # plane-wise GEMM + fused BatchNorm + Hardswish
+    else:
+        x1 = conv_bn_act(ec, x)
     if self.deploy:
         z, pool = fused_dw_deploy(self, x1)
     else:
@@ -190,8 +200,11 @@ def reparam_forward(self, x):
     se = self.se
     B, E = pool.shape
     gate = se.scale_activation(se.fc2(se.activation(se.fc1(pool.to(z.dtype).view(B, E, 1, 1)))))
-    x1 = self.pointwise_conv(gate * z)
-    return x1 + self.shortcut(x)
+    if len(self.pointwise_conv) == 1 and len(self.shortcut) == 1 and _is_1x1(self.pointwise_conv[0]) \
+            and _is_1x1(self.shortcut[0]):
+        # pointwise(gate * z) + shortcut(x): two accumulating plane-wise GEMMs, the SE multiply rides in the weights
+        return pointwise_shortcut(self.pointwise_conv[0], self.shortcut[0], z, gate, x)
+    return self.pointwise_conv(gate * z) + self.shortcut(x)
 
 
 def patch_reparam_conv(cls):

@@ -1,0 +1,78 @@
+"""GPU parity for the 1x1-convolution path of ReparamConv (plane-wise GEMMs + csrc/wgrad_1x1.cu) against
+stock nn.Conv2d modules evaluated in fp64 (reference ops: /root/reference/core/modules.py:587, 598-599)."""
+import copy
+
+import pytest
+import torch
+
+from _helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+# (B, Cin, E, Cout, H, W): LM-Net's four levels, the 3-channel stem, and a ragged pixel count
+SHAPES = [(2, 12, 24, 12, 24, 40), (2, 3, 24, 12, 16, 24), (2, 24, 48, 24, 20, 16), (2, 48, 96, 48, 12, 12),
+          (2, 96, 192, 96, 8, 8), (3, 12, 24, 12, 17, 8)]
+
+
+@pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "x".join(map(str, s)))
+def test_raw_wgrad_kernel_vs_einsum(shape):
+    from lmnet_b200.conv1x1 import _wgrad, wgrad_supported
+
+    B, Cin, E, Cout, H, W = shape
+    P = H * W
+    assert wgrad_supported(B, Cout, E, Cin, P, torch.bfloat16)
+    g = torch.Generator().manual_seed(0)
+    A = torch.randn(B, Cout, P, generator=g).to(torch.bfloat16)
+    B1 = torch.randn(B, E, P, generator=g).to(torch.bfloat16)
+    B2 = torch.randn(B, Cin, P, generator=g).to(torch.bfloat16)
+    dW, drow = _wgrad(A.cuda(), B1.cuda(), B2.cuda())
+    ref = torch.einsum("bmp,bnp->bmn", A.double(), torch.cat([B1, B2], 1).double())
+    assert rel_err(dW.cpu(), ref) < 1e-5          # bf16 products are exact in fp32; only summation order differs
+    assert rel_err(drow.cpu(), A.double().sum(-1)) < 1e-5
+    dW1, _ = _wgrad(A.cuda(), B2.cuda(), None)
+    assert rel_err(dW1.cpu(), torch.einsum("bmp,bnp->bmn", A.double(), B2.double())) < 1e-5
+
+
+@pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "x".join(map(str, s)))
+def test_expand_and_pointwise_shortcut_vs_modules(shape):
+    from lmnet_b200.conv1x1 import expand_1x1, pointwise_shortcut
+
+    B, Cin, E, Cout, H, W = shape
+    torch.manual_seed(1)
+    ex, pw, sc = torch.nn.Conv2d(Cin, E, 1), torch.nn.Conv2d(E, Cout, 1), torch.nn.Conv2d(Cin, Cout, 1)
+    rex, rpw, rsc = (copy.deepcopy(m).double() for m in (ex, pw, sc))
+    x = torch.randn(B, Cin, H, W)
+    z = torch.randn(B, E, H, W)
+    gate = torch.rand(B, E, 1, 1)
+    go1, go2 = torch.randn(B, E, H, W), torch.randn(B, Cout, H, W)
+    # fp64 reference on the bf16-rounded activations
+    xr, zr, gr = (t.to(torch.bfloat16).double().requires_grad_() for t in (x, z, gate))
+    y1 = rex(xr)
+    y2 = rpw(gr * zr) + rsc(xr)
+    (y1 * go1.double()).sum().add((y2 * go2.double()).sum()).backward()
+
+    ex, pw, sc = ex.cuda(), pw.cuda(), sc.cuda()
+    xc, zc, gc = (t.cuda().requires_grad_() for t in (x, z, gate))
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        o1 = expand_1x1(ex, xc)
+        o2 = pointwise_shortcut(pw, sc, zc, gc, xc)
+    assert o1.dtype == torch.bfloat16 and o2.dtype == torch.bfloat16
+    (o1.float() * go1.cuda()).sum().add((o2.float() * go2.cuda()).sum()).backward()
+    tol = 2e-2
+    assert rel_err(o1.float().cpu(), y1) < tol and rel_err(o2.float().cpu(), y2) < tol
+    assert rel_err(xc.grad.cpu(), xr.grad) < tol
+    assert rel_err(zc.grad.cpu(), zr.grad) < tol
+    assert rel_err(gc.grad.cpu(), gr.grad) < tol
+    for m, r in ((ex, rex), (pw, rpw), (sc, rsc)):
+        assert m.weight.grad.dtype == torch.float32
+        assert rel_err(m.weight.grad.cpu(), r.weight.grad) < tol
+        assert rel_err(m.bias.grad.cpu(), r.bias.grad) < tol
+
+
+def test_fp32_inputs_take_the_module_path():
+    from lmnet_b200.conv1x1 import expand_1x1
+
+    conv = torch.nn.Conv2d(12, 24, 1).cuda()
+    x = torch.randn(2, 12, 8, 8, device="cuda")
+    assert torch.equal(expand_1x1(conv, x), conv(x))
