@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--cpu-batch", type=int, default=2, help="images per step of the CPU arms (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying a CUDA graph")
     return ap.parse_args()
 
 
@@ -159,11 +160,13 @@ def run_b200_arm(args):
     from lmnet_b200 import _lib
     from lmnet_b200.distributed import get_rank, get_world_size, init_distributed_mode, wrap_ddp
     from lmnet_b200.model import LM_Net
-    from lmnet_b200.train import ConfusionMetrics, build_training, synthetic_batches, train_one_epoch, train_step
+    from lmnet_b200.train import (ConfusionMetrics, GraphedTrainStep, build_training, synthetic_batches,
+                                  train_one_epoch, train_step)
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: the b200 arm needs a CUDA device (no CPU fallback exists)")
     _lib.lib()  # fail loudly if the extension is missing
+    os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")   # required for NCCL inside CUDA-graph capture
     dargs = init_distributed_mode()
     rank, world = get_rank(), get_world_size()
     local = getattr(dargs, "gpu", 0)
@@ -174,11 +177,24 @@ def run_b200_arm(args):
     torch.manual_seed(42 + rank)                      # train.py:42-43
 
     B, R = args.batch, args.res
+    use_graph = not args.no_graph
     net = LM_Net(3, 2).to(dev).train()
-    model = wrap_ddp(net, dev)
-    opt, crit, dice = build_training(model, dev)
+    if use_graph and world > 1:                       # DDP has to be built on a side stream to be capturable
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            model = wrap_ddp(net, dev)
+        torch.cuda.current_stream().wait_stream(side)
+    else:
+        model = wrap_ddp(net, dev)
+    opt, crit, dice = build_training(model, dev, capturable=use_graph)
     host = synthetic_batches(2, B, R, seed=rank)       # pinned host batches
     resident = [(i.to(dev), m.to(dev)) for i, m in host]
+    graphed = None
+    if use_graph:
+        graphed = GraphedTrainStep(model, opt, crit, dice, *resident[0], warmup=11 if world > 1 else 3)
+        if graphed.graph is None and rank == 0:
+            print(f"[bench] CUDA-graph capture unavailable, running eagerly: {graphed.fallback_reason}", file=sys.stderr)
 
     def barrier():
         if world > 1:
@@ -187,6 +203,8 @@ def run_b200_arm(args):
 
     def step_resident(i):
         img, msk = resident[i % len(resident)]
+        if graphed is not None:
+            return graphed(img, msk)[0]               # device-to-device copy into the static buffers + replay
         return train_step(model, opt, img, msk, crit, dice)[0]
 
     # ---- device-resident timing (value) ----
@@ -204,7 +222,10 @@ def run_b200_arm(args):
     e1.record()
     barrier()
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    launches = torch.tensor([_lib.launch_count() - launches0], device=dev, dtype=torch.int64)
+    n_launch = _lib.launch_count() - launches0
+    if graphed is not None and graphed.graph is not None:      # replayed launches are not seen by the counter
+        n_launch = graphed.library_launches_per_step * args.steps
+    launches = torch.tensor([n_launch], device=dev, dtype=torch.int64)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(launches)
@@ -224,11 +245,12 @@ def run_b200_arm(args):
 
     metrics = ConfusionMetrics(2)
     scaler_flag = object()   # non-None => autocast branch, as in the reference loop
-    train_one_epoch(model, opt, metrics, 2, Loader(max(1, min(3, args.warmup))), dev, crit, scaler_flag, dice)
+    train_one_epoch(model, opt, metrics, 2, Loader(max(1, min(3, args.warmup))), dev, crit, scaler_flag, dice,
+                    step_fn=graphed)
     barrier()
     t0 = time.perf_counter()
     e0.record()
-    train_one_epoch(model, opt, metrics, 2, Loader(args.steps), dev, crit, scaler_flag, dice)
+    train_one_epoch(model, opt, metrics, 2, Loader(args.steps), dev, crit, scaler_flag, dice, step_fn=graphed)
     e1.record()
     barrier()
     e2e_ms = torch.tensor([max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0))], device=dev)
@@ -286,6 +308,7 @@ def run_b200_arm(args):
                 "e2e": {"value": round(e2e_value, 2), "unit": "images/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h, "ms_per_step": round(float(e2e_ms) / args.steps, 3),
                         "api": "lmnet_b200.train.train_one_epoch (reference-shaped loop, pinned host batches)"},
+                "cuda_graph": bool(graphed is not None and graphed.graph is not None),
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
                 "kernels": kernels, "loss": final_loss}
         print(json.dumps(line), flush=True)

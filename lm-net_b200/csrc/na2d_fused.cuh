@@ -448,7 +448,10 @@ inline bool view_ok(const lmnet_view5* v, int vec_elems, size_t esize) {
     size_t vb = total % 16 == 0 ? 16 : total % 8 == 0 ? 8 : total % 4 == 0 ? 4 : esize;
     if (vb <= esize) return true;
     auto al = [&](int64_t s) { return ((size_t)(s < 0 ? -s : s) * esize) % vb == 0; };
-    return ((uintptr_t)v->ptr % vb == 0) && al(v->sb) && al(v->sh) && al(v->sw) && al(v->sn);
+    // the head stride only enters as (head-group index) * vec_elems when heads are contiguous (callers pass
+    // vec_elems = HG*D with sn == D); for HG == 1 it is the stride between single heads and must be aligned
+    const bool head_ok = (vec_elems > 0 && v->sn > 0 && vec_elems % v->sn == 0 && vec_elems != v->sn) ? true : al(v->sn);
+    return ((uintptr_t)v->ptr % vb == 0) && al(v->sb) && al(v->sh) && al(v->sw) && head_ok;
 }
 
 enum class Op { Fwd, BwdQ, BwdK };

@@ -42,11 +42,36 @@ class DiceLoss(nn.Module):
         return loss / self.n_classes
 
 
-def build_training(model: nn.Module, device, lr=1e-3, weight_decay=1e-4, smoothing=1e-3, fused=None):
+class WeightedSmoothedCE(nn.Module):
+    """nn.CrossEntropyLoss(weight=w, label_smoothing=eps) (train.py:157 of the reference) restated with
+    graph-capturable tensor ops: ATen's weighted + smoothed kernel path breaks CUDA-graph capture.
+        loss = [(1-eps) * sum_i w[y_i] * nll_i + eps/C * sum_i sum_c w_c * (-logp_ic)] / sum_i w[y_i]"""
+
+    def __init__(self, weight: torch.Tensor, label_smoothing: float = 0.0):
+        super().__init__()
+        self.register_buffer("weight", weight.float())
+        self.eps = float(label_smoothing)
+
+    def forward(self, logits, target):
+        logp = F.log_softmax(logits.float(), dim=1)                       # [B, C, ...]
+        C = logits.shape[1]
+        w = self.weight.view(1, C, *([1] * (logits.dim() - 2)))
+        wy = self.weight[target]                                          # [B, ...]
+        nll = -(logp.gather(1, target.unsqueeze(1)).squeeze(1) * wy).sum()
+        smooth = -(logp * w).sum()
+        return ((1.0 - self.eps) * nll + (self.eps / C) * smooth) / wy.sum()
+
+
+def build_training(model: nn.Module, device, lr=1e-3, weight_decay=1e-4, smoothing=1e-3, fused=None,
+                   capturable=False):
     dev = torch.device(device)
     fused = (dev.type == "cuda") if fused is None else fused
-    optimizer = torch.optim.AdamW(model.parameters(), lr=lr, weight_decay=weight_decay, fused=fused)
-    criterion = nn.CrossEntropyLoss(weight=torch.tensor([1.0, 4.0], device=dev), label_smoothing=smoothing)
+    optimizer = torch.optim.AdamW(model.parameters(), lr=lr, weight_decay=weight_decay, fused=fused,
+                                  capturable=capturable and dev.type == "cuda")
+    if capturable and dev.type == "cuda":
+        criterion = WeightedSmoothedCE(torch.tensor([1.0, 4.0], device=dev), smoothing).to(dev)
+    else:
+        criterion = nn.CrossEntropyLoss(weight=torch.tensor([1.0, 4.0], device=dev), label_smoothing=smoothing)
     criterion_dice = DiceLoss(2).to(dev)
     return optimizer, criterion, criterion_dice
 
@@ -65,6 +90,66 @@ def train_step(model, optimizer, images, labels, criterion, criterion_dice, amp_
     loss.backward()
     optimizer.step()
     return loss, output
+
+
+class GraphedTrainStep:
+    """The whole training step (forward, loss, backward, AdamW) captured once into a CUDA graph and replayed.
+
+    One LM-Net step is ~2 500 kernel launches; enqueueing them from Python costs ~40 ms of host time, which
+    caps the step no matter how fast the kernels are (tools/cpu_bound_probe.py).  Replaying a captured graph
+    removes that cost: inputs are copied into static device buffers, `replay()` re-issues every kernel
+    (ours through the C ABI, cuDNN/cuBLAS, NCCL under DDP) with the recorded arguments.
+    Requirements met by this code base: no host synchronisation inside the step, static shapes, the library
+    takes the *current* (capturing) stream, the optimiser is built with capturable=True.
+    Usage: step = GraphedTrainStep(...); loss, output = step(images, labels)  # tensors are static buffers.
+    Falls back to eager execution if capture is not possible (the reason is kept in `.fallback_reason`)."""
+
+    def __init__(self, model, optimizer, criterion, criterion_dice, example_images, example_labels,
+                 amp_dtype=torch.bfloat16, warmup=3):
+        self.model, self.optimizer = model, optimizer
+        self.criterion, self.criterion_dice, self.amp_dtype = criterion, criterion_dice, amp_dtype
+        self.graph, self.fallback_reason, self.library_launches_per_step = None, None, 0
+        self.images = torch.empty_like(example_images)
+        self.labels = torch.empty_like(example_labels)
+        self.images.copy_(example_images)
+        self.labels.copy_(example_labels)
+        try:
+            self._capture(warmup)
+        except Exception as e:  # noqa: BLE001 - any capture failure means: run eagerly
+            self.graph = None
+            self.fallback_reason = f"{type(e).__name__}: {e}"
+            torch.cuda.synchronize()
+
+    def _eager(self):
+        return train_step(self.model, self.optimizer, self.images, self.labels, self.criterion, self.criterion_dice,
+                          self.amp_dtype)
+
+    def _capture(self, warmup):
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._eager()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        from . import _lib
+
+        graph = torch.cuda.CUDAGraph()
+        self.optimizer.zero_grad(set_to_none=True)
+        before = _lib.launch_count()
+        with torch.cuda.graph(graph):
+            self.loss, self.output = self._eager()
+        self.library_launches_per_step = _lib.launch_count() - before    # lmnet_b200 kernels inside one replay
+        self.graph = graph
+
+    def __call__(self, images, labels):
+        self.images.copy_(images, non_blocking=True)
+        self.labels.copy_(labels, non_blocking=True)
+        if self.graph is None:
+            self.loss, self.output = self._eager()
+        else:
+            self.graph.replay()
+        return self.loss, self.output
 
 
 class ConfusionMetrics:
@@ -138,7 +223,7 @@ class _Prefetcher:
 
 def train_one_epoch(model, optimizer, metric_collection=None, num_classes=2, data_loader=None, device=0,
                     criterion=None, scaler=None, criterion_dice=None, amp_dtype=torch.bfloat16,
-                    metrics_on_device=True, prefetch=True, defer_loss_read=True):
+                    metrics_on_device=True, prefetch=True, defer_loss_read=True, step_fn=None):
     """Reference-shaped epoch loop (utils/train_eval_utils.py:120-166): H2D copy of every batch, autocast
     forward, CE + Dice(weight [1,4]), zero_grad, backward, step, loss.item() every step, argmax ->
     metric update.  `scaler` is accepted for signature compatibility; a non-None value selects the
@@ -163,8 +248,12 @@ def train_one_epoch(model, optimizer, metric_collection=None, num_classes=2, dat
     slots = [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(2)] if pipelined else None
     pending, step = None, 0
     for images, labels in batches:
-        loss, output = train_step(model, optimizer, images, labels, criterion, criterion_dice,
-                                  amp_dtype if use_amp else None)
+        if step_fn is not None:          # e.g. a GraphedTrainStep built from the same model / optimiser / criteria
+            loss, output = step_fn(images, labels)
+            labels = getattr(step_fn, "labels", labels)
+        else:
+            loss, output = train_step(model, optimizer, images, labels, criterion, criterion_dice,
+                                      amp_dtype if use_amp else None)
         with torch.no_grad():
             if metric_collection is not None:
                 pred = output.argmax(1).detach()

@@ -89,3 +89,34 @@ def test_training_step_runs_at_the_benchmark_shape():
         opt.step()
         losses.append(float(loss))
     assert all(l == l for l in losses) and losses[-1] < losses[0]
+
+
+def test_cuda_graph_step_matches_eager_steps():
+    """GraphedTrainStep (whole fwd+loss+bwd+AdamW step captured once, then replayed) follows the same loss
+    trajectory as the eager step from identical initial weights (dropout off so that no RNG stream enters)."""
+    import copy
+
+    from lmnet_b200.model import LM_Net
+    from lmnet_b200.train import GraphedTrainStep, build_training, synthetic_batches, train_step
+
+    torch.manual_seed(0)
+    base = LM_Net(3, 2).cuda().train()
+    for m in base.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    batches = [(i.cuda(), m.cuda()) for i, m in synthetic_batches(3, 2, 64, pin=False)]
+    eager = copy.deepcopy(base)
+    opt_e, crit_e, dice_e = build_training(eager, "cuda", capturable=True)
+    # the captured step runs 3 warm-up iterations on its example batch; mirror them on the eager twin
+    for _ in range(3):
+        train_step(eager, opt_e, *batches[0], crit_e, dice_e)
+    graphed_net = copy.deepcopy(base)
+    opt_g, crit_g, dice_g = build_training(graphed_net, "cuda", capturable=True)
+    step = GraphedTrainStep(graphed_net, opt_g, crit_g, dice_g, *batches[0], warmup=3)
+    assert step.graph is not None, step.fallback_reason
+    assert step.library_launches_per_step > 100
+    # the capture itself does not execute: parameters are as after the 3 warm-ups
+    for k in range(3):
+        le = float(train_step(eager, opt_e, *batches[k], crit_e, dice_e)[0])
+        lg = float(step(*batches[k])[0])
+        assert abs(le - lg) < 2e-2 * abs(le), (k, le, lg)
