@@ -98,21 +98,47 @@ class GraphedTrainStep:
     One LM-Net step is ~2 500 kernel launches; enqueueing them from Python costs ~40 ms of host time, which
     caps the step no matter how fast the kernels are (tools/cpu_bound_probe.py).  Replaying a captured graph
     removes that cost: inputs are copied into static device buffers, `replay()` re-issues every kernel
-    (ours through the C ABI, cuDNN/cuBLAS, NCCL under DDP) with the recorded arguments.
+    (ours through the C ABI, cuDNN/cuBLAS) with the recorded arguments.
     Requirements met by this code base: no host synchronisation inside the step, static shapes, the library
     takes the *current* (capturing) stream, the optimiser is built with capturable=True.
+
+    Data parallel (torch.distributed initialised, world > 1): the graph holds forward + backward of the LOCAL
+    model only; all gradients live in one flat buffer that is averaged with a single NCCL all-reduce after the
+    replay (15.9 MB over NVLink), followed by the optimiser step.  No collective is captured, so nothing can
+    dead-lock inside a capture; parameters are broadcast from rank 0 once at construction (what DDP does).
+    BatchNorm statistics stay per process, as in the reference.
+
     Usage: step = GraphedTrainStep(...); loss, output = step(images, labels)  # tensors are static buffers.
     Falls back to eager execution if capture is not possible (the reason is kept in `.fallback_reason`)."""
 
     def __init__(self, model, optimizer, criterion, criterion_dice, example_images, example_labels,
                  amp_dtype=torch.bfloat16, warmup=3):
+        import torch.distributed as dist
+
         self.model, self.optimizer = model, optimizer
         self.criterion, self.criterion_dice, self.amp_dtype = criterion, criterion_dice, amp_dtype
         self.graph, self.fallback_reason, self.library_launches_per_step = None, None, 0
+        self.world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
         self.images = torch.empty_like(example_images)
         self.labels = torch.empty_like(example_labels)
         self.images.copy_(example_images)
         self.labels.copy_(example_labels)
+        self.flat = None
+        if self.world > 1:
+            if isinstance(model, torch.nn.parallel.DistributedDataParallel):
+                raise ValueError("pass the un-wrapped module: GraphedTrainStep does its own gradient all-reduce")
+            with torch.no_grad():
+                for t in list(model.parameters()) + list(model.buffers()):
+                    dist.broadcast(t, 0)
+            params = [p for p in model.parameters() if p.requires_grad]
+            self.flat = torch.zeros(sum(p.numel() for p in params), dtype=params[0].dtype, device=params[0].device)
+            off = 0
+            for p in params:                       # every .grad is a view into the flat all-reduce buffer
+                p.grad = self.flat[off:off + p.numel()].view_as(p)
+                off += p.numel()
+        if self.images.device.type != "cuda":
+            self.fallback_reason = "not a CUDA device: eager execution"
+            return
         try:
             self._capture(warmup)
         except Exception as e:  # noqa: BLE001 - any capture failure means: run eagerly
@@ -120,11 +146,39 @@ class GraphedTrainStep:
             self.fallback_reason = f"{type(e).__name__}: {e}"
             torch.cuda.synchronize()
 
+    # -- pieces -------------------------------------------------------------------------------------
+    def _forward_backward(self):
+        with torch.autocast(self.images.device.type, dtype=self.amp_dtype, enabled=self.amp_dtype is not None):
+            output = self.model(self.images)
+            loss = loss_fn(output, self.labels, self.criterion, self.criterion_dice)
+        if self.flat is not None:
+            self.flat.zero_()                      # grads accumulate in place into the flat views
+        else:
+            self.optimizer.zero_grad(set_to_none=True)
+        loss.backward()
+        return loss, output
+
+    def _reduce_and_step(self):
+        import torch.distributed as dist
+
+        if dist.get_backend() == "nccl":
+            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG)
+        else:                                      # gloo (CPU tests) has no AVG
+            dist.all_reduce(self.flat)
+            self.flat /= self.world
+        self.optimizer.step()
+
     def _eager(self):
-        return train_step(self.model, self.optimizer, self.images, self.labels, self.criterion, self.criterion_dice,
-                          self.amp_dtype)
+        loss, output = self._forward_backward()
+        if self.flat is not None:
+            self._reduce_and_step()
+        else:
+            self.optimizer.step()
+        return loss, output
 
     def _capture(self, warmup):
+        from . import _lib
+
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -132,13 +186,14 @@ class GraphedTrainStep:
                 self._eager()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        from . import _lib
-
         graph = torch.cuda.CUDAGraph()
-        self.optimizer.zero_grad(set_to_none=True)
+        if self.flat is None:
+            self.optimizer.zero_grad(set_to_none=True)
         before = _lib.launch_count()
         with torch.cuda.graph(graph):
-            self.loss, self.output = self._eager()
+            self.loss, self.output = self._forward_backward()
+            if self.flat is None:
+                self.optimizer.step()
         self.library_launches_per_step = _lib.launch_count() - before    # lmnet_b200 kernels inside one replay
         self.graph = graph
 
@@ -149,6 +204,8 @@ class GraphedTrainStep:
             self.loss, self.output = self._eager()
         else:
             self.graph.replay()
+            if self.flat is not None:
+                self._reduce_and_step()
         return self.loss, self.output
 
 

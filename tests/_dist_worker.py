@@ -60,8 +60,32 @@ def run(rank, world, port, out_dir):
     rm = net.conv1[0].large_conv.bn.running_mean.clone()
     rms = [torch.empty_like(rm) for _ in range(world)]
     dist.all_gather(rms, rm)
+    # the flat-buffer data-parallel step used with CUDA graphs (eager here: no GPU) must give the same update
+    from lmnet_b200.train import GraphedTrainStep
+
+    torch.manual_seed(7 + rank)                # different init per rank: the constructor must broadcast rank 0's
+    flat_net = LM_Net(3, 2)
+    for m in flat_net.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    ref_net = LM_Net(3, 2)
+    for m in ref_net.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    opt_f, c_f, d_f = build_training(flat_net, "cpu", fused=False)
+    step = GraphedTrainStep(flat_net, opt_f, c_f, d_f, images, labels, amp_dtype=None)
+    assert step.graph is None and step.flat is not None
+    ref_net.load_state_dict(flat_net.state_dict())          # after the broadcast
+    ref_ddp = D.wrap_ddp(ref_net, "cpu")
+    opt_r, c_r, d_r = build_training(ref_ddp, "cpu", fused=False)
+    step(images, labels)
+    train_step(ref_ddp, opt_r, images, labels, c_r, d_r, amp_dtype=None)
+    # compare the averaged gradients (AdamW's first update is +-lr whatever the gradient's size, so parameters of
+    # ~zero-gradient entries may legitimately differ by 2*lr)
+    gscale = max(float(b.grad.abs().max()) for b in ref_net.parameters())
+    flat_vs_ddp = max(float((a.grad - b.grad).abs().max()) for a, b in zip(flat_net.parameters(), ref_net.parameters())) / gscale
     with open(os.path.join(out_dir, f"rank{rank}.txt"), "w") as f:
-        f.write(f"{worst} {int(same)} {int(not torch.equal(rms[0], rms[1]))}\n")
+        f.write(f"{worst} {int(same)} {int(not torch.equal(rms[0], rms[1]))} {flat_vs_ddp}\n")
     D.cleanup()
 
 

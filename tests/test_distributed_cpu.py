@@ -23,7 +23,8 @@ def test_two_rank_gloo_data_parallel(tmp_path):
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o[-3000:]
     for r in range(2):
-        worst, same, bn_differs = open(tmp_path / f"rank{r}.txt").read().split()
+        worst, same, bn_differs, flat_vs_ddp = open(tmp_path / f"rank{r}.txt").read().split()
+        assert float(flat_vs_ddp) < 1e-6, "flat-buffer all-reduce step != DDP step"
         assert float(worst) < 1e-5, f"DDP gradient != mean of shard gradients ({worst})"
         assert same == "1", "parameters diverged across ranks after one step"
         assert bn_differs == "1", "BatchNorm statistics should stay per-process"
