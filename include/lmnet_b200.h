@@ -217,6 +217,17 @@ size_t lmnet_wgrad_1x1_workspace_bytes(const lmnet_wgrad_dims* dims);
 int lmnet_wgrad_1x1(const void* A, const void* B1, const void* B2, float* dW, float* drow,
                     void* workspace, size_t workspace_bytes, const lmnet_wgrad_dims* dims, int dtype, void* stream);
 
+/* ---- bilinear x2 up-sampling, align_corners=True, NCHW (widening step f3) ----------------------
+ * Replaces nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True) of the decoder and skip blocks
+ * (/root/reference/core/LM_Net.py:58-74, /root/reference/core/modules.py:93-95, 129-131).
+ * x: [planes, H, W] -> y: [planes, 2H, 2W] in `dtype`; the backward maps dy -> dx (gather, deterministic). */
+typedef struct lmnet_upsample_dims {
+    int64_t planes;
+    int32_t H, W;
+} lmnet_upsample_dims;
+int lmnet_upsample2x_fwd(const void* x, void* y, const lmnet_upsample_dims* dims, int dtype, void* stream);
+int lmnet_upsample2x_bwd(const void* dy, void* dx, const lmnet_upsample_dims* dims, int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -24,7 +24,7 @@ enum KernelId : int {
     KID_DW_BWD_REDUCE, KID_DW_FIN_BWD, KID_DW_BWD_DX, KID_DW_BWD_DW, KID_DW_FIN_DW,
     KID_BN_STATS, KID_BN_FIN_FWD, KID_BN_APPLY, KID_BN_BWD_REDUCE, KID_BN_FIN_BWD, KID_BN_BWD_APPLY,
     KID_LN_FWD, KID_LN_BWD, KID_LN_BWD_PARAMS,
-    KID_WGRAD_1X1, KID_WGRAD_REDUCE,
+    KID_WGRAD_1X1, KID_WGRAD_REDUCE, KID_UPSAMPLE_FWD, KID_UPSAMPLE_BWD,
     KID_COUNT
 };
 extern bool g_profile_on;

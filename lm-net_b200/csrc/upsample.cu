@@ -1,0 +1,182 @@
+// upsample.cu — bilinear x2 up-sampling with align_corners=True on NCHW tensors, forward and backward.
+//
+// Widening step f3 of SURVEY.md §8: the nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True)
+// in front of the decoder's up-convolutions and inside the skip-fusion blocks
+// (/root/reference/core/LM_Net.py:58-74, /root/reference/core/modules.py:93-95, 129-131).  Under autocast
+// ATen runs this op in fp32 with a cast on either side (3.5 ms + casts of the round-1 step).  Here it is one
+// bandwidth kernel per direction in the storage type, fp32 interpolation arithmetic with ATen's index rule:
+//   src = dst * (in-1)/(out-1);  i0 = floor(src);  i1 = i0 + (i0 < in-1);  l1 = src - i0;  l0 = 1 - l1.
+// The backward is a gather (no atomics, deterministic): every input pixel sums the <= 6x6 output pixels whose
+// interpolation footprint contains it.
+#include "common.cuh"
+
+namespace lmnet {
+
+struct UpGeom {
+    int H, W, OH, OW;
+    int64_t planes;       // B*C
+    float rh, rw;         // (H-1)/(OH-1), (W-1)/(OW-1)
+};
+
+__device__ __forceinline__ void src_index(int o, float r, int in, int& i0, int& i1, float& l0, float& l1) {
+    const float s = r * (float)o;
+    i0 = (int)s;
+    i1 = i0 + (i0 < in - 1 ? 1 : 0);
+    l1 = s - (float)i0;
+    l0 = 1.f - l1;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+upsample2x_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, UpGeom g) {
+    // one thread: 2 adjacent output columns of one output row of one plane
+    const int64_t pairs_per_row = (g.OW + 1) / 2;
+    const int64_t total = g.planes * g.OH * pairs_per_row;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t pr = idx % pairs_per_row;
+        const int64_t t = idx / pairs_per_row;
+        const int oy = (int)(t % g.OH);
+        const int64_t plane = t / g.OH;
+        int y0, y1;
+        float ly0, ly1;
+        src_index(oy, g.rh, g.H, y0, y1, ly0, ly1);
+        const T* r0 = x + (plane * g.H + y0) * g.W;
+        const T* r1 = x + (plane * g.H + y1) * g.W;
+        float out[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int ox = (int)pr * 2 + k;
+            out[k] = 0.f;
+            if (ox < g.OW) {
+                int x0, x1;
+                float lx0, lx1;
+                src_index(ox, g.rw, g.W, x0, x1, lx0, lx1);
+                out[k] = ly0 * (lx0 * to_f(r0[x0]) + lx1 * to_f(r0[x1])) + ly1 * (lx0 * to_f(r1[x0]) + lx1 * to_f(r1[x1]));
+            }
+        }
+        T* o = y + (plane * g.OH + oy) * g.OW + pr * 2;
+        if ((int)pr * 2 + 1 < g.OW && (g.OW & 1) == 0) {
+            if constexpr (sizeof(T) == 2) {
+                uint32_t raw;
+                T* e = reinterpret_cast<T*>(&raw);
+                e[0] = from_f<T>(out[0]);
+                e[1] = from_f<T>(out[1]);
+                *reinterpret_cast<uint32_t*>(o) = raw;
+            } else {
+                *reinterpret_cast<float2*>(o) = make_float2(out[0], out[1]);
+            }
+        } else {
+            o[0] = from_f<T>(out[0]);
+            if ((int)pr * 2 + 1 < g.OW) o[1] = from_f<T>(out[1]);
+        }
+    }
+}
+
+// weight with which output index o contributes to input index i along one axis
+__device__ __forceinline__ float axis_weight(int o, int i, float r, int in) {
+    int i0, i1;
+    float l0, l1;
+    src_index(o, r, in, i0, i1, l0, l1);
+    float w = 0.f;
+    if (i0 == i) w += l0;
+    if (i1 == i) w += l1;
+    return w;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+upsample2x_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, UpGeom g) {
+    const int64_t total = g.planes * g.H * g.W;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int ix = (int)(idx % g.W);
+        const int64_t t = idx / g.W;
+        const int iy = (int)(t % g.H);
+        const int64_t plane = t / g.H;
+        // candidates: output rows/cols in [2*i - 2, 2*i + 3] (scale is just under 1/2)
+        float wy[6], wx[6];
+        int oy0 = 2 * iy - 2, ox0 = 2 * ix - 2;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            const int oy = oy0 + k, ox = ox0 + k;
+            wy[k] = (oy >= 0 && oy < g.OH) ? axis_weight(oy, iy, g.rh, g.H) : 0.f;
+            wx[k] = (ox >= 0 && ox < g.OW) ? axis_weight(ox, ix, g.rw, g.W) : 0.f;
+        }
+        float acc = 0.f;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+            if (wy[a] != 0.f) {
+                const T* row = dy + (plane * g.OH + oy0 + a) * g.OW;
+                float racc = 0.f;
+#pragma unroll
+                for (int b = 0; b < 6; ++b)
+                    if (wx[b] != 0.f) racc = fmaf(wx[b], to_f(row[ox0 + b]), racc);
+                acc = fmaf(wy[a], racc, acc);
+            }
+        }
+        dx[idx] = from_f<T>(acc);
+    }
+}
+
+static int up_validate(const lmnet_upsample_dims* d) {
+    if (d == nullptr || d->planes <= 0 || d->H <= 0 || d->W <= 0) return LMNET_ERR_INVALID_ARG;
+    return LMNET_OK;
+}
+static UpGeom up_geom(const lmnet_upsample_dims* d) {
+    UpGeom g;
+    g.H = d->H; g.W = d->W; g.OH = 2 * d->H; g.OW = 2 * d->W; g.planes = d->planes;
+    g.rh = g.OH > 1 ? (float)(g.H - 1) / (float)(g.OH - 1) : 0.f;
+    g.rw = g.OW > 1 ? (float)(g.W - 1) / (float)(g.OW - 1) : 0.f;
+    return g;
+}
+static unsigned up_blocks(int64_t total) {
+    int64_t b = (total + 255) / 256;
+    const int64_t cap = 148 * 16;
+    return (unsigned)(b < cap ? (b < 1 ? 1 : b) : cap);
+}
+
+template <typename T>
+static int up_fwd(const void* x, void* y, const lmnet_upsample_dims* d, cudaStream_t st) {
+    UpGeom g = up_geom(d);
+    const int64_t total = g.planes * g.OH * ((g.OW + 1) / 2);
+    const double bytes = (double)g.planes * ((double)g.H * g.W + (double)g.OH * g.OW) * sizeof(T);
+    LMNET_LAUNCH(KID_UPSAMPLE_FWD, st, bytes, (upsample2x_fwd_kernel<T><<<up_blocks(total), 256, 0, st>>>((const T*)x, (T*)y, g)));
+    return LMNET_OK;
+}
+template <typename T>
+static int up_bwd(const void* dy, void* dx, const lmnet_upsample_dims* d, cudaStream_t st) {
+    UpGeom g = up_geom(d);
+    const int64_t total = g.planes * g.H * g.W;
+    const double bytes = (double)g.planes * ((double)g.H * g.W + (double)g.OH * g.OW) * sizeof(T);
+    LMNET_LAUNCH(KID_UPSAMPLE_BWD, st, bytes, (upsample2x_bwd_kernel<T><<<up_blocks(total), 256, 0, st>>>((const T*)dy, (T*)dx, g)));
+    return LMNET_OK;
+}
+
+}  // namespace lmnet
+
+using namespace lmnet;
+
+extern "C" int lmnet_upsample2x_fwd(const void* x, void* y, const lmnet_upsample_dims* dims, int dtype, void* stream) {
+    int rc = up_validate(dims);
+    if (rc != LMNET_OK) return rc;
+    if (!x || !y) return LMNET_ERR_INVALID_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (dtype) {
+        case LMNET_F32: return up_fwd<float>(x, y, dims, st);
+        case LMNET_BF16: return up_fwd<__nv_bfloat16>(x, y, dims, st);
+        case LMNET_F16: return up_fwd<__half>(x, y, dims, st);
+        default: return LMNET_ERR_UNSUPPORTED;
+    }
+}
+
+extern "C" int lmnet_upsample2x_bwd(const void* dy, void* dx, const lmnet_upsample_dims* dims, int dtype, void* stream) {
+    int rc = up_validate(dims);
+    if (rc != LMNET_OK) return rc;
+    if (!dy || !dx) return LMNET_ERR_INVALID_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (dtype) {
+        case LMNET_F32: return up_bwd<float>(dy, dx, dims, st);
+        case LMNET_BF16: return up_bwd<__nv_bfloat16>(dy, dx, dims, st);
+        case LMNET_F16: return up_bwd<__half>(dy, dx, dims, st);
+        default: return LMNET_ERR_UNSUPPORTED;
+    }
+}

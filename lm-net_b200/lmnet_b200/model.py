@@ -27,6 +27,7 @@ from natten import NeighborhoodAttention2D
 from .bnact import conv_bn_act
 from .layernorm import layer_norm
 from .reparam import reparam_forward
+from .upsample import Upsample2x
 
 
 def _conv_bn(channels: int, kernel, padding) -> nn.Sequential:
@@ -150,7 +151,7 @@ class NeighborhoodTransformer(nn.Module):
 
 
 def _up2():
-    return nn.Upsample(scale_factor=2, mode="bilinear", align_corners=True)
+    return Upsample2x()     # nn.Upsample(scale_factor=2, mode="bilinear", align_corners=True) on our kernel
 
 
 class M3Skip(nn.Module):

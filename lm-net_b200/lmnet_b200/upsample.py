@@ -1,0 +1,51 @@
+"""Bilinear x2 up-sampling (align_corners=True) on the sm_100a kernels of ``csrc/upsample.cu`` — widening
+step f3 of SURVEY.md §8: the ``nn.Upsample`` of the decoder (/root/reference/core/LM_Net.py:58-74) and of the
+skip-fusion blocks (/root/reference/core/modules.py:93-95, 129-131).  Stays in the storage type (autocast's
+stock op converts to fp32 and back), interpolation arithmetic in fp32 with ATen's index rule."""
+from __future__ import annotations
+
+import torch
+from torch.amp import custom_bwd, custom_fwd
+
+from . import _lib as L
+
+
+class _Up2x(torch.autograd.Function):
+    @staticmethod
+    @custom_fwd(device_type="cuda")
+    def forward(ctx, x):
+        L.require_cuda(x)
+        x = x.contiguous()
+        B, C, H, W = x.shape
+        y = torch.empty(B, C, 2 * H, 2 * W, dtype=x.dtype, device=x.device)
+        dims = L.UpsampleDims(B * C, H, W)
+        L.check(L.lib().lmnet_upsample2x_fwd(L.ptr(x), L.ptr(y), L.byref(dims), L.dtype_code(x), L.stream_ptr()),
+                "upsample2x_fwd")
+        ctx.shape = (B, C, H, W)
+        return y
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, dy):
+        B, C, H, W = ctx.shape
+        dy = dy.contiguous()
+        dx = torch.empty(B, C, H, W, dtype=dy.dtype, device=dy.device)
+        dims = L.UpsampleDims(B * C, H, W)
+        L.check(L.lib().lmnet_upsample2x_bwd(L.ptr(dy), L.ptr(dx), L.byref(dims), L.dtype_code(dy), L.stream_ptr()),
+                "upsample2x_bwd")
+        return dx
+
+
+class Upsample2x(torch.nn.Module):
+    """Drop-in for nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True) (no parameters, so
+    state_dicts are unaffected).  CUDA tensors run the fused kernel; anything else uses F.interpolate."""
+
+    scale_factor, mode, align_corners = 2, "bilinear", True
+
+    def forward(self, x):
+        if x.is_cuda and x.dim() == 4 and x.dtype in (torch.float32, torch.bfloat16, torch.float16):
+            return _Up2x.apply(x)
+        return torch.nn.functional.interpolate(x, scale_factor=2, mode="bilinear", align_corners=True)
+
+    def extra_repr(self):
+        return "scale_factor=2, mode='bilinear', align_corners=True"
