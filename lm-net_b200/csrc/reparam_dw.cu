@@ -823,7 +823,8 @@ static DwGeom dw_geom(const lmnet_dw_dims* d, int th, int tw) {
     g.B = d->B; g.E = d->E; g.H = d->H; g.W = d->W;
     g.stripes = (d->W + tw - 1) / tw;
     const int row_tiles = (d->H + th - 1) / th;
-    int bands = (4 * 148 + g.E * g.stripes - 1) / (g.E * g.stripes);
+    static const int kCtaTarget = getenv("LMNET_DW_CTAS") ? atoi(getenv("LMNET_DW_CTAS")) : 4 * 148;
+    int bands = (kCtaTarget + g.E * g.stripes - 1) / (g.E * g.stripes);
     bands = bands < 1 ? 1 : bands > row_tiles ? row_tiles : bands;
     const int tiles_per_band = (row_tiles + bands - 1) / bands;
     g.rows_per_band = tiles_per_band * th;
@@ -968,7 +969,12 @@ static int dw_train_bwd(const void* x, const void* u, const void* dz, const floa
     T* du = (T*)(ws + L.du);
     const void* vp[4] = {x, u, dz, du};
     const int vb = dw_vec_bytes(vp, 4, d, sizeof(T));
-    int rc = with_vec<T>(vb, [&](auto v) -> int {
+    const bool use_mma = dw_mma_ok<T>(d, x) && ((uintptr_t)u % 4 == 0) && ((uintptr_t)dz % 4 == 0);
+    int rc = LMNET_OK;
+    if constexpr (sizeof(T) == 2) {
+        if (use_mma) LMNET_LAUNCH(KID_DW_BWD_REDUCE, st, 2 * t_bytes, (dw_bwd_reduce_mma_kernel<T><<<grid, kDwThreads, 0, st>>>((const T*)x, (const T*)u, (const T*)dz, dpool, du, part, g)));
+    }
+    if (!use_mma) rc = with_vec<T>(vb, [&](auto v) -> int {
         constexpr int VEC = decltype(v)::value;
         LMNET_LAUNCH(KID_DW_BWD_REDUCE, st, 2 * t_bytes, (dw_bwd_reduce_kernel<T, VEC><<<grid, kDwThreads, 0, st>>>((const T*)x, (const T*)u, (const T*)dz, dpool, du, part, g)));
         return LMNET_OK;

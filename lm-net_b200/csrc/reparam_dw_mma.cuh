@@ -282,4 +282,121 @@ dw_apply_mma_kernel(const T* __restrict__ x, const float* __restrict__ coef, T* 
         });
 }
 
+// ---------------------------------------------------------------------------------------------------
+// backward R pass on tensor cores: du = (dz + dpool/HW) * gelu'(u) (written out), sum du, and the 25 lag
+// sums P[a][b] = sum_p du(p) * x(p + (a-2, b-2)) as Gram products: for each row offset a
+//     G_a[i][j] += sum_r X[r + a][i] * du[r][j]      (M = 16 input columns, N = 8 output columns, K = 16 rows)
+// and P[a][b] = sum_j G_a[j + b][j].  Both operands are read transposed out of shared memory
+// (ldmatrix.trans); the five 16x8 accumulators persist over all tiles of the CTA.
+// ---------------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ void load_a_trans(const T* s_tile, int row, int col, int lane, uint32_t (&a)[4]) {
+    const int m = lane >> 3, rr = lane & 7;
+    const uint32_t addr = (uint32_t)__cvta_generic_to_shared(s_tile + (row + (m >> 1) * 8 + rr) * kMmaPitch + col + (m & 1) * 8);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]) : "r"(addr));
+}
+template <typename T>
+__device__ __forceinline__ void load_b_trans(const T* s_tile, int row, int col, int lane, uint32_t (&b)[2]) {
+    const int l = lane & 15;
+    const uint32_t addr = (uint32_t)__cvta_generic_to_shared(s_tile + (row + l) * kMmaPitch + col);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(b[0]), "=r"(b[1]) : "r"(addr));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kDwThreads)
+dw_bwd_reduce_mma_kernel(const T* __restrict__ x, const T* __restrict__ u, const T* __restrict__ dz,
+                         const float* __restrict__ dpool, T* __restrict__ du_out, float* __restrict__ part /* [E][ncta][26] */,
+                         DwGeom g) {
+    __shared__ __align__(16) T s_x[kMmaTileRows * kMmaPitch];
+    __shared__ __align__(16) T s_u[kMmaTH * kMmaPitch];
+    __shared__ __align__(16) T s_dz[kMmaTH * kMmaPitch];
+    __shared__ __align__(16) T s_du[kMmaTH * kMmaPitch];
+    __shared__ float s_P[26];
+    const int e = blockIdx.z, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wr = warp >> 1, wc = warp & 1;
+    const int c0 = blockIdx.x * kMmaTW;
+    const int band0 = blockIdx.y * g.rows_per_band, band1 = min(band0 + g.rows_per_band, g.H);
+    const float inv_hw = 1.f / ((float)g.H * (float)g.W);
+    if (threadIdx.x < 26) s_P[threadIdx.x] = 0.f;
+    float G[5][4];
+#pragma unroll
+    for (int a = 0; a < 5; ++a) G[a][0] = G[a][1] = G[a][2] = G[a][3] = 0.f;
+    float sdu = 0.f;
+
+    const int ntr = (band1 - band0 + kMmaTH - 1) / kMmaTH;
+    const int total = band1 > band0 ? g.B * ntr : 0;
+    MmaTileLoader<T, kMmaTileRows> lx;
+    MmaTileLoader<T, kMmaTH> lu, lz;
+    auto fetch = [&](int t) {
+        const int b = t / ntr, tr = band0 + (t - b * ntr) * kMmaTH;
+        const int64_t poff = ((int64_t)b * g.E + e) * g.H * g.W;
+        lx.fetch(x + poff, g.H, g.W, tr - 2, c0 - 2);
+        lu.fetch(u + poff, g.H, g.W, tr, c0);
+        lz.fetch(dz + poff, g.H, g.W, tr, c0);
+    };
+    if (total > 0) fetch(0);
+    for (int t = 0; t < total; ++t) {
+        const int b = t / ntr, tr = band0 + (t - b * ntr) * kMmaTH;
+        const int64_t poff = ((int64_t)b * g.E + e) * g.H * g.W;
+        __syncthreads();
+        lx.commit(s_x);
+        lu.commit(s_u);
+        lz.commit(s_dz);
+        __syncthreads();
+        if (t + 1 < total) fetch(t + 1);
+        // phase 1: du for the 32 x 64 tile (thread: row = warp*8 + o, column pair = lane)
+        const float dp = dpool != nullptr ? __ldg(dpool + b * g.E + e) * inv_hw : 0.f;
+        const int col = c0 + 2 * lane;
+#pragma unroll
+        for (int o = 0; o < 8; ++o) {
+            const int trow = warp * 8 + o, row = tr + trow;
+            uint32_t packed = 0u;
+            if (row < band1 && col < g.W) {               // W even: the pair is all in or all out
+                const uint32_t ur = *reinterpret_cast<const uint32_t*>(s_u + trow * kMmaPitch + 2 * lane);
+                const uint32_t zr = *reinterpret_cast<const uint32_t*>(s_dz + trow * kMmaPitch + 2 * lane);
+                const T* ue = reinterpret_cast<const T*>(&ur);
+                const T* ze = reinterpret_cast<const T*>(&zr);
+                const float d0 = (to_f(ze[0]) + dp) * gelu_grad_f(to_f(ue[0]));
+                const float d1 = (to_f(ze[1]) + dp) * gelu_grad_f(to_f(ue[1]));
+                packed = MmaOp<T>::pack(d0, d1);
+                *reinterpret_cast<uint32_t*>(du_out + poff + (int64_t)row * g.W + col) = packed;
+                const T* de = reinterpret_cast<const T*>(&packed);
+                sdu += to_f(de[0]) + to_f(de[1]);             // exactly what later passes read back
+            }
+            *reinterpret_cast<uint32_t*>(s_du + trow * kMmaPitch + 2 * lane) = packed;
+        }
+        __syncthreads();
+        // phase 2: Gram MMAs of this warp's 16 rows x 32 columns
+#pragma unroll
+        for (int cb = 0; cb < 4; ++cb) {
+            const int tcol = 32 * wc + 8 * cb;
+            uint32_t Bf[2];
+            load_b_trans(s_du, 16 * wr, tcol, lane, Bf);
+#pragma unroll
+            for (int a = 0; a < 5; ++a) {
+                uint32_t A[4];
+                load_a_trans(s_x, 16 * wr + a, tcol, lane, A);
+                MmaOp<T>::run(G[a], A, Bf);
+            }
+        }
+    }
+    // P[a][b] = sum_j G_a[j + b][j]: this lane holds (i = gq, gq+8 ; j = 2tq, 2tq+1)
+    __syncthreads();
+    const int gq = lane >> 2, tq = lane & 3;
+#pragma unroll
+    for (int a = 0; a < 5; ++a)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int i = gq + (k >> 1) * 8, j = 2 * tq + (k & 1);
+            const int bb = i - j;
+            if (bb >= 0 && bb < 5) atomicAdd(&s_P[a * 5 + bb], G[a][k]);
+        }
+    sdu = warp_sum(sdu);
+    if (lane == 0) atomicAdd(&s_P[25], sdu);
+    __syncthreads();
+    const int ncta = gridDim.x * gridDim.y, cta = blockIdx.y * gridDim.x + blockIdx.x;
+    if (threadIdx.x < 26) part[((int64_t)e * ncta + cta) * 26 + threadIdx.x] = s_P[threadIdx.x];
+}
+
 }  // namespace lmnet
