@@ -27,14 +27,13 @@ struct BnGeom {
 
 template <int ACT> __device__ __forceinline__ float act_fwd(float x) {
     if constexpr (ACT == LMNET_ACT_HARDSWISH) return x * fminf(fmaxf(x + 3.f, 0.f), 6.f) * (1.f / 6.f);
-    else if constexpr (ACT == LMNET_ACT_GELU) return 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
+    else if constexpr (ACT == LMNET_ACT_GELU) return gelu_fast(x);
     else if constexpr (ACT == LMNET_ACT_RELU) return fmaxf(x, 0.f);
     else return x;
 }
 template <int ACT> __device__ __forceinline__ float act_bwd(float x) {
     if constexpr (ACT == LMNET_ACT_HARDSWISH) return x < -3.f ? 0.f : (x <= 3.f ? (2.f * x + 3.f) * (1.f / 6.f) : 1.f);
-    else if constexpr (ACT == LMNET_ACT_GELU)
-        return 0.5f * (1.f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+    else if constexpr (ACT == LMNET_ACT_GELU) return gelu_grad_fast(x);
     else if constexpr (ACT == LMNET_ACT_RELU) return x > 0.f ? 1.f : 0.f;
     else return 1.f;
 }

@@ -265,10 +265,8 @@ __device__ __forceinline__ void block_sum(float (&v)[N], float* s_red /* [kDwWar
     }
 }
 
-__device__ __forceinline__ float gelu_f(float u) { return 0.5f * u * (1.f + erff(u * 0.70710678118654752f)); }
-__device__ __forceinline__ float gelu_grad_f(float u) {
-    return 0.5f * (1.f + erff(u * 0.70710678118654752f)) + u * 0.3989422804014327f * __expf(-0.5f * u * u);
-}
+__device__ __forceinline__ float gelu_f(float u) { return gelu_fast(u); }
+__device__ __forceinline__ float gelu_grad_f(float u) { return gelu_grad_fast(u); }
 
 template <typename T>
 __device__ __forceinline__ f2 load_pair(const T* __restrict__ p, bool v0, bool v1, bool vec) {
@@ -992,10 +990,13 @@ static int dw_train_bwd(const void* x, const void* u, const void* dz, const floa
         }
         dim3 ga_grid(ga.stripes, ga.bands, ga.E);
         LMNET_LAUNCH(KID_DW_BWD_DX, st, 3 * t_bytes, (dw_bwd_dx_kernel<T, VEC><<<ga_grid, kDwThreads, kA1SmemBytes, st>>>((const T*)x, du, *p, cb, (T*)dx, ga)));
-        LMNET_LAUNCH(KID_DW_BWD_DW, st, 0, (dw_bwd_dw_kernel<T, VEC><<<grid, kDwThreads, 0, st>>>((const T*)x, *p, cb, part, g)));
+        if (!use_mma) LMNET_LAUNCH(KID_DW_BWD_DW, st, 0, (dw_bwd_dw_kernel<T, VEC><<<grid, kDwThreads, 0, st>>>((const T*)x, *p, cb, part, g)));
         return LMNET_OK;
     });
     if (rc != LMNET_OK) return rc;
+    if constexpr (sizeof(T) == 2) {
+        if (use_mma) LMNET_LAUNCH(KID_DW_BWD_DW, st, 0, (dw_bwd_dw_mma_kernel<T><<<grid, kDwThreads, 0, st>>>((const T*)x, *p, cb, part, g)));
+    }
     LMNET_LAUNCH(KID_DW_FIN_DW, st, 0, (dw_fin_dw_kernel<<<g.E, 64, 0, st>>>(part, ncta, pfin, cb, *gr, g.E)));
     return LMNET_OK;
 }

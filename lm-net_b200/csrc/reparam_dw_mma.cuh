@@ -399,4 +399,139 @@ dw_bwd_reduce_mma_kernel(const T* __restrict__ x, const T* __restrict__ u, const
     if (threadIdx.x < 26) part[((int64_t)e * ncta + cta) * 26 + threadIdx.x] = s_P[threadIdx.x];
 }
 
+// ---------------------------------------------------------------------------------------------------
+// backward A2 pass on tensor cores: R_br[t] = sum_p (c2_br*y_br(p) + c0_br) * x(p+t).
+// y_br from the Toeplitz MMAs (as in the statistics pass), g_br = c2*y + c0 rounded to the storage type
+// into shared memory, then Gram MMAs  G_{br,a}[i][j] += sum_r X[r+a][i] * g_br[r][j]  with the twelve
+// (branch, kernel-row) accumulators kept in registers for the whole CTA; R_br[a][b] = sum_j G[j+b][j].
+// (g_br is the small BatchNorm-variance correction of the weight gradient: 16-bit rounding of it is far
+// below the tolerance; the main term c1*P[t] comes from the reduce pass in fp32.)
+// ---------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kDwThreads)
+dw_bwd_dw_mma_kernel(const T* __restrict__ x, lmnet_dw_params p, const float* __restrict__ cb,
+                     float* __restrict__ part /* [E][ncta][40] */, DwGeom g) {
+    __shared__ __align__(16) T s_x[kMmaTileRows * kMmaPitch];
+    __shared__ __align__(16) T s_g[4][kMmaTH * kMmaPitch];
+    __shared__ float s_R[40];
+    const int e = blockIdx.z, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wr = warp >> 1, wc = warp & 1;
+    const int c0 = blockIdx.x * kMmaTW;
+    const int band0 = blockIdx.y * g.rows_per_band, band1 = min(band0 + g.rows_per_band, g.H);
+    if (threadIdx.x < 40) s_R[threadIdx.x] = 0.f;
+    uint32_t B5[5][2], B3[3][2], B31[3][2], B13[2];
+    {
+        float w5[25], w3[9], w31[3], w13[3];
+#pragma unroll
+        for (int t = 0; t < 25; ++t) w5[t] = __ldg(p.w[0] + e * 25 + t);
+#pragma unroll
+        for (int t = 0; t < 9; ++t) w3[t] = __ldg(p.w[1] + e * 9 + t);
+#pragma unroll
+        for (int t = 0; t < 3; ++t) { w31[t] = __ldg(p.w[2] + e * 3 + t); w13[t] = __ldg(p.w[3] + e * 3 + t); }
+#pragma unroll
+        for (int a = 0; a < 5; ++a) toeplitz_frag<T>(w5 + a * 5, 5, 0, lane, B5[a]);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            toeplitz_frag<T>(w3 + a * 3, 3, 1, lane, B3[a]);
+            toeplitz_frag<T>(w31 + a, 1, 2, lane, B31[a]);
+        }
+        toeplitz_frag<T>(w13, 3, 1, lane, B13);
+    }
+    float c2[4], c0c[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        c2[k] = __ldg(cb + e * 12 + k * 3 + 1);
+        c0c[k] = __ldg(cb + e * 12 + k * 3 + 2);
+    }
+    // Gram accumulators: 5x5 rows a=0..4 | 3x3 rows a=1..3 | 3x1 rows a=1..3 | 1x3 row a=2
+    float G5[5][4], G3[3][4], G31[3][4], G13[4];
+#pragma unroll
+    for (int a = 0; a < 5; ++a) G5[a][0] = G5[a][1] = G5[a][2] = G5[a][3] = 0.f;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        G3[a][0] = G3[a][1] = G3[a][2] = G3[a][3] = 0.f;
+        G31[a][0] = G31[a][1] = G31[a][2] = G31[a][3] = 0.f;
+    }
+    G13[0] = G13[1] = G13[2] = G13[3] = 0.f;
+    const int gq = lane >> 2, tq = lane & 3;
+    mma_for_each_tile<T, kMmaTileRows>(
+        g, band0, band1, kMmaTH, 2, c0, s_x,
+        [&](int b) { return x + ((int64_t)b * g.E + e) * g.H * g.W; },
+        [&](int, int tr, bool) {
+            const int row_lo = tr + 16 * wr + gq;
+            const float rm0 = row_lo < band1 ? 1.f : 0.f, rm1 = row_lo + 8 < band1 ? 1.f : 0.f;
+            // phase 1: y_br of this warp's 16 x 32 block -> g_br tiles
+#pragma unroll
+            for (int cbk = 0; cbk < 4; ++cbk) {
+                float acc[4][4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) acc[k][0] = acc[k][1] = acc[k][2] = acc[k][3] = 0.f;
+                const int tcol = 32 * wc + 8 * cbk;
+#pragma unroll
+                for (int a = 0; a < 5; ++a) {
+                    uint32_t A[4];
+                    load_a(s_x, 16 * wr + a, tcol, lane, A);
+                    MmaOp<T>::run(acc[0], A, B5[a]);
+                    if (a >= 1 && a <= 3) {
+                        MmaOp<T>::run(acc[1], A, B3[a - 1]);
+                        MmaOp<T>::run(acc[2], A, B31[a - 1]);
+                    }
+                    if (a == 2) MmaOp<T>::run(acc[3], A, B13);
+                }
+                const int col = c0 + tcol + 2 * tq;
+                const float cm = col < g.W ? 1.f : 0.f;         // W even: pair in or out together
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t lo = MmaOp<T>::pack((c2[k] * acc[k][0] + c0c[k]) * rm0 * cm, (c2[k] * acc[k][1] + c0c[k]) * rm0 * cm);
+                    const uint32_t hi = MmaOp<T>::pack((c2[k] * acc[k][2] + c0c[k]) * rm1 * cm, (c2[k] * acc[k][3] + c0c[k]) * rm1 * cm);
+                    *reinterpret_cast<uint32_t*>(&s_g[k][(16 * wr + gq) * kMmaPitch + tcol + 2 * tq]) = lo;
+                    *reinterpret_cast<uint32_t*>(&s_g[k][(16 * wr + gq + 8) * kMmaPitch + tcol + 2 * tq]) = hi;
+                }
+            }
+            __syncwarp();      // each warp reads back only the 16 x 32 block it wrote
+            // phase 2: Gram products
+#pragma unroll
+            for (int cbk = 0; cbk < 4; ++cbk) {
+                const int tcol = 32 * wc + 8 * cbk;
+                uint32_t Bg[4][2];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) load_b_trans(s_g[k], 16 * wr, tcol, lane, Bg[k]);
+#pragma unroll
+                for (int a = 0; a < 5; ++a) {
+                    uint32_t A[4];
+                    load_a_trans(s_x, 16 * wr + a, tcol, lane, A);
+                    MmaOp<T>::run(G5[a], A, Bg[0]);
+                    if (a >= 1 && a <= 3) {
+                        MmaOp<T>::run(G3[a - 1], A, Bg[1]);
+                        MmaOp<T>::run(G31[a - 1], A, Bg[2]);
+                    }
+                    if (a == 2) MmaOp<T>::run(G13, A, Bg[3]);
+                }
+            }
+        });
+    // R_br[a][b] = sum_j G[j + b][j]; this lane holds (i = gq, gq+8 ; j = 2tq, 2tq+1); b = i - j is the 5-wide offset
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int i = gq + (k >> 1) * 8, j = 2 * tq + (k & 1);
+        const int bb = i - j;
+        if (bb >= 0 && bb < 5) {
+#pragma unroll
+            for (int a = 0; a < 5; ++a) atomicAdd(&s_R[a * 5 + bb], G5[a][k]);
+            if (bb >= 1 && bb <= 3) {
+#pragma unroll
+                for (int a = 0; a < 3; ++a) atomicAdd(&s_R[25 + a * 3 + (bb - 1)], G3[a][k]);
+                atomicAdd(&s_R[37 + (bb - 1)], G13[k]);
+            }
+            if (bb == 2) {
+#pragma unroll
+                for (int a = 0; a < 3; ++a) atomicAdd(&s_R[34 + a], G31[a][k]);
+            }
+        }
+    }
+    __syncthreads();
+    const int ncta = gridDim.x * gridDim.y, cta = blockIdx.y * gridDim.x + blockIdx.x;
+    if (threadIdx.x < 40) part[((int64_t)e * ncta + cta) * 40 + threadIdx.x] = s_R[threadIdx.x];
+}
+
 }  // namespace lmnet
