@@ -979,8 +979,16 @@ static int dw_train_bwd(const void* x, const void* u, const void* dz, const floa
     });
     if (rc != LMNET_OK) return rc;
     LMNET_LAUNCH(KID_DW_FIN_BWD, st, 0, (dw_fin_bwd_kernel<<<(g.E + 63) / 64, 64, 0, st>>>(part, ncta, *p, save_mean, save_rstd, *gr, pfin, cb, g)));
+    if constexpr (sizeof(T) == 2) {
+        if (use_mma) {
+            DwGeom gm = dw_geom(d, kDxTH, kDxTW);
+            dim3 gm_grid(gm.stripes, gm.bands, gm.E);
+            LMNET_LAUNCH(KID_DW_BWD_DX, st, 3 * t_bytes, (dw_bwd_dx_mma_kernel<T><<<gm_grid, kDwThreads, kDxMmaSmemBytes, st>>>((const T*)x, du, *p, cb, (T*)dx, gm)));
+        }
+    }
     rc = with_vec<T>(vb, [&](auto v) -> int {
         constexpr int VEC = decltype(v)::value;
+        if (use_mma) return LMNET_OK;
         DwGeom ga = dw_geom(d, kA1TH, kA1TW);
         static bool attr_set = false;  // benign race: the attribute is idempotent
         if (!attr_set) {

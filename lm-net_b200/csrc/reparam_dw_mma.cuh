@@ -534,4 +534,169 @@ dw_bwd_dw_mma_kernel(const T* __restrict__ x, lmnet_dw_params p, const float* __
     if (threadIdx.x < 40) part[((int64_t)e * ncta + cta) * 40 + threadIdx.x] = s_R[threadIdx.x];
 }
 
+// ---------------------------------------------------------------------------------------------------
+// backward A1 pass on tensor cores: dx = sum_br w_br (*)^T dy_br,  dy_br = c1*du - c2*y_br - c0 in the image.
+// Per CTA tile: dx block of 28 x 56 pixels; dy region 32 x 64 with origin (tr-2, c0-2); x tile with origin
+// (tr-4, c0-4).  Phase 1: y_br on the region by Toeplitz MMAs -> dy_br (storage type) into shared memory.
+// Phase 2: dx by Toeplitz MMAs with the FLIPPED taps over the four dy tiles, all branches into one accumulator.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kDxTH = 28, kDxTW = 56;
+
+template <typename T>
+__global__ void __launch_bounds__(kDwThreads)
+dw_bwd_dx_mma_kernel(const T* __restrict__ x, const T* __restrict__ du, lmnet_dw_params p, const float* __restrict__ cb,
+                     T* __restrict__ dx, DwGeom g) {
+    extern __shared__ __align__(16) unsigned char dx_smem_raw[];
+    T* s_x = reinterpret_cast<T*>(dx_smem_raw);                 // [36][72]
+    T* s_du = s_x + kMmaTileRows * kMmaPitch;                   // [32][72]
+    T* s_dy = s_du + kMmaTH * kMmaPitch;                        // [4][36][72]
+    const int e = blockIdx.z, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wr = warp >> 1, wc = warp & 1;
+    const int c0 = blockIdx.x * kDxTW;
+    const int band0 = blockIdx.y * g.rows_per_band, band1 = min(band0 + g.rows_per_band, g.H);
+    uint32_t B5[5][2], B3[3][2], B31[3][2], B13[2];           // forward taps (phase 1)
+    uint32_t F5[5][2], F3[3][2], F31[3][2], F13[2];           // flipped taps (phase 2), indexed by a' = row offset
+    {
+        float w5[25], w3[9], w31[3], w13[3], f[5];
+#pragma unroll
+        for (int t = 0; t < 25; ++t) w5[t] = __ldg(p.w[0] + e * 25 + t);
+#pragma unroll
+        for (int t = 0; t < 9; ++t) w3[t] = __ldg(p.w[1] + e * 9 + t);
+#pragma unroll
+        for (int t = 0; t < 3; ++t) { w31[t] = __ldg(p.w[2] + e * 3 + t); w13[t] = __ldg(p.w[3] + e * 3 + t); }
+#pragma unroll
+        for (int a = 0; a < 5; ++a) {
+            toeplitz_frag<T>(w5 + a * 5, 5, 0, lane, B5[a]);
+#pragma unroll
+            for (int j = 0; j < 5; ++j) f[j] = w5[(4 - a) * 5 + (4 - j)];
+            toeplitz_frag<T>(f, 5, 0, lane, F5[a]);
+        }
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {                          // a <-> a' = a + 1
+            toeplitz_frag<T>(w3 + a * 3, 3, 1, lane, B3[a]);
+            toeplitz_frag<T>(w31 + a, 1, 2, lane, B31[a]);
+#pragma unroll
+            for (int j = 0; j < 3; ++j) f[j] = w3[(2 - a) * 3 + (2 - j)];
+            toeplitz_frag<T>(f, 3, 1, lane, F3[a]);
+            f[0] = w31[2 - a];
+            toeplitz_frag<T>(f, 1, 2, lane, F31[a]);
+        }
+        toeplitz_frag<T>(w13, 3, 1, lane, B13);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) f[j] = w13[2 - j];
+        toeplitz_frag<T>(f, 3, 1, lane, F13);
+    }
+    float c1[4], c2[4], c0c[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        c1[k] = __ldg(cb + e * 12 + k * 3);
+        c2[k] = __ldg(cb + e * 12 + k * 3 + 1);
+        c0c[k] = __ldg(cb + e * 12 + k * 3 + 2);
+    }
+    // rows 32..35 of the dy tiles are read (for discarded outputs only) but never written: keep them finite
+    for (int i = threadIdx.x; i < 4 * 4 * kMmaPitch; i += kDwThreads) {
+        const int k = i / (4 * kMmaPitch), r = i - k * 4 * kMmaPitch;
+        s_dy[k * kMmaTileRows * kMmaPitch + kMmaTH * kMmaPitch + r] = from_f<T>(0.f);
+    }
+    const int gq = lane >> 2, tq = lane & 3;
+    const int ntr = (band1 - band0 + kDxTH - 1) / kDxTH;
+    const int total = band1 > band0 ? g.B * ntr : 0;
+    MmaTileLoader<T, kMmaTileRows> lx;
+    MmaTileLoader<T, kMmaTH> ld;
+    auto fetch = [&](int t) {
+        const int b = t / ntr, tr = band0 + (t - b * ntr) * kDxTH;
+        const int64_t poff = ((int64_t)b * g.E + e) * g.H * g.W;
+        lx.fetch(x + poff, g.H, g.W, tr - 4, c0 - 4);
+        ld.fetch(du + poff, g.H, g.W, tr - 2, c0 - 2);
+    };
+    if (total > 0) fetch(0);
+    for (int t = 0; t < total; ++t) {
+        const int b = t / ntr, tr = band0 + (t - b * ntr) * kDxTH;
+        const int64_t poff = ((int64_t)b * g.E + e) * g.H * g.W;
+        __syncthreads();
+        lx.commit(s_x);
+        ld.commit(s_du);
+        __syncthreads();
+        if (t + 1 < total) fetch(t + 1);
+        // phase 1: dy_br on this warp's 16 x 32 block of the region
+        {
+            const int rho0 = 16 * wr + gq;                         // region rows rho0, rho0 + 8
+            const int row0 = tr - 2 + rho0, row1 = row0 + 8;
+            const bool rin0 = row0 >= 0 && row0 < g.H, rin1 = row1 >= 0 && row1 < g.H;
+#pragma unroll
+            for (int cbk = 0; cbk < 4; ++cbk) {
+                float acc[4][4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) acc[k][0] = acc[k][1] = acc[k][2] = acc[k][3] = 0.f;
+                const int tcol = 32 * wc + 8 * cbk;                // region column of the block = x-tile index
+#pragma unroll
+                for (int a = 0; a < 5; ++a) {
+                    uint32_t A[4];
+                    load_a(s_x, 16 * wr + a, tcol, lane, A);
+                    MmaOp<T>::run(acc[0], A, B5[a]);
+                    if (a >= 1 && a <= 3) {
+                        MmaOp<T>::run(acc[1], A, B3[a - 1]);
+                        MmaOp<T>::run(acc[2], A, B31[a - 1]);
+                    }
+                    if (a == 2) MmaOp<T>::run(acc[3], A, B13);
+                }
+                const int kap = tcol + 2 * tq;                     // region column of this lane's pair
+                const int col = c0 - 2 + kap;
+                const bool cin = col >= 0 && col < g.W;            // W even, col even: pair in or out together
+                const uint32_t d0r = *reinterpret_cast<const uint32_t*>(s_du + rho0 * kMmaPitch + kap);
+                const uint32_t d1r = *reinterpret_cast<const uint32_t*>(s_du + (rho0 + 8) * kMmaPitch + kap);
+                const T* d0 = reinterpret_cast<const T*>(&d0r);
+                const T* d1 = reinterpret_cast<const T*>(&d1r);
+                const float m0 = (rin0 && cin) ? 1.f : 0.f, m1 = (rin1 && cin) ? 1.f : 0.f;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t lo = MmaOp<T>::pack((c1[k] * to_f(d0[0]) - c2[k] * acc[k][0] - c0c[k]) * m0,
+                                                       (c1[k] * to_f(d0[1]) - c2[k] * acc[k][1] - c0c[k]) * m0);
+                    const uint32_t hi = MmaOp<T>::pack((c1[k] * to_f(d1[0]) - c2[k] * acc[k][2] - c0c[k]) * m1,
+                                                       (c1[k] * to_f(d1[1]) - c2[k] * acc[k][3] - c0c[k]) * m1);
+                    T* tile = s_dy + k * kMmaTileRows * kMmaPitch;
+                    *reinterpret_cast<uint32_t*>(tile + rho0 * kMmaPitch + kap) = lo;
+                    *reinterpret_cast<uint32_t*>(tile + (rho0 + 8) * kMmaPitch + kap) = hi;
+                }
+            }
+        }
+        __syncthreads();
+        // phase 2: dx blocks (2 row tiles x 7 column blocks; warp (wr, wc) takes row tile wr, column blocks 4wc..)
+#pragma unroll
+        for (int cbk = 0; cbk < 4; ++cbk) {
+            const int blk = 4 * wc + cbk;
+            if (blk < kDxTW / 8) {
+                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                const int tcol = 8 * blk;                          // dx column c <-> region index c + b'
+#pragma unroll
+                for (int a = 0; a < 5; ++a) {
+                    uint32_t A[4];
+                    load_a(s_dy, 16 * wr + a, tcol, lane, A);
+                    MmaOp<T>::run(acc, A, F5[a]);
+                    if (a >= 1 && a <= 3) {
+                        load_a(s_dy + kMmaTileRows * kMmaPitch, 16 * wr + a, tcol, lane, A);
+                        MmaOp<T>::run(acc, A, F3[a - 1]);
+                        load_a(s_dy + 2 * kMmaTileRows * kMmaPitch, 16 * wr + a, tcol, lane, A);
+                        MmaOp<T>::run(acc, A, F31[a - 1]);
+                    }
+                    if (a == 2) {
+                        load_a(s_dy + 3 * kMmaTileRows * kMmaPitch, 16 * wr + a, tcol, lane, A);
+                        MmaOp<T>::run(acc, A, F13);
+                    }
+                }
+                const int col = c0 + tcol + 2 * tq;
+                if (col < g.W) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int r = 16 * wr + gq + 8 * h, row = tr + r;
+                        if (r < kDxTH && row < band1)
+                            *reinterpret_cast<uint32_t*>(dx + poff + (int64_t)row * g.W + col) = MmaOp<T>::pack(acc[2 * h], acc[2 * h + 1]);
+                    }
+                }
+            }
+        }
+    }
+}
+constexpr size_t kDxMmaSmemBytes = (size_t)(kMmaTileRows + kMmaTH + 4 * kMmaTileRows) * kMmaPitch * 2;
+
 }  // namespace lmnet
