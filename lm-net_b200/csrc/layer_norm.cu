@@ -158,14 +158,26 @@ ln_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, const float* __
     for (int i = threadIdx.x; i < 2 * C; i += kLnThreads) part[(int64_t)blockIdx.x * 2 * C + i] = s_part[i];
 }
 
-__global__ void ln_bwd_params_kernel(const float* __restrict__ part, int nblocks, int C, float* __restrict__ dgamma,
-                                     float* __restrict__ dbeta) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= 2 * C) return;
-    double a = 0;
-    for (int b = 0; b < nblocks; ++b) a += part[(int64_t)b * 2 * C + i];
-    if (i < C) { if (dgamma != nullptr) dgamma[i] = (float)a; }
-    else if (dbeta != nullptr) dbeta[i - C] = (float)a;
+// block = 32 columns x 8 row groups; each thread sums every 8th partial row of its column, then the 8 row groups
+// are combined through shared memory (fixed order)
+__global__ void __launch_bounds__(256)
+ln_bwd_params_kernel(const float* __restrict__ part, int nblocks, int C, float* __restrict__ dgamma,
+                     float* __restrict__ dbeta) {
+    __shared__ float s[8][33];
+    const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + cx;
+    float a = 0.f;
+    if (i < 2 * C)
+        for (int b = ry; b < nblocks; b += 8) a += part[(int64_t)b * 2 * C + i];
+    s[ry][cx] = a;
+    __syncthreads();
+    if (ry == 0 && i < 2 * C) {
+        float t = 0.f;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) t += s[r][cx];
+        if (i < C) { if (dgamma != nullptr) dgamma[i] = t; }
+        else if (dbeta != nullptr) dbeta[i - C] = t;
+    }
 }
 
 static int ln_blocks(int64_t rows, int G) {
@@ -191,7 +203,7 @@ static int ln_bwd_launch(const void* x, const void* dy, const float* gamma, cons
     const double bytes = 3.0 * (double)rows * C * sizeof(T);
     LMNET_LAUNCH(KID_LN_BWD, st, bytes, (ln_bwd_kernel<T, EPL, G><<<nb, kLnThreads, 0, st>>>(
         (const T*)x, (const T*)dy, gamma, mean, rstd, (T*)dx, part, rows)));
-    LMNET_LAUNCH(KID_LN_BWD_PARAMS, st, 0, (ln_bwd_params_kernel<<<(2 * C + 127) / 128, 128, 0, st>>>(part, nb, C, dgamma, dbeta)));
+    LMNET_LAUNCH(KID_LN_BWD_PARAMS, st, 0, (ln_bwd_params_kernel<<<(2 * C + 31) / 32, 256, 0, st>>>(part, nb, C, dgamma, dbeta)));
     return LMNET_OK;
 }
 

@@ -370,15 +370,19 @@ dw_stats_kernel(const T* __restrict__ x, lmnet_dw_params p, float* __restrict__ 
 __global__ void dw_fin_fwd_kernel(const float* __restrict__ part, int ncta, lmnet_dw_params p, float* __restrict__ save_mean,
                                   float* __restrict__ save_rstd, float* __restrict__ coef, float eps, float momentum,
                                   int64_t* nbt0, int64_t* nbt1, int64_t* nbt2, int64_t* nbt3, DwGeom g) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= g.E) return;
+    // one warp per channel: lanes 0..7 each reduce one of the 8 partial sums over the CTAs, lane 0 finishes
+    const int e = blockIdx.x;
+    __shared__ double s_tot[8];
+    if (threadIdx.x < 8) {
+        double a = 0;
+        for (int c = 0; c < ncta; ++c) a += part[((int64_t)e * ncta + c) * 8 + threadIdx.x];
+        s_tot[threadIdx.x] = a;
+    }
+    __syncwarp();
+    if (threadIdx.x != 0) return;
     const double n = (double)g.B * g.H * g.W;
-    double sum[4] = {0, 0, 0, 0}, sq[4] = {0, 0, 0, 0};
-    for (int c = 0; c < ncta; ++c)
-        for (int k = 0; k < 4; ++k) {
-            sum[k] += part[((int64_t)e * ncta + c) * 8 + k];
-            sq[k] += part[((int64_t)e * ncta + c) * 8 + 4 + k];
-        }
+    double sum[4], sq[4];
+    for (int k = 0; k < 4; ++k) { sum[k] = s_tot[k]; sq[k] = s_tot[4 + k]; }
     float m5[25];
     for (int t = 0; t < 25; ++t) m5[t] = 0.f;
     float bias = 0.f;
@@ -575,14 +579,20 @@ dw_bwd_reduce_kernel(const T* __restrict__ x, const T* __restrict__ u, const T* 
 __global__ void dw_fin_bwd_kernel(const float* __restrict__ part, int ncta, lmnet_dw_params p,
                                   const float* __restrict__ save_mean, const float* __restrict__ save_rstd,
                                   lmnet_dw_grads gr, float* __restrict__ Pfin, float* __restrict__ cb, DwGeom g) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= g.E) return;
+    // one warp per channel: lanes 0..25 each reduce one partial sum over the CTAs, lane 0 finishes
+    const int e = blockIdx.x;
+    __shared__ double s_P[26];
+    if (threadIdx.x < 26) {
+        double a = 0;
+        for (int c = 0; c < ncta; ++c) a += part[((int64_t)e * ncta + c) * 26 + threadIdx.x];
+        s_P[threadIdx.x] = a;
+        Pfin[e * 26 + threadIdx.x] = (float)a;
+    }
+    __syncwarp();
+    if (threadIdx.x != 0) return;
     const double n = (double)g.B * g.H * g.W;
     double P[26];
-    for (int t = 0; t < 26; ++t) P[t] = 0;
-    for (int c = 0; c < ncta; ++c)
-        for (int t = 0; t < 26; ++t) P[t] += part[((int64_t)e * ncta + c) * 26 + t];
-    for (int t = 0; t < 26; ++t) Pfin[e * 26 + t] = (float)P[t];
+    for (int t = 0; t < 26; ++t) P[t] = s_P[t];
     const double sdu = P[25];
     for (int k = 0; k < 4; ++k) {
         double sduy = 0;
@@ -898,7 +908,7 @@ static int dw_train_fwd(const void* x, const lmnet_dw_params* p, void* u, void* 
         return LMNET_OK;
     });
     if (rc != LMNET_OK) return rc;
-    LMNET_LAUNCH(KID_DW_FIN_FWD, st, 0, (dw_fin_fwd_kernel<<<(g.E + 63) / 64, 64, 0, st>>>(part, ncta, *p, save_mean, save_rstd, coef, eps, momentum,
+    LMNET_LAUNCH(KID_DW_FIN_FWD, st, 0, (dw_fin_fwd_kernel<<<g.E, 32, 0, st>>>(part, ncta, *p, save_mean, save_rstd, coef, eps, momentum,
                                                      nbt ? nbt[0] : nullptr, nbt ? nbt[1] : nullptr,
                                                      nbt ? nbt[2] : nullptr, nbt ? nbt[3] : nullptr, g)));
     if constexpr (sizeof(T) == 2) {
@@ -978,7 +988,7 @@ static int dw_train_bwd(const void* x, const void* u, const void* dz, const floa
         return LMNET_OK;
     });
     if (rc != LMNET_OK) return rc;
-    LMNET_LAUNCH(KID_DW_FIN_BWD, st, 0, (dw_fin_bwd_kernel<<<(g.E + 63) / 64, 64, 0, st>>>(part, ncta, *p, save_mean, save_rstd, *gr, pfin, cb, g)));
+    LMNET_LAUNCH(KID_DW_FIN_BWD, st, 0, (dw_fin_bwd_kernel<<<g.E, 32, 0, st>>>(part, ncta, *p, save_mean, save_rstd, *gr, pfin, cb, g)));
     if constexpr (sizeof(T) == 2) {
         if (use_mma) {
             DwGeom gm = dw_geom(d, kDxTH, kDxTW);

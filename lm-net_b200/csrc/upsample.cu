@@ -29,12 +29,14 @@ __device__ __forceinline__ void src_index(int o, float r, int in, int& i0, int& 
 template <typename T>
 __global__ void __launch_bounds__(256)
 upsample2x_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, UpGeom g) {
-    // one thread: 2 adjacent output columns of one output row of one plane
-    const int64_t pairs_per_row = (g.OW + 1) / 2;
-    const int64_t total = g.planes * g.OH * pairs_per_row;
+    // one thread: kOut adjacent output columns of one output row of one plane (one 16-byte store for 16-bit types)
+    constexpr int kOut = 8;
+    const int64_t groups_per_row = (g.OW + kOut - 1) / kOut;
+    const int64_t total = g.planes * g.OH * groups_per_row;
+    const bool vec_ok = (g.OW % kOut) == 0 && sizeof(T) == 2;
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t pr = idx % pairs_per_row;
-        const int64_t t = idx / pairs_per_row;
+        const int64_t gr = idx % groups_per_row;
+        const int64_t t = idx / groups_per_row;
         const int oy = (int)(t % g.OH);
         const int64_t plane = t / g.OH;
         int y0, y1;
@@ -42,32 +44,48 @@ upsample2x_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, UpGeom g) {
         src_index(oy, g.rh, g.H, y0, y1, ly0, ly1);
         const T* r0 = x + (plane * g.H + y0) * g.W;
         const T* r1 = x + (plane * g.H + y1) * g.W;
-        float out[2];
+        const int ox0 = (int)gr * kOut;
+        // the kOut outputs read input columns [xa, xa + 5] at most (scale just under 1/2): fetch them once
+        int xa, xdummy;
+        float l0, l1;
+        src_index(ox0, g.rw, g.W, xa, xdummy, l0, l1);
+        float c0v[6], c1v[6];
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const int ox = (int)pr * 2 + k;
+        for (int k = 0; k < 6; ++k) {
+            const int xi = min(xa + k, g.W - 1);
+            c0v[k] = to_f(r0[xi]);
+            c1v[k] = to_f(r1[xi]);
+        }
+        float out[kOut];
+#pragma unroll
+        for (int k = 0; k < kOut; ++k) {
+            const int ox = ox0 + k;
             out[k] = 0.f;
             if (ox < g.OW) {
                 int x0, x1;
                 float lx0, lx1;
                 src_index(ox, g.rw, g.W, x0, x1, lx0, lx1);
-                out[k] = ly0 * (lx0 * to_f(r0[x0]) + lx1 * to_f(r0[x1])) + ly1 * (lx0 * to_f(r1[x0]) + lx1 * to_f(r1[x1]));
+                const int i0 = x0 - xa, i1 = x1 - xa;        // 0..5
+                float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+#pragma unroll
+                for (int q = 0; q < 6; ++q) {
+                    a0 = i0 == q ? c0v[q] : a0; a1 = i1 == q ? c0v[q] : a1;
+                    b0 = i0 == q ? c1v[q] : b0; b1 = i1 == q ? c1v[q] : b1;
+                }
+                out[k] = ly0 * (lx0 * a0 + lx1 * a1) + ly1 * (lx0 * b0 + lx1 * b1);
             }
         }
-        T* o = y + (plane * g.OH + oy) * g.OW + pr * 2;
-        if ((int)pr * 2 + 1 < g.OW && (g.OW & 1) == 0) {
-            if constexpr (sizeof(T) == 2) {
-                uint32_t raw;
-                T* e = reinterpret_cast<T*>(&raw);
-                e[0] = from_f<T>(out[0]);
-                e[1] = from_f<T>(out[1]);
-                *reinterpret_cast<uint32_t*>(o) = raw;
-            } else {
-                *reinterpret_cast<float2*>(o) = make_float2(out[0], out[1]);
-            }
+        T* o = y + (plane * g.OH + oy) * g.OW + ox0;
+        if (vec_ok) {
+            uint4 raw;
+            T* e = reinterpret_cast<T*>(&raw);
+#pragma unroll
+            for (int k = 0; k < kOut; ++k) e[k] = from_f<T>(out[k]);
+            *reinterpret_cast<uint4*>(o) = raw;
         } else {
-            o[0] = from_f<T>(out[0]);
-            if ((int)pr * 2 + 1 < g.OW) o[1] = from_f<T>(out[1]);
+#pragma unroll
+            for (int k = 0; k < kOut; ++k)
+                if (ox0 + k < g.OW) o[k] = from_f<T>(out[k]);
         }
     }
 }
@@ -137,7 +155,7 @@ static unsigned up_blocks(int64_t total) {
 template <typename T>
 static int up_fwd(const void* x, void* y, const lmnet_upsample_dims* d, cudaStream_t st) {
     UpGeom g = up_geom(d);
-    const int64_t total = g.planes * g.OH * ((g.OW + 1) / 2);
+    const int64_t total = g.planes * g.OH * ((g.OW + 7) / 8);
     const double bytes = (double)g.planes * ((double)g.H * g.W + (double)g.OH * g.OW) * sizeof(T);
     LMNET_LAUNCH(KID_UPSAMPLE_FWD, st, bytes, (upsample2x_fwd_kernel<T><<<up_blocks(total), 256, 0, st>>>((const T*)x, (T*)y, g)));
     return LMNET_OK;
