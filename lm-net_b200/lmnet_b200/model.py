@@ -30,6 +30,12 @@ from .reparam import reparam_forward
 from .upsample import Upsample2x
 
 
+def _cl(t: torch.Tensor) -> torch.Tensor:
+    """channels-last copy (no-op when already channels-last).  cuDNN's 16-bit convolutions compute in NHWC and
+    transpose NCHW operands around every call; handing them NHWC tensors once per producer removes that."""
+    return t.contiguous(memory_format=torch.channels_last) if t.is_cuda else t
+
+
 def _conv_bn(channels: int, kernel, padding) -> nn.Sequential:
     return nn.Sequential(OrderedDict(
         conv=nn.Conv2d(channels, channels, kernel, stride=1, padding=padding, groups=channels, bias=False),
@@ -144,7 +150,7 @@ class NeighborhoodTransformer(nn.Module):
         self.mlp = Mlp(channels, 2 * channels, channels)
 
     def forward(self, x):
-        emb = self.patchembedding(x)
+        emb = self.patchembedding(_cl(x))          # NHWC conv output: the permute below is then a free view
         att = self.att1(layer_norm(self.norm1, emb)) + emb
         y = self.mlp(layer_norm(self.norm2, att)) + att
         return y.permute(0, 3, 1, 2).contiguous()
@@ -166,7 +172,7 @@ class M3Skip(nn.Module):
         self.fuse_conv = nn.Sequential(nn.Conv2d(3 * mid, mid, 3, 1, 1), nn.BatchNorm2d(mid), nn.GELU())
 
     def forward(self, xl, xm, xs):
-        return conv_bn_act(self.fuse_conv, torch.cat([self.convl(xl), self.convm(xm), self.convs(xs)], dim=1))
+        return conv_bn_act(self.fuse_conv, torch.cat([self.convl(_cl(xl)), self.convm(_cl(xm)), self.convs(xs)], dim=1))
 
 
 class M2Skip(nn.Module):
@@ -187,7 +193,8 @@ class M2Skip(nn.Module):
         self.fuse_conv = nn.Sequential(nn.Conv2d(2 * width, width, 3, 1, 1), nn.BatchNorm2d(width), nn.GELU())
 
     def forward(self, xl, xs):
-        return conv_bn_act(self.fuse_conv, torch.cat([self.convl(xl), self.convs(xs)], dim=1))
+        xs = self.convs(_cl(xs)) if self.model_type == "bottom" else self.convs(xs)
+        return conv_bn_act(self.fuse_conv, torch.cat([self.convl(_cl(xl)), xs], dim=1))
 
 
 class GlobalAttention(nn.Module):
@@ -287,13 +294,18 @@ class LM_Net(nn.Module):
                 m.switch_to_deploy()
 
     def forward(self, x):
+        # stage outputs feed several cuDNN 3x3 convolutions each: make ONE channels-last copy per stage
         x1 = self.conv1(x)
-        x2 = self.conv2(self.down1(x1))
-        x3 = self.conv3(self.down2(x2))
-        x4 = self.conv4(self.down3(x3))
-        bottom = self.down4(x4)
+        x1c = _cl(x1)
+        x2 = self.conv2(self.down1(x1c))
+        x2c = _cl(x2)
+        x3 = self.conv3(self.down2(x2c))
+        x3c = _cl(x3)
+        x4 = self.conv4(self.down3(x3c))
+        x4c = _cl(x4)
+        bottom = self.down4(x4c)
         x5 = self.gft(self.pyramidpool(x1, x2, x3, x4, bottom))
-        s1, s2, s3, s4 = self.skip1(x3, x4), self.skip2(x2, x3, x4), self.skip3(x1, x2, x3), self.skip4(x1, x2)
+        s1, s2, s3, s4 = self.skip1(x3c, x4c), self.skip2(x2c, x3c, x4c), self.skip3(x1c, x2c, x3c), self.skip4(x1c, x2c)
         y = self.dconv1(self.up1(x5) + self.natt1(s1))
         y = self.dconv2(self.up2(y) + self.natt2(s2))
         y = self.dconv3(self.up3(y) + self.natt3(s3))

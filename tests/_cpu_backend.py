@@ -63,6 +63,9 @@ def apply(setattr_fn):
     setattr_fn(reparam, "expand_1x1", lambda conv, x: conv(x))
     setattr_fn(reparam, "pointwise_shortcut", lambda pw, sc, z, gate, x: pw(gate * z) + sc(x))
     setattr_fn(model, "layer_norm", lambda ln, x: ln(x))
+    from lmnet_b200 import patch
+
+    setattr_fn(patch, "layer_norm", lambda ln, x: ln(x))
     setattr_fn(reparam, "fused_dw_bn_gelu", lambda mod, x1: reparam_ref.dw_bn_gelu(mod, x1))
     setattr_fn(reparam, "fused_dw_deploy", lambda mod, x1: reparam_ref.dw_bn_gelu(mod, x1))
     return o

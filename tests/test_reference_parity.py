@@ -40,9 +40,9 @@ def test_oracle_restatement_of_reparamconv_equals_reference_class():
 
 
 def test_patched_reference_model_equals_reference(cpu_backend):
-    """patch_reparam_conv + natten drop-in on the REAL reference model == the reference's own forward
+    """patch_reference_modules + natten drop-in on the REAL reference model == the reference's own forward
     (natten's arithmetic answered by the CPU oracle on both sides)."""
-    from lmnet_b200.reparam import patch_reparam_conv
+    from lmnet_b200.patch import convert_upsample, patch_reference_modules, unpatch_reference_modules
     from oracle.lmnet_ref import to_oracle
 
     lm, mods = import_reference()
@@ -53,11 +53,13 @@ def test_patched_reference_model_equals_reference(cpu_backend):
     x = torch.randn(1, 3, 32, 32, dtype=torch.float64)
     with torch.no_grad():
         want = ref(x)
-    original = patch_reparam_conv(mods.ReparamConv)
+    originals = patch_reference_modules(mods)     # ReparamConv, NeighborhoodTransformer, M2Skip, M3Skip
     try:
+        ours = convert_upsample(ours)
+        assert sum(type(m).__name__ == "Upsample2x" for m in ours.modules()) == 7
         with torch.no_grad():
-            got = ours.eval()(x)                  # reference classes, our forward + our natten module
+            got = ours.eval()(x)                  # reference classes, our forwards + our natten module
     finally:
-        mods.ReparamConv.forward = original
+        unpatch_reference_modules(mods, originals)
     assert rel_err(got, want) < 1e-7
     assert torch.equal(got.argmax(1), want.argmax(1))
