@@ -72,28 +72,34 @@ __device__ __forceinline__ void toeplitz_frag(const float* taps, int ntaps, int 
 }
 
 // Raw 16-bit tile (rows x kMmaPitch) staged with 32-bit accesses: index i of a row <-> image column c0 + i.
+// Thread layout: 36 column lanes (one 32-bit pair each) x 3 row lanes; a thread walks rows rl, rl+3, ... so that
+// its global pointer and shared index advance by constants (no per-slot division, one unsigned row check).
 template <typename T, int ROWS>
 struct MmaTileLoader {
-    static constexpr int N = (ROWS * kMmaPairs + kDwThreads - 1) / kDwThreads;
+    static constexpr int RL = 3;
+    static constexpr int N = (ROWS + RL - 1) / RL;
     uint32_t raw[N];
     __device__ __forceinline__ void fetch(const T* __restrict__ plane, int H, int W, int r0, int c0) {
+        const int rl = threadIdx.x / kMmaPairs, v = threadIdx.x - rl * kMmaPairs;
+        const int gc = c0 + 2 * v;
+        const bool cok = rl < RL && gc >= 0 && gc + 2 <= W;
+        const T* ptr = plane + (int64_t)(r0 + rl) * W + gc;
 #pragma unroll
         for (int u = 0; u < N; ++u) {
-            const int idx = threadIdx.x + u * kDwThreads;
-            const int r = idx / kMmaPairs, v = idx - r * kMmaPairs;
-            const int gr = r0 + r, gc = c0 + 2 * v;
+            const int r = rl + RL * u;
             uint32_t val = 0u;
-            if (idx < ROWS * kMmaPairs && gr >= 0 && gr < H && gc >= 0 && gc + 2 <= W)
-                val = __ldg(reinterpret_cast<const uint32_t*>(plane + (int64_t)gr * W + gc));
+            if (cok && r < ROWS && (unsigned)(r0 + r) < (unsigned)H) val = __ldg(reinterpret_cast<const uint32_t*>(ptr));
             raw[u] = val;
+            ptr += RL * W;
         }
     }
     __device__ __forceinline__ void commit(T* s) const {
+        const int rl = threadIdx.x / kMmaPairs, v = threadIdx.x - rl * kMmaPairs;
+        if (rl >= RL) return;
+        uint32_t* dst = reinterpret_cast<uint32_t*>(s) + rl * kMmaPairs + v;
 #pragma unroll
-        for (int u = 0; u < N; ++u) {
-            const int idx = threadIdx.x + u * kDwThreads;
-            if (idx < ROWS * kMmaPairs) reinterpret_cast<uint32_t*>(s)[idx] = raw[u];
-        }
+        for (int u = 0; u < N; ++u)
+            if (rl + RL * u < ROWS) dst[u * RL * kMmaPairs] = raw[u];
     }
 };
 
@@ -163,6 +169,7 @@ dw_stats_mma_kernel(const T* __restrict__ x, lmnet_dw_params p, float* __restric
         [&](int, int tr, bool) {
             const int row_lo = tr + 16 * wr + gq;            // image rows of c0/c1 and (+8) c2/c3
             const float rm0 = row_lo < band1 ? 1.f : 0.f, rm1 = row_lo + 8 < band1 ? 1.f : 0.f;
+            const bool full = tr + kMmaTH <= band1 && c0 + kMmaTW <= g.W;
 #pragma unroll
             for (int cb = 0; cb < 4; ++cb) {
                 float acc[4][4];
@@ -180,17 +187,27 @@ dw_stats_mma_kernel(const T* __restrict__ x, lmnet_dw_params p, float* __restric
                     }
                     if (a == 2) MmaOp<T>::run(acc[3], A, B13);
                 }
-                const int col = c0 + tcol + 2 * tq;
-                const float cm0 = col < g.W ? 1.f : 0.f, cm1 = col + 1 < g.W ? 1.f : 0.f;
-                const float m[4] = {rm0 * cm0, rm0 * cm1, rm1 * cm0, rm1 * cm1};
+                if (full) {                                   // tile inside the band and the image: no masks
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
+                    for (int k = 0; k < 4; ++k)
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float y = acc[k][i] * m[i];
-                        s[k] += y;
-                        ss[k] = fmaf(y, acc[k][i], ss[k]);
-                    }
+                        for (int i = 0; i < 4; ++i) {
+                            s[k] += acc[k][i];
+                            ss[k] = fmaf(acc[k][i], acc[k][i], ss[k]);
+                        }
+                } else {
+                    const int col = c0 + tcol + 2 * tq;
+                    const float cm0 = col < g.W ? 1.f : 0.f, cm1 = col + 1 < g.W ? 1.f : 0.f;
+                    const float m[4] = {rm0 * cm0, rm0 * cm1, rm1 * cm0, rm1 * cm1};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float y = acc[k][i] * m[i];
+                            s[k] += y;
+                            ss[k] = fmaf(y, acc[k][i], ss[k]);
+                        }
+                }
             }
         });
     float v[8];
@@ -239,8 +256,12 @@ dw_apply_mma_kernel(const T* __restrict__ x, const float* __restrict__ coef, T* 
         g, band0, band1, kMmaTH, 2, c0, s_tile,
         [&](int b) { return x + ((int64_t)b * g.E + e) * g.H * g.W; },
         [&](int b, int tr, bool last) {
-            const int64_t poff = ((int64_t)b * g.E + e) * g.H * g.W;
             const int row_lo = tr + 16 * wr + gq;
+            const int col_lo = c0 + 32 * wc + 2 * tq;
+            // element offset of this lane's first output pair; the other seven pairs are +8*cb columns / +8 rows away
+            const int64_t base = ((int64_t)b * g.E + e) * g.H * g.W + (int64_t)row_lo * g.W + col_lo;
+            const int64_t row8 = (int64_t)8 * g.W;
+            const bool full = tr + kMmaTH <= band1 && c0 + kMmaTW <= g.W;
 #pragma unroll
             for (int cb = 0; cb < 4; ++cb) {
                 float acc[4] = {bias, bias, bias, bias};
@@ -252,21 +273,17 @@ dw_apply_mma_kernel(const T* __restrict__ x, const float* __restrict__ coef, T* 
                     MmaOp<T>::run(acc, A, Bhi[a]);
                     MmaOp<T>::run(acc, A, Blo[a]);
                 }
-                const int col = c0 + tcol + 2 * tq;
-                if (col < g.W) {                          // W is even on this path: the pair is all in or all out
+                const bool cok = full || (col_lo + 8 * cb < g.W);         // W even: the pair is all in or all out
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int row = row_lo + 8 * h;
-                        if (row < band1) {
-                            const int64_t off = poff + (int64_t)row * g.W + col;
-                            const uint32_t up = MmaOp<T>::pack(acc[2 * h], acc[2 * h + 1]);
-                            if (u_out != nullptr) *reinterpret_cast<uint32_t*>(u_out + off) = up;
-                            const T* ur = reinterpret_cast<const T*>(&up);
-                            const uint32_t zp = MmaOp<T>::pack(gelu_f(to_f(ur[0])), gelu_f(to_f(ur[1])));
-                            *reinterpret_cast<uint32_t*>(z_out + off) = zp;
-                            const T* zr = reinterpret_cast<const T*>(&zp);
-                            psum += to_f(zr[0]) + to_f(zr[1]);
-                        }
+                for (int h = 0; h < 2; ++h) {
+                    if (cok && (full || row_lo + 8 * h < band1)) {
+                        const int64_t off = base + 8 * cb + h * row8;
+                        const uint32_t up = MmaOp<T>::pack(acc[2 * h], acc[2 * h + 1]);
+                        if (u_out != nullptr) *reinterpret_cast<uint32_t*>(u_out + off) = up;
+                        const T* ur = reinterpret_cast<const T*>(&up);      // GELU of the value as stored
+                        const float z0 = gelu_f(to_f(ur[0])), z1 = gelu_f(to_f(ur[1]));
+                        *reinterpret_cast<uint32_t*>(z_out + off) = MmaOp<T>::pack(z0, z1);
+                        psum += z0 + z1;
                     }
                 }
             }
