@@ -365,11 +365,14 @@ dw_bwd_reduce_mma_kernel(const T* __restrict__ x, const T* __restrict__ u, const
         // phase 1: du for the 32 x 64 tile (thread: row = warp*8 + o, column pair = lane)
         const float dp = dpool != nullptr ? __ldg(dpool + b * g.E + e) * inv_hw : 0.f;
         const int col = c0 + 2 * lane;
+        const bool cok = col < g.W;                           // W even: the pair is all in or all out
+        const bool full = tr + kMmaTH <= band1;
+        T* dptr = du_out + poff + (int64_t)(tr + warp * 8) * g.W + col;
 #pragma unroll
         for (int o = 0; o < 8; ++o) {
-            const int trow = warp * 8 + o, row = tr + trow;
+            const int trow = warp * 8 + o;
             uint32_t packed = 0u;
-            if (row < band1 && col < g.W) {               // W even: the pair is all in or all out
+            if (cok && (full || tr + trow < band1)) {
                 const uint32_t ur = *reinterpret_cast<const uint32_t*>(s_u + trow * kMmaPitch + 2 * lane);
                 const uint32_t zr = *reinterpret_cast<const uint32_t*>(s_dz + trow * kMmaPitch + 2 * lane);
                 const T* ue = reinterpret_cast<const T*>(&ur);
@@ -377,11 +380,12 @@ dw_bwd_reduce_mma_kernel(const T* __restrict__ x, const T* __restrict__ u, const
                 const float d0 = (to_f(ze[0]) + dp) * gelu_grad_f(to_f(ue[0]));
                 const float d1 = (to_f(ze[1]) + dp) * gelu_grad_f(to_f(ue[1]));
                 packed = MmaOp<T>::pack(d0, d1);
-                *reinterpret_cast<uint32_t*>(du_out + poff + (int64_t)row * g.W + col) = packed;
+                *reinterpret_cast<uint32_t*>(dptr) = packed;
                 const T* de = reinterpret_cast<const T*>(&packed);
                 sdu += to_f(de[0]) + to_f(de[1]);             // exactly what later passes read back
             }
             *reinterpret_cast<uint32_t*>(s_du + trow * kMmaPitch + 2 * lane) = packed;
+            dptr += g.W;
         }
         __syncthreads();
         // phase 2: Gram MMAs of this warp's 16 rows x 32 columns
@@ -477,6 +481,7 @@ dw_bwd_dw_mma_kernel(const T* __restrict__ x, lmnet_dw_params p, const float* __
         [&](int, int tr, bool) {
             const int row_lo = tr + 16 * wr + gq;
             const float rm0 = row_lo < band1 ? 1.f : 0.f, rm1 = row_lo + 8 < band1 ? 1.f : 0.f;
+            const bool full = tr + kMmaTH <= band1 && c0 + kMmaTW <= g.W;
             // phase 1: y_br of this warp's 16 x 32 block -> g_br tiles
 #pragma unroll
             for (int cbk = 0; cbk < 4; ++cbk) {
@@ -496,11 +501,12 @@ dw_bwd_dw_mma_kernel(const T* __restrict__ x, lmnet_dw_params p, const float* __
                     if (a == 2) MmaOp<T>::run(acc[3], A, B13);
                 }
                 const int col = c0 + tcol + 2 * tq;
-                const float cm = col < g.W ? 1.f : 0.f;         // W even: pair in or out together
+                const float cm = (full || col < g.W) ? 1.f : 0.f;     // W even: pair in or out together
+                const float m0 = full ? 1.f : rm0 * cm, m1 = full ? 1.f : rm1 * cm;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const uint32_t lo = MmaOp<T>::pack((c2[k] * acc[k][0] + c0c[k]) * rm0 * cm, (c2[k] * acc[k][1] + c0c[k]) * rm0 * cm);
-                    const uint32_t hi = MmaOp<T>::pack((c2[k] * acc[k][2] + c0c[k]) * rm1 * cm, (c2[k] * acc[k][3] + c0c[k]) * rm1 * cm);
+                    const uint32_t lo = MmaOp<T>::pack(fmaf(c2[k], acc[k][0], c0c[k]) * m0, fmaf(c2[k], acc[k][1], c0c[k]) * m0);
+                    const uint32_t hi = MmaOp<T>::pack(fmaf(c2[k], acc[k][2], c0c[k]) * m1, fmaf(c2[k], acc[k][3], c0c[k]) * m1);
                     *reinterpret_cast<uint32_t*>(&s_g[k][(16 * wr + gq) * kMmaPitch + tcol + 2 * tq]) = lo;
                     *reinterpret_cast<uint32_t*>(&s_g[k][(16 * wr + gq + 8) * kMmaPitch + tcol + 2 * tq]) = hi;
                 }
@@ -640,6 +646,7 @@ dw_bwd_dx_mma_kernel(const T* __restrict__ x, const T* __restrict__ du, lmnet_dw
             const int rho0 = 16 * wr + gq;                         // region rows rho0, rho0 + 8
             const int row0 = tr - 2 + rho0, row1 = row0 + 8;
             const bool rin0 = row0 >= 0 && row0 < g.H, rin1 = row1 >= 0 && row1 < g.H;
+            const bool inside = tr - 2 >= 0 && tr - 2 + kMmaTH <= g.H && c0 - 2 >= 0 && c0 - 2 + kMmaTW <= g.W;
 #pragma unroll
             for (int cbk = 0; cbk < 4; ++cbk) {
                 float acc[4][4];
@@ -664,13 +671,14 @@ dw_bwd_dx_mma_kernel(const T* __restrict__ x, const T* __restrict__ du, lmnet_dw
                 const uint32_t d1r = *reinterpret_cast<const uint32_t*>(s_du + (rho0 + 8) * kMmaPitch + kap);
                 const T* d0 = reinterpret_cast<const T*>(&d0r);
                 const T* d1 = reinterpret_cast<const T*>(&d1r);
-                const float m0 = (rin0 && cin) ? 1.f : 0.f, m1 = (rin1 && cin) ? 1.f : 0.f;
+                const float m0 = (inside || (rin0 && cin)) ? 1.f : 0.f, m1 = (inside || (rin1 && cin)) ? 1.f : 0.f;
+                const float da = to_f(d0[0]), db = to_f(d0[1]), dc = to_f(d1[0]), dd = to_f(d1[1]);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const uint32_t lo = MmaOp<T>::pack((c1[k] * to_f(d0[0]) - c2[k] * acc[k][0] - c0c[k]) * m0,
-                                                       (c1[k] * to_f(d0[1]) - c2[k] * acc[k][1] - c0c[k]) * m0);
-                    const uint32_t hi = MmaOp<T>::pack((c1[k] * to_f(d1[0]) - c2[k] * acc[k][2] - c0c[k]) * m1,
-                                                       (c1[k] * to_f(d1[1]) - c2[k] * acc[k][3] - c0c[k]) * m1);
+                    const uint32_t lo = MmaOp<T>::pack(fmaf(c1[k], da, fmaf(-c2[k], acc[k][0], -c0c[k])) * m0,
+                                                       fmaf(c1[k], db, fmaf(-c2[k], acc[k][1], -c0c[k])) * m0);
+                    const uint32_t hi = MmaOp<T>::pack(fmaf(c1[k], dc, fmaf(-c2[k], acc[k][2], -c0c[k])) * m1,
+                                                       fmaf(c1[k], dd, fmaf(-c2[k], acc[k][3], -c0c[k])) * m1);
                     T* tile = s_dy + k * kMmaTileRows * kMmaPitch;
                     *reinterpret_cast<uint32_t*>(tile + rho0 * kMmaPitch + kap) = lo;
                     *reinterpret_cast<uint32_t*>(tile + (rho0 + 8) * kMmaPitch + kap) = hi;
