@@ -1,6 +1,6 @@
 // na2d_fused_api.cu — extern "C" entry points of the fused neighbourhood attention
 // (validation, workspace layout, per-dtype dispatch).  Kernels: na2d_fused.cuh.
-#include "na2d_fused.cuh"
+#include "na2d_stream.cuh"
 
 namespace lmnet {
 
@@ -62,6 +62,8 @@ extern "C" int lmnet_na2d_fwd(const lmnet_view5* q, const lmnet_view5* k, const 
     FusedArgs a{};
     a.q = q; a.k = k; a.v = v; a.out = out; a.rpb = rpb; a.lse = lse;
     a.g = make_geom(dims); a.scale = scale; a.stream = (cudaStream_t)stream;
+    rc = stream_fwd(a, dtype);   // row-streaming kernel for 16-bit storage; UNSUPPORTED = not eligible
+    if (rc != LMNET_ERR_UNSUPPORTED) return rc;
     return dispatch(Op::Fwd, a, dtype, hg);
 }
 
@@ -96,17 +98,22 @@ extern "C" int lmnet_na2d_bwd(const lmnet_view5* q, const lmnet_view5* k, const 
     a.stats = reinterpret_cast<float2*>((char*)workspace + L.stats_off);
     a.drpb_part = drpb ? reinterpret_cast<float*>((char*)workspace + L.part_off) : nullptr;
     a.g = make_geom(dims); a.scale = scale; a.stream = (cudaStream_t)stream;
-    rc = dispatch(Op::BwdQ, a, dtype, hg);
-    if (rc != LMNET_OK) return rc;
-    rc = dispatch(Op::BwdK, a, dtype, hg);
-    if (rc != LMNET_OK) return rc;
-    if (drpb) {
-        const NAGeom& g = a.g;
-        int R = 2 * g.K - 1;
+    const NAGeom& g = a.g;
+    int64_t n_part = 0;
+    rc = stream_bwd(a, dtype, L.n_part, &n_part);   // one-kernel streaming backward when eligible
+    if (rc != LMNET_OK && rc != LMNET_ERR_UNSUPPORTED) return rc;
+    if (rc == LMNET_ERR_UNSUPPORTED) {
+        rc = dispatch(Op::BwdQ, a, dtype, hg);
+        if (rc != LMNET_OK) return rc;
+        rc = dispatch(Op::BwdK, a, dtype, hg);
+        if (rc != LMNET_OK) return rc;
         int NG = g.heads / hg;
         int64_t gx = ((int64_t)g.Wmax * NG + kThreads - 1) / kThreads;
         int64_t gy = (g.Hmax + kRowChunk - 1) / kRowChunk;
-        int64_t n_part = gx * gy * g.B * g.d * g.d;
+        n_part = gx * gy * g.B * g.d * g.d;
+    }
+    if (drpb) {
+        int R = 2 * g.K - 1;
         LMNET_LAUNCH(KID_NA_DRPB_REDUCE, a.stream, 0,
             (drpb_reduce_kernel<<<g.heads * R * R, 256, 0, a.stream>>>(a.drpb_part, n_part, g.heads * R * R, drpb)));
     }

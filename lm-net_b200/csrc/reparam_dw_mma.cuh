@@ -25,6 +25,9 @@ constexpr int kMmaPitch = 72;                 // bf16 elements per shared row (1
 constexpr int kMmaTH = 32, kMmaTW = 64;       // output tile
 constexpr int kMmaTileRows = kMmaTH + 4;
 constexpr int kMmaPairs = kMmaPitch / 2;      // 32-bit pairs per row
+#ifndef LMNET_DW_MINBLOCKS
+#define LMNET_DW_MINBLOCKS 1
+#endif
 
 __device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* p) {
     const uint32_t addr = (uint32_t)__cvta_generic_to_shared(p);
@@ -134,7 +137,7 @@ __device__ __forceinline__ void load_a(const T* s_tile, int row, int col, int la
 // statistics pass: per-channel sum / sum of squares of the four branch outputs
 // ---------------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(kDwThreads)
+__global__ void __launch_bounds__(kDwThreads, LMNET_DW_MINBLOCKS)
 dw_stats_mma_kernel(const T* __restrict__ x, lmnet_dw_params p, float* __restrict__ part /* [E][ncta][8] */, DwGeom g) {
     __shared__ __align__(16) T s_tile[kMmaTileRows * kMmaPitch];
     __shared__ float s_red[kDwWarps * 8];
@@ -223,7 +226,7 @@ dw_stats_mma_kernel(const T* __restrict__ x, lmnet_dw_params p, float* __restric
 // rounding beyond fp32.
 // ---------------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(kDwThreads)
+__global__ void __launch_bounds__(kDwThreads, LMNET_DW_MINBLOCKS)
 dw_apply_mma_kernel(const T* __restrict__ x, const float* __restrict__ coef, T* __restrict__ u_out, T* __restrict__ z_out,
                     float* __restrict__ pool_part, DwGeom g) {
     __shared__ __align__(16) T s_tile[kMmaTileRows * kMmaPitch];
@@ -321,7 +324,7 @@ __device__ __forceinline__ void load_b_trans(const T* s_tile, int row, int col, 
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kDwThreads)
+__global__ void __launch_bounds__(kDwThreads, LMNET_DW_MINBLOCKS)
 dw_bwd_reduce_mma_kernel(const T* __restrict__ x, const T* __restrict__ u, const T* __restrict__ dz,
                          const float* __restrict__ dpool, T* __restrict__ du_out, float* __restrict__ part /* [E][ncta][26] */,
                          DwGeom g) {
@@ -566,7 +569,7 @@ dw_bwd_dw_mma_kernel(const T* __restrict__ x, lmnet_dw_params p, const float* __
 constexpr int kDxTH = 28, kDxTW = 56;
 
 template <typename T>
-__global__ void __launch_bounds__(kDwThreads)
+__global__ void __launch_bounds__(kDwThreads, LMNET_DW_MINBLOCKS)
 dw_bwd_dx_mma_kernel(const T* __restrict__ x, const T* __restrict__ du, lmnet_dw_params p, const float* __restrict__ cb,
                      T* __restrict__ dx, DwGeom g) {
     extern __shared__ __align__(16) unsigned char dx_smem_raw[];

@@ -14,7 +14,8 @@ from ctypes import POINTER, Structure, byref, c_float, c_int, c_int32, c_int64, 
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblmnet_b200.so")
+# LMNET_B200_LIB points at an alternative build of the same ABI (kernel A/B experiments); the default is the in-tree library.
+LIB_PATH = os.environ.get("LMNET_B200_LIB") or os.path.join(_HERE, "liblmnet_b200.so")
 
 F32, BF16, F16 = 0, 1, 2
 _DTYPES = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16}

@@ -28,6 +28,14 @@ FUSED_CASES = [
     (1, 19, 20, 2, 16, 9, 1),    # runtime-K path
     (1, 14, 14, 3, 32, 5, 2),    # NAT-style head dim
     (1, 14, 15, 3, 1, 13, 1),    # largest kernel
+    # row-streaming kernels (16-bit storage): several stripes / bands, stripe boundary moved off the last K-1 columns
+    (1, 40, 70, 12, 1, 3, 1),    # 2 stripes of 62 + 8, 5 bands
+    (1, 27, 64, 12, 1, 3, 1),    # 64 - 62 < K: boundary moves to W - K; bands 8,8,8,3 -> last boundary moves too
+    (1, 33, 61, 12, 2, 3, 1),    # stripes of 30: 61 - 60 < K
+    (1, 30, 30, 12, 4, 3, 1),    # stripes of 14
+    (1, 26, 29, 12, 2, 3, 2),    # dilation 2: four sub-grids of different extents
+    (2, 24, 40, 12, 1, 5, 1),    # streaming forward only (K = 5), backward on the general path
+    (1, 30, 33, 12, 4, 7, 1),    # streaming forward, K = 7
 ]
 
 
