@@ -34,25 +34,33 @@ struct Plan {
     unsigned z;
 };
 
-bool make_plan(const NAGeom& g, bool bwd, int64_t max_parts, Plan& p) {
+bool make_plan(const NAGeom& g, bool bwd, int64_t max_parts, int ctas_per_sm, Plan& p, int hg_override = 0) {
     const int K = g.K, NS = K / 2;
     if (g.D != 1 && g.D != 2 && g.D != 4 && g.D != 8) return false;
-    p.HG = stream_hg(K, g.D);
+    p.HG = hg_override > 0 ? hg_override : stream_hg(K, g.D);
     if (g.heads % p.HG != 0 || (g.heads * g.D) % 2 != 0) return false;
     p.cfg.NG = g.heads / p.HG;
     if (p.cfg.NG > kStreamThreads) return false;
     static const int threads = getenv("LMNET_NA_THREADS") ? atoi(getenv("LMNET_NA_THREADS")) : kStreamThreads;   // tuning knob
     if (threads < 32 || threads > kStreamThreads) return false;
     p.cfg.QW = threads / p.cfg.NG;
-    const int TW = bwd ? p.cfg.QW - 2 * NS : p.cfg.QW;
-    if (TW < K) return false;
+    const int halo = bwd ? 2 * NS : 0;
+    if (p.cfg.QW - halo < K) return false;
     if (2 * NS > p.cfg.QW) return false;   // the halo columns are staged by the first 2*(K/2) column threads
     if (bwd && (g.H / g.d < 2 * K || g.W / g.d < 2 * K)) return false;   // stream_boundary needs L >= 2K
     p.z = (unsigned)(g.B * g.d * g.d);
-    p.stripes = (g.Wmax + TW - 1) / TW;
+    // equal-width stripes: as few as the widest CTA allows, then shrink the CTA to the stripe
+    p.stripes = (g.Wmax + (p.cfg.QW - halo) - 1) / (p.cfg.QW - halo);
+    int TW = (g.Wmax + p.stripes - 1) / p.stripes;
+    if (TW < K) TW = K;
+    p.cfg.QW = TW + halo;
+    // bands: fill the GPU once (148 SMs x resident CTAs) rather than leave a mostly empty last wave
     const int min_rb = 8 > K ? 8 : K;
-    const int64_t target = bwd ? 4 * 148 : 8 * 148;
-    int64_t bands = (target + (int64_t)p.stripes * p.z - 1) / ((int64_t)p.stripes * p.z);
+    const size_t smem = bwd ? stream_bwd_smem_bytes(K, g.D, p.HG, g.heads, p.cfg.QW) : stream_fwd_smem_bytes(K, g.D, g.heads, p.cfg.QW);
+    const int by_smem = (int)((size_t)(227 * 1024) / (smem + 1024));   // 1 KB per CTA reserved by the driver
+    if (by_smem < 1) return false;
+    const int64_t resident = 148 * (int64_t)(ctas_per_sm < by_smem ? ctas_per_sm : by_smem);
+    int64_t bands = resident / ((int64_t)p.stripes * p.z);
     const int64_t max_bands = g.Hmax / min_rb > 0 ? g.Hmax / min_rb : 1;
     bands = bands < 1 ? 1 : bands > max_bands ? max_bands : bands;
     if (bwd && max_parts > 0) {
@@ -132,7 +140,7 @@ template <typename T>
 int bwd_typed(const FusedArgs& a, const Plan& p) {
     if (a.g.K != 3) return LMNET_ERR_UNSUPPORTED;
     switch (a.g.D) {
-        case 1: return launch_bwd<T, 3, 1, 4>(a, p);
+        case 1: return p.HG == 2 ? launch_bwd<T, 3, 1, 2>(a, p) : launch_bwd<T, 3, 1, 4>(a, p);
         case 2: return launch_bwd<T, 3, 2, 2>(a, p);
         case 4: return launch_bwd<T, 3, 4, 1>(a, p);
         case 8: return launch_bwd<T, 3, 8, 1>(a, p);
@@ -147,7 +155,7 @@ int stream_fwd(const FusedArgs& a, int dtype) {
     const NAGeom& g = a.g;
     if (g.K != 3 && g.K != 5 && g.K != 7) return LMNET_ERR_UNSUPPORTED;
     Plan p;
-    if (!make_plan(g, false, 0, p)) return LMNET_ERR_UNSUPPORTED;
+    if (!make_plan(g, false, 0, stream_fwd_minblocks(g.K, stream_hg(g.K, g.D)), p)) return LMNET_ERR_UNSUPPORTED;
     const int vb = p.HG * g.D * 2;
     if (!strides_ok(a.k, g.D, vb) || !strides_ok(a.v, g.D, vb) || !strides_ok(a.q, g.D, vb) ||
         !strides_ok(a.out, g.D, vb))
@@ -160,7 +168,9 @@ int stream_bwd(const FusedArgs& a, int dtype, int64_t max_parts, int64_t* n_part
     const NAGeom& g = a.g;
     if (g.K != 3) return LMNET_ERR_UNSUPPORTED;
     Plan p;
-    if (!make_plan(g, true, max_parts, p)) return LMNET_ERR_UNSUPPORTED;
+    static const bool hg2 = getenv("LMNET_NA_BWD_HG2") != nullptr && atoi(getenv("LMNET_NA_BWD_HG2")) != 0;   // tuning knob
+    const int resident = (g.D == 2 || g.D == 4 || (hg2 && g.D == 1)) ? 3 : 2;   // StreamBwdSmem::MINB
+    if (!make_plan(g, true, max_parts, resident, p, (hg2 && g.D == 1) ? 2 : 0)) return LMNET_ERR_UNSUPPORTED;
     const int vb = p.HG * g.D * 2;
     const lmnet_view5* staged[] = {a.q, a.k, a.v, a.dout};
     for (auto* x : staged)

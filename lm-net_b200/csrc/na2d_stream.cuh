@@ -154,21 +154,32 @@ template <int RING> __device__ __forceinline__ int ring_rel(int slot, int delta)
 
 __host__ __device__ __forceinline__ size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
+// CTAs per SM the forward's register budget is sized for (no spills at these: 80 / 96 / 168 registers)
+__host__ __device__ constexpr int stream_fwd_minblocks(int K, int HG) { return HG * K * K > 60 ? 2 : K == 3 ? 4 : 3; }
+
 // ------------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------------
+// Query rows computed between two barriers (the barrier was ~1/3 of the stall samples at one row per barrier,
+// profiles/r01_ncu_na_stream_*): the rings hold the K-1+RS rows of the current group plus the RS rows of the next.
+template <int KT> struct StreamFwdCfg {
+    static constexpr int RS = KT == 3 ? 4 : 2;
+    static constexpr int RING = KT - 1 + 2 * RS;
+};
+inline size_t stream_fwd_smem_bytes(int K, int D, int heads, int QW) {
+    const int R = 2 * K - 1, Cb = heads * D * 2, KW = QW + 2 * (K / 2), RS = K == 3 ? 4 : 2, RING = K - 1 + 2 * RS;
+    return align16((size_t)heads * R * R * 4) + 2 * (size_t)RING * KW * Cb;
+}
 template <int KT, int D, int HG> struct StreamFwdSmem {
-    static size_t bytes(int heads, int QW) {
-        const int R = 2 * KT - 1, Cb = heads * D * 2, KW = QW + 2 * (KT / 2);
-        return align16((size_t)heads * R * R * 4) + 2 * (size_t)(KT + 1) * KW * Cb;
-    }
+    static size_t bytes(int heads, int QW) { return stream_fwd_smem_bytes(KT, D, heads, QW); }
 };
 
 template <typename T, int KT, int D, int HG>
-__global__ void __launch_bounds__(kStreamThreads, (HG * KT * KT > 60) ? 2 : 3)
+__global__ void __launch_bounds__(kStreamThreads, stream_fwd_minblocks(KT, HG))
 na2d_stream_fwd_kernel(V5<const T> q, V5<const T> k, V5<const T> v, const float* __restrict__ rpb,
                        V5<T> out, float* __restrict__ lse, NAGeom g, StreamCfg cfg, float scale) {
-    constexpr int K = KT, NS = K / 2, KK = K * K, R = 2 * K - 1, RING = K + 1;
+    constexpr int K = KT, NS = K / 2, KK = K * K, R = 2 * K - 1;
+    constexpr int RS = StreamFwdCfg<KT>::RS, RING = StreamFwdCfg<KT>::RING;
     constexpr int VEC = HG * D, VB = VEC * 2, VW = (VB + 3) / 4, PW = (KK + 1) / 2;
     using M = Mixed<T>;
     extern __shared__ __align__(16) unsigned char stream_smem[];
@@ -203,15 +214,18 @@ na2d_stream_fwd_kernel(V5<const T> q, V5<const T> k, V5<const T> v, const float*
     ks.init(k.ptr + sg.b * k.sb + (sg.ri + (int64_t)g.d * kv_next) * k.sh, k.sw, g.d, sg.rj, kv_lo, kv_n, colq, QW, h0 * D);
     vs.init(v.ptr + sg.b * v.sb + (sg.ri + (int64_t)g.d * kv_next) * v.sh, v.sw, g.d, sg.rj, kv_lo, kv_n, colq, QW, h0 * D);
     const uint32_t k_s32 = smem_u32(kring) + sthr, v_s32 = smem_u32(vring) + sthr;
-    auto stage_row = [&]() {
-        ks.stage(k_s32 + kv_soff, QW * Cb, kdh);
-        vs.stage(v_s32 + kv_soff, QW * Cb, vdh);
-        kv_soff += ring_row;
-        kv_soff = kv_soff == ring_bytes ? 0 : kv_soff;
-        ++kv_next;
-    };
+    auto stage_until = [&](int last_query_row) {   // everything query rows <= last_query_row read
+        const int need = axis_window(last_query_row, sg.Hr, K).start + K;
 #pragma unroll 1
-    for (int x = 0; x < K; ++x) stage_row();   // the K rows of query row r0
+        while (kv_next < need) {
+            ks.stage(k_s32 + kv_soff, QW * Cb, kdh);
+            vs.stage(v_s32 + kv_soff, QW * Cb, vdh);
+            kv_soff += ring_row;
+            kv_soff = kv_soff == ring_bytes ? 0 : kv_soff;
+            ++kv_next;
+        }
+    };
+    stage_until(min(r0 + RS, r1) - 1);
     cp_async_commit();
 
     const int cq = c0 + colq;
@@ -223,90 +237,97 @@ na2d_stream_fwd_kernel(V5<const T> q, V5<const T> k, V5<const T> v, const float*
     T* op = out.ptr + sg.b * out.sb + (sg.ri + (int64_t)g.d * r0) * out.sh + (int64_t)j * out.sw + h0 * D;
     const int64_t qdh = g.d * q.sh, odh = g.d * out.sh;
     const float* rp_col = s_rpb + (wj.pb * heads + h0);
+    uint32_t qnext[VW];
+    if (active) load_words<VB, VW>(qp, qnext);
 
 #pragma unroll 1
-    for (int t = r0; t < r1; ++t, qp += qdh, op += odh) {
-        uint32_t qw[VW];
-        if (active) load_words<VB, VW>(qp, qw);          // issued before the barrier: latency overlaps the wait
+    for (int t0 = r0; t0 < r1; t0 += RS) {
+        const int t1 = min(t0 + RS, r1);
         cp_async_wait_all();
         __syncthreads();
-        // a query row needs at most one key row more than its predecessor
-        if (t + 1 < r1 && kv_next < axis_window(t + 1, sg.Hr, K).start + K) stage_row();
+        if (t1 < r1) stage_until(min(t1 + RS, r1) - 1);   // next group's rows land while this group computes
         cp_async_commit();
         if (!active) continue;
-        const AxisWin wi = axis_window(t, sg.Hr, K);
-        const float* rp = rp_col + wi.pb * R * heads;
-        const int slot0 = wi.start % RING;
+#pragma unroll 1
+        for (int t = t0; t < t1; ++t, qp += qdh, op += odh) {
+            uint32_t qw[VW];
+#pragma unroll
+            for (int x = 0; x < VW; ++x) qw[x] = qnext[x];
+            if (t + 1 < r1) load_words<VB, VW>(qp + qdh, qnext);   // next row's query: latency hidden by this row
+            const AxisWin wi = axis_window(t, sg.Hr, K);
+            const float* rp = rp_col + wi.pb * R * heads;
+            const int slot0 = wi.start % RING;
 
-        float s[HG][KK], mx[HG];
+            float s[HG][KK], mx[HG];
 #pragma unroll
-        for (int hg = 0; hg < HG; ++hg) mx[hg] = -INFINITY;
+            for (int hg = 0; hg < HG; ++hg) mx[hg] = -INFINITY;
 #pragma unroll
-        for (int mi = 0; mi < K; ++mi) {
-            const unsigned char* krow = kring + ring_rel<RING>(slot0, mi) * ring_row + kthr;
+            for (int mi = 0; mi < K; ++mi) {
+                const unsigned char* krow = kring + ring_rel<RING>(slot0, mi) * ring_row + kthr;
 #pragma unroll
-            for (int mj = 0; mj < K; ++mj) {
-                uint32_t kw[VW];
-                load_words<VB, VW>(krow + mj * Cb, kw);
-                float rb[HG];
-                load_floats<HG>(rp + (mi * R + mj) * heads, rb);
+                for (int mj = 0; mj < K; ++mj) {
+                    uint32_t kw[VW];
+                    load_words<VB, VW>(krow + mj * Cb, kw);
+                    float rb[HG];
+                    load_floats<HG>(rp + (mi * R + mj) * heads, rb);
 #pragma unroll
-                for (int hg = 0; hg < HG; ++hg) {
-                    float a = rb[hg];
+                    for (int hg = 0; hg < HG; ++hg) {
+                        float a = rb[hg];
 #pragma unroll
-                    for (int e = 0; e < D; ++e) a = M::fma(elem_of<VW>(qw, hg * D + e), elem_of<VW>(kw, hg * D + e), a);
-                    s[hg][mi * K + mj] = a;
-                    mx[hg] = fmaxf(mx[hg], a);
+                        for (int e = 0; e < D; ++e) a = M::fma(elem_of<VW>(qw, hg * D + e), elem_of<VW>(kw, hg * D + e), a);
+                        s[hg][mi * K + mj] = a;
+                        mx[hg] = fmaxf(mx[hg], a);
+                    }
                 }
             }
-        }
-        uint32_t pw[HG][PW];
-        float inv[HG], lse2[HG];
+            uint32_t pw[HG][PW];
+            float inv[HG], lse2[HG];
 #pragma unroll
-        for (int hg = 0; hg < HG; ++hg) {
-            const float mc = mx[hg] * c;
-            float den = 0.f;
+            for (int hg = 0; hg < HG; ++hg) {
+                const float mc = mx[hg] * c;
+                float den = 0.f;
 #pragma unroll
-            for (int n = 0; n < KK; ++n) {
-                const float p = fast_exp2(fmaf(s[hg][n], c, -mc));
-                s[hg][n] = p;
-                den += p;
+                for (int n = 0; n < KK; ++n) {
+                    const float p = fast_exp2(fmaf(s[hg][n], c, -mc));
+                    s[hg][n] = p;
+                    den += p;
+                }
+                inv[hg] = __fdividef(1.f, den);
+                lse2[hg] = mc + __log2f(den);
+#pragma unroll
+                for (int n2 = 0; n2 < PW; ++n2) pw[hg][n2] = M::pack(s[hg][2 * n2], 2 * n2 + 1 < KK ? s[hg][2 * n2 + 1] : 0.f);
             }
-            inv[hg] = __fdividef(1.f, den);
-            lse2[hg] = mc + __log2f(den);
+            float acc[VEC];
 #pragma unroll
-            for (int n2 = 0; n2 < PW; ++n2) pw[hg][n2] = M::pack(s[hg][2 * n2], 2 * n2 + 1 < KK ? s[hg][2 * n2 + 1] : 0.f);
-        }
-        float acc[VEC];
+            for (int e = 0; e < VEC; ++e) acc[e] = 0.f;
 #pragma unroll
-        for (int e = 0; e < VEC; ++e) acc[e] = 0.f;
+            for (int mi = 0; mi < K; ++mi) {
+                const unsigned char* vrow = vring + ring_rel<RING>(slot0, mi) * ring_row + kthr;
 #pragma unroll
-        for (int mi = 0; mi < K; ++mi) {
-            const unsigned char* vrow = vring + ring_rel<RING>(slot0, mi) * ring_row + kthr;
+                for (int mj = 0; mj < K; ++mj) {
+                    uint32_t vw[VW];
+                    load_words<VB, VW>(vrow + mj * Cb, vw);
+                    const int n = mi * K + mj;
 #pragma unroll
-            for (int mj = 0; mj < K; ++mj) {
-                uint32_t vw[VW];
-                load_words<VB, VW>(vrow + mj * Cb, vw);
-                const int n = mi * K + mj;
+                    for (int hg = 0; hg < HG; ++hg)
+#pragma unroll
+                        for (int e = 0; e < D; ++e)
+                            acc[hg * D + e] = M::fma(half_of(pw[hg][n >> 1], n & 1), elem_of<VW>(vw, hg * D + e), acc[hg * D + e]);
+                }
+            }
+            uint32_t ow[VW];
+#pragma unroll
+            for (int x = 0; x < VW; ++x) {
+                const int e0 = 2 * x, e1 = 2 * x + 1;
+                ow[x] = M::pack(acc[e0] * inv[e0 / D], e1 < VEC ? acc[e1] * inv[e1 / D] : 0.f);
+            }
+            store_words<VB, VW>(op, ow);
+            if (lse != nullptr) {
+                const int i = sg.ri + g.d * t;
 #pragma unroll
                 for (int hg = 0; hg < HG; ++hg)
-#pragma unroll
-                    for (int e = 0; e < D; ++e)
-                        acc[hg * D + e] = M::fma(half_of(pw[hg][n >> 1], n & 1), elem_of<VW>(vw, hg * D + e), acc[hg * D + e]);
+                    lse[(((int64_t)sg.b * g.H + i) * g.W + j) * heads + h0 + hg] = lse2[hg] * kLn2;
             }
-        }
-        uint32_t ow[VW];
-#pragma unroll
-        for (int x = 0; x < VW; ++x) {
-            const int e0 = 2 * x, e1 = 2 * x + 1;
-            ow[x] = M::pack(acc[e0] * inv[e0 / D], e1 < VEC ? acc[e1] * inv[e1 / D] : 0.f);
-        }
-        store_words<VB, VW>(op, ow);
-        if (lse != nullptr) {
-            const int i = sg.ri + g.d * t;
-#pragma unroll
-            for (int hg = 0; hg < HG; ++hg)
-                lse[(((int64_t)sg.b * g.H + i) * g.W + j) * heads + h0 + hg] = lse2[hg] * kLn2;
         }
     }
 }
@@ -323,17 +344,22 @@ __host__ __device__ __forceinline__ int stream_boundary(int s, int T, int L, int
     return (int)b;
 }
 
+inline size_t stream_bwd_smem_bytes(int K, int D, int HG, int heads, int QW) {
+    const int R = 2 * K - 1, Cb = heads * D * 2, KW = QW + 2 * (K / 2), nthr = QW * (heads / HG), RING = K + K / 2 + 2;
+    return 2 * align16((size_t)heads * R * R * 4) + 2 * (size_t)RING * KW * Cb + 2 * (size_t)RING * QW * Cb +
+           (size_t)RING * QW * heads * sizeof(float2) + (size_t)nthr * HG * K * K * 4 + align16((size_t)QW * 4);
+}
 template <int KT, int D, int HG> struct StreamBwdSmem {
     static constexpr int RING = KT + KT / 2 + 2;
-    static size_t bytes(int heads, int QW) {
-        const int R = 2 * KT - 1, Cb = heads * D * 2, KW = QW + 2 * (KT / 2), nthr = QW * (heads / HG);
-        return 2 * align16((size_t)heads * R * R * 4) + 2 * (size_t)RING * KW * Cb + 2 * (size_t)RING * QW * Cb +
-               (size_t)RING * QW * heads * sizeof(float2) + (size_t)nthr * HG * KT * KT * 4 + align16((size_t)QW * 4);
-    }
+    // CTAs per SM the register budget is sized for: 36+ score registers per head group of 4 need 168 registers
+    // (2 CTAs); the narrower variants fit 96 registers without spills, and shared memory allows 3 CTAs except at
+    // head dim 8
+    static constexpr int MINB = (HG * KT * KT > 18 || D >= 8) ? 2 : 3;
+    static size_t bytes(int heads, int QW) { return stream_bwd_smem_bytes(KT, D, HG, heads, QW); }
 };
 
 template <typename T, int KT, int D, int HG>
-__global__ void __launch_bounds__(kStreamThreads, 2)
+__global__ void __launch_bounds__(kStreamThreads, StreamBwdSmem<KT, D, HG>::MINB)
 na2d_stream_bwd_kernel(V5<const T> q, V5<const T> k, V5<const T> v, V5<const T> dout, const float* __restrict__ rpb,
                        V5<T> dq, V5<T> dk, V5<T> dv, float* __restrict__ drpb_part, NAGeom g, StreamCfg cfg,
                        float scale) {
