@@ -60,9 +60,18 @@ bool make_plan(const NAGeom& g, bool bwd, int64_t max_parts, int ctas_per_sm, Pl
     const int by_smem = (int)((size_t)(227 * 1024) / (smem + 1024));   // 1 KB per CTA reserved by the driver
     if (by_smem < 1) return false;
     const int64_t resident = 148 * (int64_t)(ctas_per_sm < by_smem ? ctas_per_sm : by_smem);
-    int64_t bands = resident / ((int64_t)p.stripes * p.z);
+    // whole waves: with b bands the grid is b*stripes*z CTAs; pick the wave count (1..6) whose last wave is fullest
+    const int64_t sz = (int64_t)p.stripes * p.z;
     const int64_t max_bands = g.Hmax / min_rb > 0 ? g.Hmax / min_rb : 1;
-    bands = bands < 1 ? 1 : bands > max_bands ? max_bands : bands;
+    int64_t bands = 1;
+    double best = -1.0;
+    for (int w = 1; w <= 6; ++w) {
+        int64_t b = w * resident / sz;
+        b = b < 1 ? 1 : b > max_bands ? max_bands : b;
+        const int64_t waves = (b * sz + resident - 1) / resident;
+        const double eff = (double)(b * sz) / (double)(waves * resident);
+        if (eff > best + 0.03) { best = eff; bands = b; }
+    }
     if (bwd && max_parts > 0) {
         const int64_t cap = max_parts / ((int64_t)p.stripes * p.z);
         if (cap < 1) return false;
@@ -169,7 +178,7 @@ int stream_bwd(const FusedArgs& a, int dtype, int64_t max_parts, int64_t* n_part
     if (g.K != 3) return LMNET_ERR_UNSUPPORTED;
     Plan p;
     static const bool hg2 = getenv("LMNET_NA_BWD_HG2") != nullptr && atoi(getenv("LMNET_NA_BWD_HG2")) != 0;   // tuning knob
-    const int resident = (g.D == 2 || g.D == 4 || (hg2 && g.D == 1)) ? 3 : 2;   // StreamBwdSmem::MINB
+    const int resident = g.D == 4 ? 3 : 2;   // StreamBwdSmem::MINB
     if (!make_plan(g, true, max_parts, resident, p, (hg2 && g.D == 1) ? 2 : 0)) return LMNET_ERR_UNSUPPORTED;
     const int vb = p.HG * g.D * 2;
     const lmnet_view5* staged[] = {a.q, a.k, a.v, a.dout};

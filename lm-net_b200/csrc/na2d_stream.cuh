@@ -345,16 +345,18 @@ __host__ __device__ __forceinline__ int stream_boundary(int s, int T, int L, int
 }
 
 inline size_t stream_bwd_smem_bytes(int K, int D, int HG, int heads, int QW) {
-    const int R = 2 * K - 1, Cb = heads * D * 2, KW = QW + 2 * (K / 2), nthr = QW * (heads / HG), RING = K + K / 2 + 2;
+    const int R = 2 * K - 1, Cb = heads * D * 2, KW = QW + 2 * (K / 2), nthr = QW * (heads / HG), RING = K + K / 2 + 3;
     return 2 * align16((size_t)heads * R * R * 4) + 2 * (size_t)RING * KW * Cb + 2 * (size_t)RING * QW * Cb +
-           (size_t)RING * QW * heads * sizeof(float2) + (size_t)nthr * HG * K * K * 4 + align16((size_t)QW * 4);
+           (size_t)RING * QW * heads * sizeof(float2) + align16((size_t)nthr * K * K * 4) + align16((size_t)QW * 4) + 16;
 }
 template <int KT, int D, int HG> struct StreamBwdSmem {
-    static constexpr int RING = KT + KT / 2 + 2;
-    // CTAs per SM the register budget is sized for: 36+ score registers per head group of 4 need 168 registers
-    // (2 CTAs); the narrower variants fit 96 registers without spills, and shared memory allows 3 CTAs except at
-    // head dim 8
-    static constexpr int MINB = (HG * KT * KT > 18 || D >= 8) ? 2 : 3;
+    // rows per ring: K + K/2 live rows for phase B, the row of phase A, the row being prefetched, and one row of
+    // slack because warps may run one phase apart (mbarrier instead of a CTA-wide barrier, see the kernel)
+    static constexpr int RING = KT + KT / 2 + 3;
+    // CTAs per SM the register budget is sized for: scores + dP + drpb sums of 2-4 heads need ~165 registers
+    // (2 CTAs); one head per thread fits 96 registers without spills (3 CTAs) unless shared memory (head dim 8)
+    // allows only 2
+    static constexpr int MINB = (HG * KT * KT > 9 || D >= 8) ? 2 : 3;
     static size_t bytes(int heads, int QW) { return stream_bwd_smem_bytes(KT, D, HG, heads, QW); }
 };
 
@@ -379,8 +381,9 @@ na2d_stream_bwd_kernel(V5<const T> q, V5<const T> k, V5<const T> v, V5<const T> 
     unsigned char* qring = vring + kv_bytes;
     unsigned char* gring = qring + RING * q_row;
     float2* sring = reinterpret_cast<float2*>(gring + RING * q_row);             // [RING][QW][heads] (lse2, delta)
-    float* s_tbl = reinterpret_cast<float*>(sring + (size_t)RING * QW * heads);  // [nthr][HG][KK] drpb flush table
-    int* s_pbj = reinterpret_cast<int*>(s_tbl + (size_t)nthr * HG * KK);         // [QW] column rpb offset of each thread
+    float* s_tbl = reinterpret_cast<float*>(sring + (size_t)RING * QW * heads);  // [nthr][KK] drpb flush table (one head per pass)
+    int* s_pbj = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(s_tbl) + align16((size_t)nthr * KK * 4));  // [QW] column rpb offset
+    const uint32_t mbar = smem_u32(reinterpret_cast<unsigned char*>(s_pbj) + align16((size_t)QW * 4));              // row hand-off barrier
     const int64_t cta = ((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
 
     const SubGrid sg = decode_subgrid(g, blockIdx.z);
@@ -467,32 +470,57 @@ na2d_stream_bwd_kernel(V5<const T> q, V5<const T> k, V5<const T> v, V5<const T> 
     if (hgi == 0) s_pbj[colq] = wjA.pb;
     auto flush_racc = [&]() {   // called by every thread of the CTA
 #pragma unroll
-        for (int hg = 0; hg < HG; ++hg)
+        for (int hg = 0; hg < HG; ++hg) {
 #pragma unroll
             for (int n = 0; n < KK; ++n) {
-                s_tbl[(tid * HG + hg) * KK + n] = racc[hg][n];
+                s_tbl[tid * KK + n] = racc[hg][n];
                 racc[hg][n] = 0.f;
             }
-        __syncthreads();
-        for (int x = tid; x < nb; x += nthr) {
-            const int h = x % heads, pp = x / heads, pi = pp / R, pj = pp - pi * R;
-            const int mi = pi - cur_pb;
-            if (mi < 0 || mi >= K) continue;
-            const int hgx = h / HG, hg = h - hgx * HG;
-            float sum = 0.f;
-            for (int cc = 0; cc < QW; ++cc) {
-                const int mj = pj - s_pbj[cc];
-                if (mj >= 0 && mj < K) sum += s_tbl[((cc * NG + hgx) * HG + hg) * KK + mi * K + mj];
+            __syncthreads();
+            for (int x = tid; x < nb; x += nthr) {
+                const int h = x % heads, pp = x / heads, pi = pp / R, pj = pp - pi * R;
+                const int mi = pi - cur_pb, hgx = h / HG;
+                if (mi < 0 || mi >= K || h - hgx * HG != hg) continue;
+                float sum = 0.f;
+                for (int cc = 0; cc < QW; ++cc) {
+                    const int mj = pj - s_pbj[cc];
+                    if (mj >= 0 && mj < K) sum += s_tbl[(cc * NG + hgx) * KK + mi * K + mj];
+                }
+                s_acc[x] += sum;
             }
-            s_acc[x] += sum;
+            __syncthreads();
         }
-        __syncthreads();
     };
+
+    // Row hand-off.  Instead of a CTA-wide barrier per row (30 % of the stall samples when it was one), every
+    // thread ARRIVES on an mbarrier once its phase A of row t is done and its copies for row t+1 have landed,
+    // runs phase B of row t-1 (which only reads what earlier phases published) and WAITS just before phase A of
+    // row t+1: warps may drift one phase apart, which the extra ring row makes safe.
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(nthr) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto row_arrive = [&]() { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory"); };
+    auto row_wait = [&](uint32_t parity) {
+        asm volatile(
+            "{\n"
+            ".reg .pred P1;\n"
+            "LAB_WAIT:\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+            "@P1 bra DONE;\n"
+            "bra LAB_WAIT;\n"
+            "DONE:\n"
+            "}" ::"r"(mbar), "r"(parity) : "memory");
+    };
+    cp_async_wait_all();
+    row_arrive();
+    uint32_t parity = 0;
 
 #pragma unroll 1
     for (int t = tq_lo; t <= tq_hi + 1; ++t) {
-        cp_async_wait_all();
-        __syncthreads();
+        row_wait(parity);
+        parity ^= 1u;
         if (t + 1 <= tq_hi) {
             stage_q(ring_rel<RING>(slot_t, 1));
             if (kv_next < axis_window(t + 1, sg.Hr, K).start + K) stage_kv();
@@ -602,6 +630,9 @@ na2d_stream_bwd_kernel(V5<const T> q, V5<const T> k, V5<const T> v, V5<const T> 
                 }
             }
         }
+
+        cp_async_wait_all();
+        row_arrive();
 
         // ---------------- phase B: key rows whose last attending query row is t-1 ----------------
         const int tb = t - 1;

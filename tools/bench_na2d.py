@@ -5,7 +5,7 @@
 For each LM-Net stage shape of the 352x352 / batch-16 workload ([16,R,R,12,hd], R,hd = 352,1 / 176,2 / 88,4 /
 44,8), kernel 3 (what the model runs) and kernel 7 with dilation 1 and 2 (the BASELINE micro-benchmark), bf16:
 fused forward and forward+backward time (CUDA events, L2 flushed between iterations by writing a 512 MB
-buffer), algorithmic GB/s (fwd 4*N*es, bwd 7*N*es) and the fraction of the measured HBM peak.
+buffer; a device-side spin before the first event keeps host launch latency out of the interval), algorithmic GB/s (fwd 4*N*es, bwd 7*N*es) and the fraction of the measured HBM peak.
 Then one LM-Net inference pass at batch 8, 1024x1024, bf16 (eval mode: running statistics folded).
 """
 import argparse
@@ -34,7 +34,8 @@ def time_it(fn, flush, iters=10, warm=3):
     ts = []
     for _ in range(iters):
         flush.fill_(1.0)
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda._sleep(2_000_000)   # ~1 ms of device spin: the host enqueues fn() meanwhile, so the events
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)  # bracket device time only
         a.record()
         fn()
         b.record()
