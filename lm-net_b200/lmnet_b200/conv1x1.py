@@ -118,21 +118,23 @@ def _compute_dtype(x):
 
 
 def expand_1x1(conv: torch.nn.Conv2d, x: torch.Tensor) -> torch.Tensor:
-    """conv(x) for a 1x1 convolution on a CUDA NCHW tensor (falls back to the module for uncovered cases)."""
+    """conv(x) for a 1x1 convolution on a CUDA NCHW tensor (cuDNN through the module for uncovered shapes)."""
+    L.require_cuda(x)
     dt = _compute_dtype(x)
     B, K, H, W = x.shape
     M = conv.out_channels
-    if x.is_cuda and wgrad_supported(B, M, K, 0, H * W, dt):
+    if wgrad_supported(B, M, K, 0, H * W, dt):
         return _Expand1x1.apply(x.to(dt).contiguous(), conv.weight.view(M, K), conv.bias)
     return conv(x)
 
 
 def pointwise_shortcut(pw: torch.nn.Conv2d, sc: torch.nn.Conv2d, z, gate, x):
-    """pw(gate * z) + sc(x) with gate [B,E,1,1]; fused path on CUDA, module calls otherwise."""
+    """pw(gate * z) + sc(x) with gate [B,E,1,1] on CUDA tensors (module calls for uncovered shapes)."""
+    L.require_cuda(z, x)
     dt = _compute_dtype(z)
     B, E, H, W = z.shape
     Cin, Cout = x.shape[1], pw.out_channels
-    if z.is_cuda and pw.bias is not None and sc.bias is not None and wgrad_supported(B, Cout, E, Cin, H * W, dt):
+    if pw.bias is not None and sc.bias is not None and wgrad_supported(B, Cout, E, Cin, H * W, dt):
         bias = pw.bias + sc.bias
         return _PointwiseShortcut.apply(z.to(dt).contiguous(), gate.reshape(B, E), x.to(dt).contiguous(),
                                         pw.weight.view(Cout, E), sc.weight.view(Cout, Cin), bias)

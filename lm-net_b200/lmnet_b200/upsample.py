@@ -38,12 +38,14 @@ class _Up2x(torch.autograd.Function):
 
 class Upsample2x(torch.nn.Module):
     """Drop-in for nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True) (no parameters, so
-    state_dicts are unaffected).  CUDA tensors run the fused kernel; anything else uses F.interpolate."""
+    state_dicts are unaffected).  CUDA only, like every operator of the package: a CPU tensor raises.  fp32 / bf16 /
+    fp16 NCHW tensors run the fused kernel; other CUDA dtypes or ranks go to ATen's kernel."""
 
     scale_factor, mode, align_corners = 2, "bilinear", True
 
     def forward(self, x):
-        if x.is_cuda and x.dim() == 4 and x.dtype in (torch.float32, torch.bfloat16, torch.float16):
+        L.require_cuda(x)
+        if x.dim() == 4 and x.dtype in (torch.float32, torch.bfloat16, torch.float16):
             return _Up2x.apply(x)
         return torch.nn.functional.interpolate(x, scale_factor=2, mode="bilinear", align_corners=True)
 

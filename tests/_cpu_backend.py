@@ -66,6 +66,10 @@ def apply(setattr_fn):
     from lmnet_b200 import patch
 
     setattr_fn(patch, "layer_norm", lambda ln, x: ln(x))
+    from lmnet_b200 import upsample
+
+    setattr_fn(upsample.Upsample2x, "forward",
+               lambda self, x: F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=True))
     setattr_fn(reparam, "fused_dw_bn_gelu", lambda mod, x1: reparam_ref.dw_bn_gelu(mod, x1))
     setattr_fn(reparam, "fused_dw_deploy", lambda mod, x1: reparam_ref.dw_bn_gelu(mod, x1))
     return o

@@ -163,3 +163,23 @@ def test_oracle_module_state_dict_keys():
     assert y.shape == x.shape
     y.sum().backward()
     assert m.rpb.grad is not None and m.rpb.grad.abs().sum() > 0
+
+
+def test_cpu_reference_model_is_self_contained():
+    """bench.py's cpu_baseline / `--impl reference` arm: the oracle's LM-Net must run forward + backward on CPU
+    tensors WITHOUT the test backend that stands in for the CUDA library — i.e. it may not reach any lmnet_b200
+    operator (those raise on CPU tensors).  Guards the widened modules (LayerNorm, BN+act, up-sampling)."""
+    import torch
+
+    from lmnet_b200 import _lib
+    from lmnet_b200.train import build_training, synthetic_batches, train_step
+    from oracle.lmnet_ref import build_cpu_reference
+
+    with pytest.raises(RuntimeError):          # the product really is CUDA-only in this process
+        _lib.require_cuda(torch.zeros(1))
+    net = build_cpu_reference(3, 2, seed=42).train()
+    opt, crit, dice = build_training(net, "cpu", fused=False)
+    images, labels = synthetic_batches(1, 1, 32, seed=0, pin=False)[0]
+    loss, out = train_step(net, opt, images, labels, crit, dice, amp_dtype=None)
+    assert torch.isfinite(loss) and out.shape == (1, 2, 32, 32)
+    assert all(p.grad is None or torch.isfinite(p.grad).all() for p in net.parameters())
