@@ -229,7 +229,13 @@ class ConfusionMetrics:
 
     def update(self, pred, labels):
         idx = labels.reshape(-1) * self.n + pred.reshape(-1)
-        cm = torch.bincount(idx, minlength=self.n * self.n)
+        if idx.is_cuda and self.n * self.n <= 16:
+            # torch.bincount synchronises the host on CUDA (it reads max(idx) to size its output), which would
+            # serialise host and device every step; a compare-and-sum histogram needs no host round trip
+            bins = torch.arange(self.n * self.n, device=idx.device, dtype=idx.dtype)
+            cm = (idx.unsqueeze(1) == bins).sum(0)
+        else:
+            cm = torch.bincount(idx, minlength=self.n * self.n)
         self.cm = cm if self.cm is None else self.cm + cm.to(self.cm.device)
 
     def compute(self):
