@@ -2,7 +2,7 @@
 // eligibility, stripe / band sizing, shared-memory opt-in and the template fan-out for bf16 / fp16.
 #include "na2d_stream.cuh"
 
-#include <climits>
+#include <atomic>
 #include <cstdlib>
 
 namespace lmnet {
@@ -34,16 +34,14 @@ struct Plan {
     unsigned z;
 };
 
-bool make_plan(const NAGeom& g, bool bwd, int64_t max_parts, int ctas_per_sm, Plan& p, int hg_override = 0) {
+bool make_plan(const NAGeom& g, bool bwd, int64_t max_parts, int ctas_per_sm, Plan& p) {
     const int K = g.K, NS = K / 2;
     if (g.D != 1 && g.D != 2 && g.D != 4 && g.D != 8) return false;
-    p.HG = hg_override > 0 ? hg_override : stream_hg(K, g.D);
+    p.HG = stream_hg(K, g.D);
     if (g.heads % p.HG != 0 || (g.heads * g.D) % 2 != 0) return false;
     p.cfg.NG = g.heads / p.HG;
     if (p.cfg.NG > kStreamThreads) return false;
-    static const int threads = getenv("LMNET_NA_THREADS") ? atoi(getenv("LMNET_NA_THREADS")) : kStreamThreads;   // tuning knob
-    if (threads < 32 || threads > kStreamThreads) return false;
-    p.cfg.QW = threads / p.cfg.NG;
+    p.cfg.QW = kStreamThreads / p.cfg.NG;
     const int halo = bwd ? 2 * NS : 0;
     if (p.cfg.QW - halo < K) return false;
     if (2 * NS > p.cfg.QW) return false;   // the halo columns are staged by the first 2*(K/2) column threads
@@ -83,13 +81,22 @@ bool make_plan(const NAGeom& g, bool bwd, int64_t max_parts, int ctas_per_sm, Pl
     return true;
 }
 
-template <typename Kern> bool ensure_smem(Kern kern, size_t bytes) {
+// Opt-in to > 48 KB of dynamic shared memory, once per kernel, device and size (the attribute is per device;
+// granted[dev] = largest size set so far).
+constexpr int kMaxDevices = 64;
+template <typename Kern> bool ensure_smem(Kern kern, size_t bytes, std::atomic<size_t>* granted_per_device) {
     if (bytes > 227 * 1024) return false;
-    if (bytes > 48 * 1024 &&
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) {
+    if (bytes <= 48 * 1024) return true;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return false;
+    std::atomic<size_t>& granted = granted_per_device[dev];
+    if (bytes <= granted.load(std::memory_order_relaxed)) return true;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) {
         (void)cudaGetLastError();
         return false;
     }
+    size_t prev = granted.load(std::memory_order_relaxed);
+    while (prev < bytes && !granted.compare_exchange_weak(prev, bytes, std::memory_order_relaxed)) {}
     return true;
 }
 
@@ -98,7 +105,8 @@ int launch_fwd(const FusedArgs& a, const Plan& p) {
     const NAGeom& g = a.g;
     const size_t smem = StreamFwdSmem<KT, D, HG>::bytes(g.heads, p.cfg.QW);
     auto kern = na2d_stream_fwd_kernel<T, KT, D, HG>;
-    if (!ensure_smem(kern, smem)) return LMNET_ERR_UNSUPPORTED;
+    static std::atomic<size_t> granted[kMaxDevices];
+    if (!ensure_smem(kern, smem, granted)) return LMNET_ERR_UNSUPPORTED;
     const dim3 grid((unsigned)p.stripes, (unsigned)p.bands, p.z);
     const double n_bytes = (double)g.B * g.H * g.W * g.heads * g.D * sizeof(T);
     LMNET_LAUNCH(KID_NA_STREAM_FWD, a.stream, 4 * n_bytes,
@@ -112,7 +120,8 @@ int launch_bwd(const FusedArgs& a, const Plan& p) {
     const NAGeom& g = a.g;
     const size_t smem = StreamBwdSmem<KT, D, HG>::bytes(g.heads, p.cfg.QW);
     auto kern = na2d_stream_bwd_kernel<T, KT, D, HG>;
-    if (!ensure_smem(kern, smem)) return LMNET_ERR_UNSUPPORTED;
+    static std::atomic<size_t> granted[kMaxDevices];
+    if (!ensure_smem(kern, smem, granted)) return LMNET_ERR_UNSUPPORTED;
     const dim3 grid((unsigned)p.stripes, (unsigned)p.bands, p.z);
     const double n_bytes = (double)g.B * g.H * g.W * g.heads * g.D * sizeof(T);
     LMNET_LAUNCH(KID_NA_STREAM_BWD, a.stream, 7 * n_bytes,
@@ -149,7 +158,7 @@ template <typename T>
 int bwd_typed(const FusedArgs& a, const Plan& p) {
     if (a.g.K != 3) return LMNET_ERR_UNSUPPORTED;
     switch (a.g.D) {
-        case 1: return p.HG == 2 ? launch_bwd<T, 3, 1, 2>(a, p) : launch_bwd<T, 3, 1, 4>(a, p);
+        case 1: return launch_bwd<T, 3, 1, 4>(a, p);
         case 2: return launch_bwd<T, 3, 2, 2>(a, p);
         case 4: return launch_bwd<T, 3, 4, 1>(a, p);
         case 8: return launch_bwd<T, 3, 8, 1>(a, p);
@@ -177,9 +186,8 @@ int stream_bwd(const FusedArgs& a, int dtype, int64_t max_parts, int64_t* n_part
     const NAGeom& g = a.g;
     if (g.K != 3) return LMNET_ERR_UNSUPPORTED;
     Plan p;
-    static const bool hg2 = getenv("LMNET_NA_BWD_HG2") != nullptr && atoi(getenv("LMNET_NA_BWD_HG2")) != 0;   // tuning knob
     const int resident = g.D == 4 ? 3 : 2;   // StreamBwdSmem::MINB
-    if (!make_plan(g, true, max_parts, resident, p, (hg2 && g.D == 1) ? 2 : 0)) return LMNET_ERR_UNSUPPORTED;
+    if (!make_plan(g, true, max_parts, resident, p)) return LMNET_ERR_UNSUPPORTED;
     const int vb = p.HG * g.D * 2;
     const lmnet_view5* staged[] = {a.q, a.k, a.v, a.dout};
     for (auto* x : staged)

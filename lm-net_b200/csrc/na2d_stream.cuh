@@ -144,6 +144,27 @@ template <typename T, int VB, bool HALO> struct RowStager {
     }
 };
 
+// CTA-local mbarrier: arrive (release) / wait on a phase parity (acquire).  Used instead of __syncthreads where a
+// thread has independent work between publishing its data and needing everybody else's.
+__device__ __forceinline__ void mbar_init(uint32_t mbar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t mbar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(mbar), "r"(parity) : "memory");
+}
+
 // slot of the ring row `delta` rows away from the row held in `slot` (|delta| < RING)
 template <int RING> __device__ __forceinline__ int ring_rel(int slot, int delta) {
     int x = slot + delta;
@@ -160,15 +181,19 @@ __host__ __device__ constexpr int stream_fwd_minblocks(int K, int HG) { return H
 // ------------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------------
-// Query rows computed between two barriers (the barrier was ~1/3 of the stall samples at one row per barrier,
-// profiles/r01_ncu_na_stream_*): the rings hold the K-1+RS rows of the current group plus the RS rows of the next.
-template <int KT> struct StreamFwdCfg {
-    static constexpr int RS = KT == 3 ? 4 : 2;
-    static constexpr int RING = KT - 1 + 2 * RS;
+// Query rows are computed in groups of RS.  The rings hold three groups: the K-1+RS rows being read, the RS rows of
+// the next group (landed or landing) and the RS rows being staged for the group after that.  Hand-off is an
+// mbarrier: a thread arrives once ITS copies for the next group have landed (after the first row of the current
+// group) and waits at the top of the next group, so nobody waits for the slowest warp's compute; the third group of
+// ring rows is what makes the early staging safe (every thread has left group g-1 when staging for g+2 starts).
+__host__ __device__ constexpr int stream_fwd_rs(int K, int D) { return (K == 3 && D < 8) ? 4 : 2; }
+template <int KT, int D> struct StreamFwdCfg {
+    static constexpr int RS = stream_fwd_rs(KT, D);
+    static constexpr int RING = KT - 1 + 3 * RS;
 };
 inline size_t stream_fwd_smem_bytes(int K, int D, int heads, int QW) {
-    const int R = 2 * K - 1, Cb = heads * D * 2, KW = QW + 2 * (K / 2), RS = K == 3 ? 4 : 2, RING = K - 1 + 2 * RS;
-    return align16((size_t)heads * R * R * 4) + 2 * (size_t)RING * KW * Cb;
+    const int R = 2 * K - 1, Cb = heads * D * 2, KW = QW + 2 * (K / 2), RING = K - 1 + 3 * stream_fwd_rs(K, D);
+    return align16((size_t)heads * R * R * 4) + align16(2 * (size_t)RING * KW * Cb) + 16;
 }
 template <int KT, int D, int HG> struct StreamFwdSmem {
     static size_t bytes(int heads, int QW) { return stream_fwd_smem_bytes(KT, D, heads, QW); }
@@ -179,7 +204,7 @@ __global__ void __launch_bounds__(kStreamThreads, stream_fwd_minblocks(KT, HG))
 na2d_stream_fwd_kernel(V5<const T> q, V5<const T> k, V5<const T> v, const float* __restrict__ rpb,
                        V5<T> out, float* __restrict__ lse, NAGeom g, StreamCfg cfg, float scale) {
     constexpr int K = KT, NS = K / 2, KK = K * K, R = 2 * K - 1;
-    constexpr int RS = StreamFwdCfg<KT>::RS, RING = StreamFwdCfg<KT>::RING;
+    constexpr int RS = StreamFwdCfg<KT, D>::RS, RING = StreamFwdCfg<KT, D>::RING;
     constexpr int VEC = HG * D, VB = VEC * 2, VW = (VB + 3) / 4, PW = (KK + 1) / 2;
     using M = Mixed<T>;
     extern __shared__ __align__(16) unsigned char stream_smem[];
@@ -225,8 +250,14 @@ na2d_stream_fwd_kernel(V5<const T> q, V5<const T> k, V5<const T> v, const float*
             ++kv_next;
         }
     };
+    const uint32_t mbar = smem_u32(vring + align16((size_t)ring_bytes * 2) - ring_bytes);   // after both rings
+    if (tid == 0) mbar_init(mbar, nthr);
+    __syncthreads();                          // barrier initialised, rpb table visible
     stage_until(min(r0 + RS, r1) - 1);
     cp_async_commit();
+    cp_async_wait_all();
+    mbar_arrive(mbar);                        // phase 0: the first group's rows
+    uint32_t parity = 0;
 
     const int cq = c0 + colq;
     const bool active = cq < c1;
@@ -243,11 +274,15 @@ na2d_stream_fwd_kernel(V5<const T> q, V5<const T> k, V5<const T> v, const float*
 #pragma unroll 1
     for (int t0 = r0; t0 < r1; t0 += RS) {
         const int t1 = min(t0 + RS, r1);
-        cp_async_wait_all();
-        __syncthreads();
+        mbar_wait(mbar, parity);                          // every thread's copies for this group have landed
+        parity ^= 1u;
         if (t1 < r1) stage_until(min(t1 + RS, r1) - 1);   // next group's rows land while this group computes
         cp_async_commit();
-        if (!active) continue;
+        if (!active) {
+            cp_async_wait_all();
+            mbar_arrive(mbar);
+            continue;
+        }
 #pragma unroll 1
         for (int t = t0; t < t1; ++t, qp += qdh, op += odh) {
             uint32_t qw[VW];
@@ -327,6 +362,10 @@ na2d_stream_fwd_kernel(V5<const T> q, V5<const T> k, V5<const T> v, const float*
 #pragma unroll
                 for (int hg = 0; hg < HG; ++hg)
                     lse[(((int64_t)sg.b * g.H + i) * g.W + j) * heads + h0 + hg] = lse2[hg] * kLn2;
+            }
+            if (t == t0) {                    // one row of compute later this thread's copies have landed
+                cp_async_wait_all();
+                mbar_arrive(mbar);
             }
         }
     }
@@ -496,23 +535,10 @@ na2d_stream_bwd_kernel(V5<const T> q, V5<const T> k, V5<const T> v, V5<const T> 
     // thread ARRIVES on an mbarrier once its phase A of row t is done and its copies for row t+1 have landed,
     // runs phase B of row t-1 (which only reads what earlier phases published) and WAITS just before phase A of
     // row t+1: warps may drift one phase apart, which the extra ring row makes safe.
-    if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(nthr) : "memory");
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
+    if (tid == 0) mbar_init(mbar, nthr);
     __syncthreads();
-    auto row_arrive = [&]() { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory"); };
-    auto row_wait = [&](uint32_t parity) {
-        asm volatile(
-            "{\n"
-            ".reg .pred P1;\n"
-            "LAB_WAIT:\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-            "@P1 bra DONE;\n"
-            "bra LAB_WAIT;\n"
-            "DONE:\n"
-            "}" ::"r"(mbar), "r"(parity) : "memory");
-    };
+    auto row_arrive = [&]() { mbar_arrive(mbar); };
+    auto row_wait = [&](uint32_t parity) { mbar_wait(mbar, parity); };
     cp_async_wait_all();
     row_arrive();
     uint32_t parity = 0;
