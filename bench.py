@@ -154,6 +154,30 @@ def measured_peaks():
         return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
+def step_roofline(batch, res, ms_per_step):
+    """t_roof = sum_ops max(B/BW, F/P) over one training step, from the committed per-op byte / FLOP
+    table (profiles/step_roofline.json, generated on the CPU by tests/golden/make_step_roofline.py) and the measured
+    peaks of this box; `frac` = t_roof / measured step time of one GPU."""
+    try:
+        tab = json.load(open(os.path.join(ROOT, "profiles", "step_roofline.json")))
+        if tab["resolution"] != res:
+            return None
+        try:
+            pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            bw, tf, src = float(pk["hbm_gbs"]) * 1e9, float(pk["bf16_tflops_sustained"]) * 1e12, "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            bw, tf, src = FALLBACK_HBM_GBS * 1e9, 1400e12, "fallback (B200_PROFILING.md)"
+        t = sum(max((batch * bf + p) / bw, batch * ff / tf) + max((batch * bb + p) / bw, batch * fb / tf)
+                for bf, ff, bb, fb, p in tab["ops"])
+        tot = tab["totals_per_image"]
+        return {"t_roof_ms": round(1e3 * t, 3), "frac": round(1e3 * t / ms_per_step, 4),
+                "algorithmic_GB_per_step": round(batch * (tot["bytes_fwd"] + tot["bytes_bwd"]) / 1e9, 2),
+                "algorithmic_GFLOP_per_step": round(batch * (tot["flops_fwd"] + tot["flops_bwd"]) / 1e9, 1),
+                "peaks": src, "formula": tab["formula"], "source": "profiles/step_roofline.json"}
+    except Exception:
+        return None
+
+
 def run_b200_arm(args):
     import torch.distributed as dist
 
@@ -320,6 +344,7 @@ def run_b200_arm(args):
                         "api": "lmnet_b200.train.train_one_epoch (reference-shaped loop, pinned host batches)"},
                 "cuda_graph": bool(graphed is not None and graphed.graph is not None),
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+                "step_roofline": step_roofline(B, R, ms_total / args.steps),
                 "kernels": kernels, "loss": final_loss}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -245,3 +245,24 @@ def test_bench_reference_arm_prints_the_contract_line():
         assert key in d, key
     assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_step_roofline_table_is_committed_and_plausible():
+    """profiles/step_roofline.json feeds bench.py's `step_roofline`; forward FLOPs per image must agree
+    with the survey's independent probe (19.9 GFLOP at 352x352) and the hot-path units with §8 d4/d5."""
+    import importlib.util
+    import json
+    import os
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    tab = json.load(open(os.path.join(root, "profiles", "step_roofline.json")))
+    assert tab["resolution"] == 352 and len(tab["ops"]) > 200
+    assert abs(tab["totals_per_image"]["flops_fwd"] / 19.9e9 - 1) < 0.05
+    na, dw = tab["by_class"]["NeighborhoodAttention2D.core"], tab["by_class"]["ReparamConv.dw_section"]
+    assert na["ops"] == 4 and abs((na["bytes_fwd"] + na["bytes_bwd"]) * 16 / 981e6 - 1) < 0.01      # §8 d4: 981 MB at batch 16
+    assert dw["ops"] == 16 and abs((dw["bytes_fwd"] + dw["bytes_bwd"]) * 16 / 5.71e9 - 1) < 0.01    # §8 d5: 5.71 GB
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    r = bench.step_roofline(16, 352, 46.8)
+    assert r is not None and 4.0 < r["t_roof_ms"] < 9.0 and 0 < r["frac"] < 1
