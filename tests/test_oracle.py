@@ -183,3 +183,42 @@ def test_cpu_reference_model_is_self_contained():
     loss, out = train_step(net, opt, images, labels, crit, dice, amp_dtype=None)
     assert torch.isfinite(loss) and out.shape == (1, 2, 32, 32)
     assert all(p.grad is None or torch.isfinite(p.grad).all() for p in net.parameters())
+
+
+@pytest.mark.parametrize("H,W,K,heads,D", [(9, 11, 3, 2, 4), (7, 7, 7, 1, 2), (12, 8, 5, 3, 1), (6, 13, 3, 12, 1)])
+def test_oracle_against_flex_attention_with_the_published_natten_mask(H, W, K, heads, D):
+    """Independent pin of the forward: PyTorch's own FlexAttention (unfused CPU path; it has no CPU backward) with the
+    neighbourhood mask as published for NATTEN in PyTorch's attention-gym examples — window centre =
+    clamp(query, K//2, L-1-K//2) per axis, keys within K//2 of the centre — plus the relative positional bias as a
+    score_mod indexed by (key - query + K - 1).  The oracle's backward is pinned to its forward by autograd elsewhere
+    in this file."""
+    import warnings
+
+    from torch.nn.attention.flex_attention import create_block_mask, flex_attention
+
+    def mask_mod(b, h, q_idx, kv_idx):
+        qy, qx, ky, kx = q_idx // W, q_idx % W, kv_idx // W, kv_idx % W
+        cx = qx.clamp(K // 2, (W - 1) - K // 2)
+        cy = qy.clamp(K // 2, (H - 1) - K // 2)
+        return ((cx - kx).abs() <= K // 2) & ((cy - ky).abs() <= K // 2)
+
+    g = torch.Generator().manual_seed(H * 100 + W)
+    q, k, v = (torch.randn(1, heads, H * W, D, generator=g, dtype=torch.float64) for _ in range(3))
+    rpb = 0.5 * torch.randn(heads, 2 * K - 1, 2 * K - 1, generator=g, dtype=torch.float64)
+
+    def score_mod(score, b, h, q_idx, kv_idx):
+        dy = (kv_idx // W - q_idx // W + K - 1).clamp(0, 2 * K - 2)     # masked-out pairs may index anything valid
+        dx = (kv_idx % W - q_idx % W + K - 1).clamp(0, 2 * K - 2)
+        return score + rpb[h, dy, dx]
+
+    def nhwc(t):   # [1, heads, H*W, D] -> [1, H, W, heads, D]
+        return t.view(1, heads, H, W, D).permute(0, 2, 3, 1, 4).contiguous()
+
+    o = R.c_oracle()
+    with warnings.catch_warnings(), torch.no_grad():
+        warnings.simplefilter("ignore")
+        bm = create_block_mask(mask_mod, 1, heads, H * W, H * W, device="cpu")
+        plain = flex_attention(q, k, v, block_mask=bm)
+        biased = flex_attention(q, k, v, score_mod=score_mod, block_mask=bm)
+    assert (nhwc(plain) - o.fused_fwd(nhwc(q), nhwc(k), nhwc(v), None, K, 1)).abs().max() < 1e-10
+    assert (nhwc(biased) - o.fused_fwd(nhwc(q), nhwc(k), nhwc(v), rpb, K, 1)).abs().max() < 1e-10
