@@ -9,7 +9,8 @@
  * algorithm statement and citations).  Built twice: *_f32 and *_f64.
  *
  * PARITY UNPINNED against natten (absent offline, un-pinned in the reference);
- * pinned by known-answer properties — see tests/test_oracle.py and DESIGN.md §3.
+ * pinned by known-answer properties and against PyTorch FlexAttention with the
+ * published NATTEN mask — see tests/test_oracle.py and DESIGN.md §3.
  */
 #include <math.h>
 #include <stdlib.h>

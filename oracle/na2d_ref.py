@@ -17,6 +17,9 @@ see DESIGN.md §3):
 3. the known-answer tests in ``tests/test_oracle.py`` (K == L ⇒ global attention
    with a Swin-style relative bias; interior pixels ⇒ ``F.unfold`` sliding window;
    dilation ⇒ independent sub-grids).
+4. an implementation that is not ours: PyTorch's FlexAttention with the neighbourhood mask
+   published for NATTEN in PyTorch's attention-gym examples reproduces the fused forward to
+   1e-10 in fp64 (``tests/test_oracle.py``).
 
 Call sites restated: /root/reference/core/modules.py:509 (construction, kernel 3,
 12 heads) and :517 (forward).
