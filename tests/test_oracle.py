@@ -222,3 +222,35 @@ def test_oracle_against_flex_attention_with_the_published_natten_mask(H, W, K, h
         biased = flex_attention(q, k, v, score_mod=score_mod, block_mask=bm)
     assert (nhwc(plain) - o.fused_fwd(nhwc(q), nhwc(k), nhwc(v), None, K, 1)).abs().max() < 1e-10
     assert (nhwc(biased) - o.fused_fwd(nhwc(q), nhwc(k), nhwc(v), rpb, K, 1)).abs().max() < 1e-10
+
+
+def test_two_formulations_agree_on_random_shapes():
+    """Hypothesis sweep over (H, W, K, dilation, heads, head dim): the C oracle (sub-sequence / clamp formulation) and
+    the closed-form gather tables must give the same logits and the same aggregation on every legal shape — the
+    parametrised cases above only sample the edge conditions by hand."""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    o = R.c_oracle()
+
+    @st.composite
+    def shapes(draw):
+        K = draw(st.sampled_from([3, 5, 7, 9]))
+        d = draw(st.integers(1, 3))
+        H = draw(st.integers(K * d, K * d + 9))
+        W = draw(st.integers(K * d, K * d + 9))
+        return H, W, K, d, draw(st.integers(1, 3)), draw(st.sampled_from([1, 2, 4]))
+
+    @settings(max_examples=40, deadline=None, derandomize=True)
+    @given(shapes())
+    def check(s):
+        H, W, K, d, heads, D = s
+        g = torch.Generator().manual_seed(H * 1000 + W * 10 + K + d)
+        q, k, v = (torch.randn(1, heads, H, W, D, generator=g, dtype=torch.float64) for _ in range(3))
+        rpb = torch.randn(heads, 2 * K - 1, 2 * K - 1, generator=g, dtype=torch.float64)
+        attn_c, attn_g = o.qk_fwd(q, k, rpb, K, d), R.na2d_qk_gather(q, k, rpb, K, d)
+        torch.testing.assert_close(attn_c, attn_g, rtol=1e-12, atol=1e-12)
+        p = attn_g.softmax(-1).contiguous()
+        torch.testing.assert_close(o.av_fwd(p, v, K, d), R.na2d_av_gather(p, v, K, d), rtol=1e-12, atol=1e-12)
+
+    check()
