@@ -25,15 +25,15 @@ struct BnGeom {
     int64_t per_chunk;     // elements of one channel handled by one CTA (multiple of the vector width)
 };
 
-template <int ACT> __device__ __forceinline__ float act_fwd(float x) {
+template <int ACT, typename T> __device__ __forceinline__ float act_fwd(float x) {
     if constexpr (ACT == LMNET_ACT_HARDSWISH) return x * fminf(fmaxf(x + 3.f, 0.f), 6.f) * (1.f / 6.f);
-    else if constexpr (ACT == LMNET_ACT_GELU) return gelu_fast(x);
+    else if constexpr (ACT == LMNET_ACT_GELU) return gelu_t<T>(x);
     else if constexpr (ACT == LMNET_ACT_RELU) return fmaxf(x, 0.f);
     else return x;
 }
-template <int ACT> __device__ __forceinline__ float act_bwd(float x) {
+template <int ACT, typename T> __device__ __forceinline__ float act_bwd(float x) {
     if constexpr (ACT == LMNET_ACT_HARDSWISH) return x < -3.f ? 0.f : (x <= 3.f ? (2.f * x + 3.f) * (1.f / 6.f) : 1.f);
-    else if constexpr (ACT == LMNET_ACT_GELU) return gelu_grad_fast(x);
+    else if constexpr (ACT == LMNET_ACT_GELU) return gelu_grad_t<T>(x);
     else if constexpr (ACT == LMNET_ACT_RELU) return x > 0.f ? 1.f : 0.f;
     else return 1.f;
 }
@@ -167,7 +167,7 @@ bnact_apply_kernel(const T* __restrict__ y, const float2* __restrict__ coef, T* 
 #pragma unroll
         for (int j = 0; j < Lane<T, VEC>::N; ++j) {
             const float pre = to_f(from_f<T>(fmaf(f[j], ab.x, ab.y)));
-            f[j] = act_fwd<ACT>(pre);
+            f[j] = act_fwd<ACT, T>(pre);
         }
         st_elems<T, VEC>(out + off, f, nv);
     });
@@ -192,7 +192,7 @@ bnact_bwd_reduce_kernel(const T* __restrict__ y, const T* __restrict__ dout, con
         for (int j = 0; j < Lane<T, VEC>::N; ++j) {
             const float yh = (f[j] - mean) * rstd;
             const float pre = to_f(from_f<T>(fmaf(yh, ga, be)));
-            const float dh = d[j] * act_bwd<ACT>(pre);
+            const float dh = d[j] * act_bwd<ACT, T>(pre);
             s += dh;
             sy = fmaf(dh, yh, sy);
         }
@@ -238,7 +238,7 @@ bnact_bwd_apply_kernel(const T* __restrict__ y, const T* __restrict__ dout, cons
         for (int j = 0; j < Lane<T, VEC>::N; ++j) {
             const float yh = (f[j] - mean) * rstd;
             const float pre = to_f(from_f<T>(fmaf(yh, ga, be)));
-            const float dh = d[j] * act_bwd<ACT>(pre);
+            const float dh = d[j] * act_bwd<ACT, T>(pre);
             f[j] = gr * (dh - m.x - yh * m.y);
         }
         st_elems<T, VEC>(dy + off, f, nv);

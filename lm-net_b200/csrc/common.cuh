@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "../../include/lmnet_b200.h"
 
 namespace lmnet {
@@ -47,6 +49,25 @@ struct LaunchScope {
         { lmnet::LaunchScope _scope((kid), (st), (double)(alg_bytes)); __VA_ARGS__; } \
         if (cudaGetLastError() != cudaSuccess) return LMNET_ERR_LAUNCH;  \
     } while (0)
+
+// Opt-in to > 48 KB of dynamic shared memory, once per kernel, device and size (the attribute is per device;
+// granted[dev] = largest size set so far).
+constexpr int kMaxDevices = 64;
+template <typename Kern> bool ensure_smem(Kern kern, size_t bytes, std::atomic<size_t>* granted_per_device) {
+    if (bytes > 227 * 1024) return false;
+    if (bytes <= 48 * 1024) return true;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return false;
+    std::atomic<size_t>& granted = granted_per_device[dev];
+    if (bytes <= granted.load(std::memory_order_relaxed)) return true;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return false;
+    }
+    size_t prev = granted.load(std::memory_order_relaxed);
+    while (prev < bytes && !granted.compare_exchange_weak(prev, bytes, std::memory_order_relaxed)) {}
+    return true;
+}
 
 // ---------------------------------------------------------------------------------------
 // element <-> float conversion
@@ -164,6 +185,19 @@ __device__ __forceinline__ float gelu_grad_fast(float u) {
     float e;                                   // = exp(-u*u/2)
     const float cdf = 0.5f * (1.f + erf_as(u * 0.70710678118654752f, e));
     return fmaf(u * 0.3989422804014327f, e, cdf);
+}
+
+// fp32 storage is the parity configuration (1e-4 relative, masks bit-identical): libdevice erff / expf there
+__device__ __forceinline__ float gelu_exact(float u) { return 0.5f * u * (1.f + erff(u * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_grad_exact(float u) {
+    const float cdf = 0.5f * (1.f + erff(u * 0.70710678118654752f));
+    return fmaf(u * 0.3989422804014327f, expf(-0.5f * u * u), cdf);
+}
+template <typename T> __device__ __forceinline__ float gelu_t(float u) {
+    if constexpr (sizeof(T) == 4) return gelu_exact(u); else return gelu_fast(u);
+}
+template <typename T> __device__ __forceinline__ float gelu_grad_t(float u) {
+    if constexpr (sizeof(T) == 4) return gelu_grad_exact(u); else return gelu_grad_fast(u);
 }
 
 __device__ __forceinline__ float fast_exp2(float x) {

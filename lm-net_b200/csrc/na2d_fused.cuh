@@ -475,6 +475,13 @@ static int launch(Op op, const FusedArgs& a) {
     const size_t rpb_bytes = (size_t)g.heads * R * R * sizeof(float);
     const unsigned z = (unsigned)(g.B * g.d * g.d);
     const double n_bytes = (double)g.B * g.H * g.W * g.heads * g.D * sizeof(T);  // one q-sized tensor
+    {   // rpb tables above 48 KB (e.g. 12 heads x kernel 13) need the per-device opt-in
+        static std::atomic<size_t> granted_f[kMaxDevices], granted_q[kMaxDevices], granted_k[kMaxDevices];
+        const bool ok = op == Op::Fwd    ? ensure_smem(na2d_fwd_kernel<T, KT, D, HG>, a.rpb ? rpb_bytes : 0, granted_f)
+                        : op == Op::BwdQ ? ensure_smem(na2d_bwd_query_kernel<T, KT, D, HG>, 2 * rpb_bytes, granted_q)
+                                         : ensure_smem(na2d_bwd_key_kernel<T, KT, D, HG>, a.rpb ? rpb_bytes : 0, granted_k);
+        if (!ok) return LMNET_ERR_UNSUPPORTED;
+    }
     if (op == Op::Fwd) {
         int64_t total = (int64_t)g.Hmax * g.Wmax * NG;
         dim3 grid((unsigned)((total + kThreads - 1) / kThreads), 1, z);

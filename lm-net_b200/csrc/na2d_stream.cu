@@ -81,25 +81,6 @@ bool make_plan(const NAGeom& g, bool bwd, int64_t max_parts, int ctas_per_sm, Pl
     return true;
 }
 
-// Opt-in to > 48 KB of dynamic shared memory, once per kernel, device and size (the attribute is per device;
-// granted[dev] = largest size set so far).
-constexpr int kMaxDevices = 64;
-template <typename Kern> bool ensure_smem(Kern kern, size_t bytes, std::atomic<size_t>* granted_per_device) {
-    if (bytes > 227 * 1024) return false;
-    if (bytes <= 48 * 1024) return true;
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return false;
-    std::atomic<size_t>& granted = granted_per_device[dev];
-    if (bytes <= granted.load(std::memory_order_relaxed)) return true;
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) {
-        (void)cudaGetLastError();
-        return false;
-    }
-    size_t prev = granted.load(std::memory_order_relaxed);
-    while (prev < bytes && !granted.compare_exchange_weak(prev, bytes, std::memory_order_relaxed)) {}
-    return true;
-}
-
 template <typename T, int KT, int D, int HG>
 int launch_fwd(const FusedArgs& a, const Plan& p) {
     const NAGeom& g = a.g;

@@ -219,12 +219,8 @@ static WgGeom wg_geom(const lmnet_wgrad_dims* d, int NT) {
 template <typename T, int MT, int NTW>
 static int wg_launch(const void* A, const void* B1, const void* B2, float* part, const WgGeom& g, cudaStream_t st) {
     const size_t smem = 2 * (size_t)(MT * 16 + g.NT * 8) * kWgPitch * sizeof(T);
-    static size_t attr_bytes = 0;
-    if (smem > 48 * 1024 && smem > attr_bytes) {
-        if (cudaFuncSetAttribute(wgrad_1x1_kernel<T, MT, NTW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-            return LMNET_ERR_LAUNCH;
-        attr_bytes = smem;
-    }
+    static std::atomic<size_t> granted[kMaxDevices];
+    if (!ensure_smem(wgrad_1x1_kernel<T, MT, NTW>, smem, granted)) return LMNET_ERR_LAUNCH;
     const double bytes = (double)g.B * (g.M + g.N1 + g.N2) * g.P * sizeof(T);
     dim3 grid(g.splits, g.B);
     LMNET_LAUNCH(KID_WGRAD_1X1, st, bytes, (wgrad_1x1_kernel<T, MT, NTW><<<grid, kWgThreads, smem, st>>>(

@@ -151,6 +151,13 @@ def check(rc: int, what: str) -> None:
 
 
 def dtype_code(t: torch.Tensor) -> int:
+    """dtype enum of the launch's main tensor.  Every launch passes through here, so this is also where the device
+    contract is enforced: the library launches on the CURRENT device's current stream, and a tensor that lives on a
+    different GPU would be touched from the wrong context (illegal address or unsynchronised execution)."""
+    if t.is_cuda and t.device.index != torch.cuda.current_device():
+        raise RuntimeError(
+            f"lmnet_b200: tensor on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()}; "
+            "call torch.cuda.set_device(...) or wrap the call in `with torch.cuda.device(tensor.device):`")
     try:
         return _DTYPES[t.dtype]
     except KeyError:

@@ -84,6 +84,13 @@ def bn_act(bn: torch.nn.BatchNorm2d, y: torch.Tensor, act: str = "none") -> torc
         if bn.momentum is None:
             raise NotImplementedError("cumulative-average BatchNorm (momentum=None) is not supported by the fused path")
         update = bn.training and tracked
+        if update:
+            for t in (bn.running_mean, bn.running_var):
+                if t.dtype != torch.float32 or not t.is_contiguous():
+                    raise NotImplementedError(f"fused BatchNorm update needs contiguous float32 running statistics, got "
+                                              f"{t.dtype} (keep BatchNorm buffers in fp32: autocast, not model.half())")
+            if bn.num_batches_tracked is not None and bn.num_batches_tracked.dtype != torch.int64:
+                raise NotImplementedError("num_batches_tracked must be int64")
         running = (bn.running_mean, bn.running_var, bn.num_batches_tracked) if update else (None, None, None)
         return _BNActTrain.apply(y, bn.weight, bn.bias, running, bn.eps, bn.momentum, code)
     if torch.is_grad_enabled() and (y.requires_grad or (bn.weight is not None and bn.weight.requires_grad)):

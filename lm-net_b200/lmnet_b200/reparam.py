@@ -137,6 +137,18 @@ def _check_branch_shapes(mod):
                 f"stride 1, no bias (got weight {tuple(c.weight.shape)}, stride {c.stride}, groups {c.groups})")
 
 
+def _check_running_buffers(bns):
+    """The finalize kernels update running_mean / running_var as fp32 and num_batches_tracked as int64 in place."""
+    for bn in bns:
+        for t in (bn.running_mean, bn.running_var):
+            if t.dtype != torch.float32 or not t.is_contiguous():
+                raise NotImplementedError(f"fused BatchNorm update needs contiguous float32 running statistics, got {t.dtype} "
+                                          "(keep BatchNorm buffers in fp32, e.g. use autocast instead of model.half())")
+        nbt = bn.num_batches_tracked
+        if nbt is not None and nbt.dtype != torch.int64:
+            raise NotImplementedError(f"num_batches_tracked must be int64, got {nbt.dtype}")
+
+
 def fused_dw_bn_gelu(mod, x1):
     """z, pool for the non-deploy ReparamConv `mod` (four conv+BN branches) applied to x1 [B,E,H,W]."""
     _check_branch_shapes(mod)
@@ -146,11 +158,18 @@ def fused_dw_bn_gelu(mod, x1):
     if any(bn.eps != eps for bn in bns):
         raise NotImplementedError("the four BatchNorms must share eps")
     tracked = all(bn.running_mean is not None for bn in bns)
-    if mod.training or not tracked:
+    # nn.BatchNorm2d decides batch vs running statistics from ITS OWN .training flag (frozen BNs inside a training
+    # block keep and use their running statistics); the fused kernel handles the four branches together
+    batch_mode = [bn.training or bn.running_mean is None for bn in bns]
+    if any(batch_mode) and not all(batch_mode):
+        raise NotImplementedError("fused ReparamConv: the four branch BatchNorms must all be in training mode or all in "
+                                  "eval mode (mixed frozen / live BatchNorms are not supported)")
+    if batch_mode[0]:
         momentum = bns[0].momentum
         if momentum is None or any(bn.momentum != momentum for bn in bns):
             raise NotImplementedError("cumulative-average BatchNorm (momentum=None) is not supported by the fused path")
-        update = mod.training and tracked
+        update = tracked and all(bn.training for bn in bns)
+        _check_running_buffers(bns if update else ())
         running = ([bn.running_mean for bn in bns] if update else None,
                    [bn.running_var for bn in bns] if update else None,
                    [bn.num_batches_tracked for bn in bns] if update else None)

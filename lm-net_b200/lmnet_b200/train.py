@@ -93,26 +93,38 @@ def train_step(model, optimizer, images, labels, criterion, criterion_dice, amp_
 
 
 class GraphedTrainStep:
-    """The whole training step (forward, loss, backward, AdamW) captured once into a CUDA graph and replayed.
+    """The whole training step (forward, loss, backward, gradient all-reduce, AdamW) captured once into a CUDA
+    graph and replayed.
 
-    One LM-Net step is ~2 500 kernel launches; enqueueing them from Python costs ~40 ms of host time, which
+    One LM-Net step is ~2 000 kernel launches; enqueueing them from Python costs ~40 ms of host time, which
     caps the step no matter how fast the kernels are (tools/cpu_bound_probe.py).  Replaying a captured graph
     removes that cost: inputs are copied into static device buffers, `replay()` re-issues every kernel
-    (ours through the C ABI, cuDNN/cuBLAS) with the recorded arguments.
+    (ours through the C ABI, cuDNN/cuBLAS, NCCL) with the recorded arguments.
     Requirements met by this code base: no host synchronisation inside the step, static shapes, the library
     takes the *current* (capturing) stream, the optimiser is built with capturable=True.
 
-    Data parallel (torch.distributed initialised, world > 1): the graph holds forward + backward of the LOCAL
-    model only; all gradients live in one flat buffer that is averaged with a single NCCL all-reduce after the
-    replay (15.9 MB over NVLink), followed by the optimiser step.  No collective is captured, so nothing can
-    dead-lock inside a capture; parameters are broadcast from rank 0 once at construction (what DDP does).
-    BatchNorm statistics stay per process, as in the reference.
+    Data parallel (torch.distributed initialised, world > 1; mirrors what utils/distributed_utils.py:7-28 sets up):
+    every .grad is a view into ONE flat buffer; it is averaged by a single NCCL all-reduce (15.9 MB over NVLink)
+    that is captured INSIDE the graph together with the optimiser step, so a replay is the complete data-parallel
+    step and nothing is launched eagerly afterwards.  If the collective cannot be captured on this build
+    (`capture_collective=False`, or the capture raises) the graph holds forward + backward only and the
+    all-reduce + optimiser step follow the replay eagerly.  Parameters and buffers are broadcast from rank 0 once
+    at construction (what DDP does); BatchNorm statistics stay per process, as in the reference.
+
+    Construction has no side effects on the training trajectory: the warm-up iterations that CUDA-graph capture
+    needs run on a snapshot — parameters, buffers (BatchNorm running statistics, num_batches_tracked) and the
+    optimiser state are restored before the capture.
 
     Usage: step = GraphedTrainStep(...); loss, output = step(images, labels)  # tensors are static buffers.
-    Falls back to eager execution if capture is not possible (the reason is kept in `.fallback_reason`)."""
+    A batch whose shape differs from the example batch (a short last batch) runs eagerly.  If capture is not
+    possible the step runs eagerly and says so: a RuntimeWarning carries the reason (also kept in
+    `.fallback_reason`); with LMNET_REQUIRE_GRAPH=1 in the environment the constructor raises instead."""
 
     def __init__(self, model, optimizer, criterion, criterion_dice, example_images, example_labels,
-                 amp_dtype=torch.bfloat16, warmup=3):
+                 amp_dtype=torch.bfloat16, warmup=3, capture_collective=True):
+        import os
+        import warnings
+
         import torch.distributed as dist
 
         self.model, self.optimizer = model, optimizer
@@ -124,6 +136,7 @@ class GraphedTrainStep:
         self.images.copy_(example_images)
         self.labels.copy_(example_labels)
         self.flat = None
+        self.collective_in_graph = False
         if self.world > 1:
             if isinstance(model, torch.nn.parallel.DistributedDataParallel):
                 raise ValueError("pass the un-wrapped module: GraphedTrainStep does its own gradient all-reduce")
@@ -139,18 +152,27 @@ class GraphedTrainStep:
         if self.images.device.type != "cuda":
             self.fallback_reason = "not a CUDA device: eager execution"
             return
-        try:
-            self._capture(warmup)
-        except Exception as e:  # noqa: BLE001 - any capture failure means: run eagerly
-            self.graph = None
-            self.fallback_reason = f"{type(e).__name__}: {e}"
-            torch.cuda.synchronize()
+        attempts = [True, False] if (self.world > 1 and capture_collective) else [False]
+        for with_collective in attempts:
+            try:
+                self._capture(warmup, with_collective)
+                self.fallback_reason = None
+                break
+            except Exception as e:  # noqa: BLE001 - any capture failure means: next variant, then eager
+                self.graph = None
+                self.fallback_reason = f"{type(e).__name__}: {e}"
+                torch.cuda.synchronize()
+        if self.graph is None:
+            msg = f"GraphedTrainStep: CUDA-graph capture failed, the step runs EAGERLY (~2x slower): {self.fallback_reason}"
+            if os.environ.get("LMNET_REQUIRE_GRAPH") == "1":
+                raise RuntimeError(msg)
+            warnings.warn(msg, RuntimeWarning, stacklevel=2)
 
     # -- pieces -------------------------------------------------------------------------------------
-    def _forward_backward(self):
-        with torch.autocast(self.images.device.type, dtype=self.amp_dtype, enabled=self.amp_dtype is not None):
-            output = self.model(self.images)
-            loss = loss_fn(output, self.labels, self.criterion, self.criterion_dice)
+    def _forward_backward(self, images, labels):
+        with torch.autocast(images.device.type, dtype=self.amp_dtype, enabled=self.amp_dtype is not None):
+            output = self.model(images)
+            loss = loss_fn(output, labels, self.criterion, self.criterion_dice)
         if self.flat is not None:
             self.flat.zero_()                      # grads accumulate in place into the flat views
         else:
@@ -158,7 +180,7 @@ class GraphedTrainStep:
         loss.backward()
         return loss, output
 
-    def _reduce_and_step(self):
+    def _reduce(self):
         import torch.distributed as dist
 
         if dist.get_backend() == "nccl":
@@ -166,46 +188,79 @@ class GraphedTrainStep:
         else:                                      # gloo (CPU tests) has no AVG
             dist.all_reduce(self.flat)
             self.flat /= self.world
-        self.optimizer.step()
 
-    def _eager(self):
-        loss, output = self._forward_backward()
+    def _eager(self, images, labels):
+        loss, output = self._forward_backward(images, labels)
         if self.flat is not None:
-            self._reduce_and_step()
-        else:
-            self.optimizer.step()
+            self._reduce()
+        self.optimizer.step()
         return loss, output
 
-    def _capture(self, warmup):
+    def _snapshot(self):
+        import copy
+
+        model_state = {k: v.detach().clone() for k, v in self.model.state_dict().items()}
+        return model_state, copy.deepcopy(self.optimizer.state_dict())
+
+    def _restore(self, snap):
+        model_state, opt_state = snap
+        with torch.no_grad():
+            for k, v in self.model.state_dict().items():
+                v.copy_(model_state[k])
+            if opt_state["state"]:
+                self.optimizer.load_state_dict(opt_state)
+            else:
+                # a fresh optimiser: its state was created by the warm-up.  Adam's initial state is all zeros, so
+                # zeroing in place (same tensors the capture will record) is exactly "never stepped".
+                for st in self.optimizer.state.values():
+                    for t in st.values():
+                        if torch.is_tensor(t):
+                            t.zero_()
+
+    def _capture(self, warmup, with_collective):
         from . import _lib
 
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for _ in range(warmup):
-                self._eager()
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
+        snap = self._snapshot()
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(warmup):
+                    self._eager(self.images, self.labels)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+        finally:
+            self._restore(snap)
         graph = torch.cuda.CUDAGraph()
         if self.flat is None:
             self.optimizer.zero_grad(set_to_none=True)
         before = _lib.launch_count()
         with torch.cuda.graph(graph):
-            self.loss, self.output = self._forward_backward()
+            self.loss, self.output = self._forward_backward(self.images, self.labels)
             if self.flat is None:
+                self.optimizer.step()
+            elif with_collective:
+                self._reduce()
                 self.optimizer.step()
         self.library_launches_per_step = _lib.launch_count() - before    # lmnet_b200 kernels inside one replay
         self.graph = graph
+        self.collective_in_graph = bool(with_collective and self.flat is not None)
+        self._restore(snap)            # capture does not execute, but the optimiser may touch host-side counters
 
     def __call__(self, images, labels):
+        if images.shape != self.images.shape or labels.shape != self.labels.shape:
+            # e.g. a short last batch: the captured graph has static shapes, run this one eagerly
+            self.loss, self.output = self._eager(images.to(self.images.device), labels.to(self.labels.device))
+            return self.loss, self.output
         self.images.copy_(images, non_blocking=True)
         self.labels.copy_(labels, non_blocking=True)
         if self.graph is None:
-            self.loss, self.output = self._eager()
+            self.loss, self.output = self._eager(self.images, self.labels)
         else:
             self.graph.replay()
-            if self.flat is not None:
-                self._reduce_and_step()
+            if self.flat is not None and not self.collective_in_graph:
+                self._reduce()
+                self.optimizer.step()
         return self.loss, self.output
 
 
@@ -297,12 +352,17 @@ def train_one_epoch(model, optimizer, metric_collection=None, num_classes=2, dat
     the confusion matrix is accumulated on the GPU instead of shipping the [B,H,W] int64 mask to the CPU
     every step (`metrics_on_device`; set False for the reference's exact D2H behaviour).  `defer_loss_read` reads
     each step's loss one step late (same values, same total)."""
+    dev = torch.device(device if not isinstance(device, int) else f"cuda:{device}")
+    if dev.type == "cuda" and (dev.index if dev.index is not None else torch.cuda.current_device()) != torch.cuda.current_device():
+        # the C-ABI launches go to the CURRENT device's stream: make the loop's device current for its duration
+        with torch.cuda.device(dev):
+            return train_one_epoch(model, optimizer, metric_collection, num_classes, data_loader, dev, criterion, scaler,
+                                   criterion_dice, amp_dtype, metrics_on_device, prefetch, defer_loss_read, step_fn)
     model.train()
     if metric_collection is not None:
         metric_collection.reset()
     total_loss = 0.0
     use_amp = scaler is not None
-    dev = torch.device(device if not isinstance(device, int) else f"cuda:{device}")
     batches = _Prefetcher(data_loader, dev) if prefetch else (
         (i.to(dev, non_blocking=True), l.to(dev, non_blocking=True)) for i, l in data_loader)
     # loss.item() every step, as in the reference — but read one step late through pinned memory, so the

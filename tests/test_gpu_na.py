@@ -176,7 +176,43 @@ def test_module_vs_oracle_module(dtype):
 
 
 # ---------------------------------------------------------------------------------------------
-# size-independent properties at the BASELINE sizes (oracle would take too long there)
+# the real BASELINE stage shapes (352x352 config) against the C oracle: B = 1 (B = 2 at the two small stages),
+# kernel 3 (what LM-Net runs) and BASELINE's microbench kernel 7 with dilation 1 and 2, fwd + bwd + drpb.
+# The C oracle needs < 1 s per case at these sizes.
+# ---------------------------------------------------------------------------------------------
+STAGE_SHAPES = [(1, 352, 1), (1, 176, 2), (2, 88, 4), (2, 44, 8)]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("K,d", [(3, 1), (7, 1), (7, 2)])
+@pytest.mark.parametrize("B,R,D", STAGE_SHAPES, ids=lambda v: str(v))
+def test_stage_shapes_vs_oracle(B, R, D, K, d, dtype):
+    from natten.functional import na2d
+    from oracle.na2d_ref import c_oracle
+
+    heads = 12
+    q, k, v, go = (_mk((B, R, R, heads, D), dtype, s) for s in (11, 12, 13, 14))
+    rpb = 0.3 * _mk((heads, 2 * K - 1, 2 * K - 1), torch.float32, 15)
+    o = c_oracle()
+    q64, k64, v64, go64 = (t.double() for t in (q, k, v, go))
+    ref = o.fused_fwd(q64, k64, v64, rpb.double(), K, d)
+    rdq, rdk, rdv, rdrpb = o.fused_bwd(q64, k64, v64, rpb.double(), go64, K, d)
+    qc, kc, vc = (t.cuda().requires_grad_() for t in (q, k, v))
+    rc = rpb.cuda().requires_grad_()
+    out = na2d(qc, kc, vc, K, d, rel_pos_bias=rc)
+    out.backward(go.cuda())
+    tol = TOL[dtype]
+    assert rel_err(out.cpu(), ref) < tol
+    assert rel_err(qc.grad.cpu(), rdq) < tol
+    assert rel_err(kc.grad.cpu(), rdk) < tol
+    assert rel_err(vc.grad.cpu(), rdv) < tol
+    # drpb sums B*R*R*9..49 products per bin: rounding noise of 16-bit dS grows like sqrt(N) against a sum that can
+    # cancel; the bound is relative to the largest bin as everywhere else
+    assert rel_err(rc.grad.cpu(), rdrpb) < tol
+
+
+# ---------------------------------------------------------------------------------------------
+# size-independent properties at the full BASELINE batch (B = 16)
 # ---------------------------------------------------------------------------------------------
 STAGES = [(16, 352, 1), (16, 176, 2), (16, 88, 4), (16, 44, 8)]
 

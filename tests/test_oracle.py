@@ -254,3 +254,86 @@ def test_two_formulations_agree_on_random_shapes():
         torch.testing.assert_close(o.av_fwd(p, v, K, d), R.na2d_av_gather(p, v, K, d), rtol=1e-12, atol=1e-12)
 
     check()
+
+
+def _dense_neighbourhood_mask_and_bias_index(H, W, K, d):
+    """Independent dense statement of (dilated) neighbourhood attention, written without any of the oracle's index
+    helpers: query (qy, qx) attends key (ky, kx) iff, per axis, both lie in the same residue class mod d and — in the
+    coordinates of that sub-sequence (index // d, length ceil((L - r) / d)) — the key is within K//2 of the window
+    centre clamp(query, K//2, Lsub-1-K//2) (the attention-gym NATTEN mask applied to each of the d sub-sequences, which
+    is DiNAT's definition of dilation).  Returns mask [HW, HW] (bool) and the two bias index maps [HW, HW]."""
+    def axis(L):
+        i = torch.arange(L)
+        r, s = i % d, i // d
+        lsub = (L - r + d - 1) // d                                       # length of the query's sub-sequence
+        centre = torch.minimum(torch.maximum(s, torch.full_like(s, K // 2)), lsub - 1 - K // 2)
+        same = r[:, None] == r[None, :]
+        near = (centre[:, None] - s[None, :]).abs() <= K // 2
+        rel = (s[None, :] - s[:, None]) + K - 1                           # (key - query) / d + K - 1
+        return same & near, rel.clamp(0, 2 * K - 2)
+    my, ry = axis(H)
+    mx, rx = axis(W)
+    mask = (my[:, None, :, None] & mx[None, :, None, :]).reshape(H * W, H * W)
+    by = ry[:, None, :, None].expand(H, W, H, W).reshape(H * W, H * W)
+    bx = rx[None, :, None, :].expand(H, W, H, W).reshape(H * W, H * W)
+    return mask, by, bx
+
+
+@pytest.mark.parametrize("H,W,K,d,heads,D", [(9, 11, 3, 1, 2, 4), (13, 12, 3, 2, 3, 2), (11, 14, 3, 3, 2, 1),
+                                             (15, 17, 7, 2, 2, 2), (21, 22, 7, 3, 1, 4), (12, 10, 5, 2, 12, 1)])
+def test_oracle_forward_and_backward_against_dense_masked_sdpa_autograd(H, W, K, d, heads, D):
+    """Pins dilation (d = 2, 3) and EVERY backward output (dq, dk, dv, drpb) of the C oracle against torch's own
+    autograd through a dense masked softmax attention (fp64): F.scaled_dot_product_attention (math backend on CPU) for
+    the forward, and the same attention written with explicit matmul / softmax for the gradients."""
+    g = torch.Generator().manual_seed(H * 131 + W * 7 + K + d)
+    q, k, v, go = (torch.randn(1, heads, H * W, D, generator=g, dtype=torch.float64) for _ in range(4))
+    rpb = 0.5 * torch.randn(heads, 2 * K - 1, 2 * K - 1, generator=g, dtype=torch.float64)
+    mask, by, bx = _dense_neighbourhood_mask_and_bias_index(H, W, K, d)
+    assert int(mask.sum(1).min()) == K * K and int(mask.sum(1).max()) == K * K     # every query sees exactly K*K keys
+
+    def nhwc(t):
+        return t.view(1, heads, H, W, D).permute(0, 2, 3, 1, 4).contiguous()
+
+    qr, kr, vr, rr = (t.clone().requires_grad_() for t in (q, k, v, rpb))
+    bias = rr[:, by, bx].masked_fill(~mask, float("-inf"))                    # [heads, HW, HW]
+    scale = D ** -0.5
+    attn = ((qr * scale) @ kr.transpose(-2, -1) + bias[None]).softmax(-1)
+    out = attn @ vr
+    out.backward(go)
+    with torch.no_grad():
+        sdpa = torch.nn.functional.scaled_dot_product_attention(q, k, v, attn_mask=bias.detach()[None], scale=scale)
+    assert (sdpa - out.detach()).abs().max() < 1e-12
+
+    o = R.c_oracle()
+    ref = o.fused_fwd(nhwc(q), nhwc(k), nhwc(v), rpb, K, d)
+    assert (nhwc(out.detach()) - ref).abs().max() < 1e-11
+    dq, dk, dv, drpb = o.fused_bwd(nhwc(q), nhwc(k), nhwc(v), rpb, nhwc(go), K, d)
+    assert (nhwc(qr.grad) - dq).abs().max() < 1e-10
+    assert (nhwc(kr.grad) - dk).abs().max() < 1e-10
+    assert (nhwc(vr.grad) - dv).abs().max() < 1e-10
+    assert (rr.grad - drpb).abs().max() < 1e-9
+
+
+@pytest.mark.parametrize("H,W,K,d", [(13, 12, 3, 2), (15, 16, 5, 3), (21, 15, 7, 2)])
+def test_oracle_against_flex_attention_with_dilation(H, W, K, d):
+    """FlexAttention (PyTorch's own implementation) with the dense dilated mask above as mask_mod: third independent
+    implementation agreeing on dilation > 1 (forward; FlexAttention has no CPU backward)."""
+    import warnings
+
+    from torch.nn.attention.flex_attention import create_block_mask, flex_attention
+
+    heads, D = 2, 4
+    mask, by, bx = _dense_neighbourhood_mask_and_bias_index(H, W, K, d)
+    g = torch.Generator().manual_seed(H + W + K + d)
+    q, k, v = (torch.randn(1, heads, H * W, D, generator=g, dtype=torch.float64) for _ in range(3))
+    rpb = 0.5 * torch.randn(heads, 2 * K - 1, 2 * K - 1, generator=g, dtype=torch.float64)
+
+    def nhwc(t):
+        return t.view(1, heads, H, W, D).permute(0, 2, 3, 1, 4).contiguous()
+
+    with warnings.catch_warnings(), torch.no_grad():
+        warnings.simplefilter("ignore")
+        bm = create_block_mask(lambda b, h, qi, ki: mask[qi, ki], 1, heads, H * W, H * W, device="cpu")
+        got = flex_attention(q, k, v, score_mod=lambda s, b, h, qi, ki: s + rpb[h, by[qi, ki], bx[qi, ki]], block_mask=bm)
+    ref = R.c_oracle().fused_fwd(nhwc(q), nhwc(k), nhwc(v), rpb, K, d)
+    assert (nhwc(got) - ref).abs().max() < 1e-10
