@@ -227,6 +227,14 @@ typedef struct lmnet_upsample_dims {
 } lmnet_upsample_dims;
 int lmnet_upsample2x_fwd(const void* x, void* y, const lmnet_upsample_dims* dims, int dtype, void* stream);
 int lmnet_upsample2x_bwd(const void* dy, void* dx, const lmnet_upsample_dims* dims, int dtype, void* stream);
+/* channels-last variant: x [B, H, W, C] -> y [B, 2H, 2W, C] (the layout cuDNN's 16-bit convolutions on either side
+ * of these call sites compute in, so the tensor never changes layout). */
+typedef struct lmnet_upsample_cl_dims {
+    int64_t B;
+    int32_t H, W, C;
+} lmnet_upsample_cl_dims;
+int lmnet_upsample2x_cl_fwd(const void* x, void* y, const lmnet_upsample_cl_dims* dims, int dtype, void* stream);
+int lmnet_upsample2x_cl_bwd(const void* dy, void* dx, const lmnet_upsample_cl_dims* dims, int dtype, void* stream);
 
 #ifdef __cplusplus
 }

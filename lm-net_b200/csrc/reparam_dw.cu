@@ -21,6 +21,8 @@
 // every (col, col+1) pair is an aligned 64-bit shared load.  A CTA owns one channel, one column
 // stripe and one band of rows, and loops over the batch, so per-channel reductions need no atomics:
 // per-CTA partials are reduced by the finalize kernels in a fixed order (deterministic).
+#include <algorithm>
+#include <initializer_list>
 #include <cstdlib>
 #include <type_traits>
 
@@ -805,14 +807,15 @@ __global__ void dw_fin_dw_kernel(const float* __restrict__ part, int ncta, const
     else if (t < 34) { k = 1; idx = t - 25; lag = (idx / 3 + 1) * 5 + idx % 3 + 1; }
     else if (t < 37) { k = 2; idx = t - 34; lag = (idx + 1) * 5 + 2; }
     else { k = 3; idx = t - 37; lag = 2 * 5 + idx + 1; }
-    const double c1 = cb[e * 12 + k * 3];
-    const float val = (float)(c1 * (double)Pfin[e * 26 + lag] - r);
+    // Pfin == nullptr: the partials already are dw (the TMA dx kernel correlates dy_br with x directly)
+    const float val = Pfin == nullptr ? (float)r : (float)((double)cb[e * 12 + k * 3] * (double)Pfin[e * 26 + lag] - r);
     const int per = k == 0 ? 25 : k == 1 ? 9 : 3;
     if (gr.dw[k] != nullptr) gr.dw[k][e * per + idx] = val;
 }
 
 }  // namespace lmnet
 #include "reparam_dw_mma.cuh"
+#include "reparam_dw_tma.cuh"
 namespace lmnet {
 
 // =================================================================================================
@@ -827,12 +830,13 @@ static int dw_validate(const lmnet_dw_dims* d) {
 }
 
 // CTA grid for a kernel with tile (th x tw): enough CTAs for ~4 waves of 148 SMs, bands aligned to th
-static DwGeom dw_geom(const lmnet_dw_dims* d, int th, int tw) {
+static DwGeom dw_geom(const lmnet_dw_dims* d, int th, int tw, int ctas_per_sm = 4, int shift = 0) {
     DwGeom g;
     g.B = d->B; g.E = d->E; g.H = d->H; g.W = d->W;
-    g.stripes = (d->W + tw - 1) / tw;
+    g.stripes = (d->W + shift + tw - 1) / tw;          // TMA kernels: stripe s starts at s*tw - shift
     const int row_tiles = (d->H + th - 1) / th;
-    static const int kCtaTarget = getenv("LMNET_DW_CTAS") ? atoi(getenv("LMNET_DW_CTAS")) : 4 * 148;
+    static const int kCtaOverride = getenv("LMNET_DW_CTAS") ? atoi(getenv("LMNET_DW_CTAS")) : 0;
+    const int kCtaTarget = kCtaOverride > 0 ? kCtaOverride : ctas_per_sm * 148;     // one wave of resident CTAs
     int bands = (kCtaTarget + g.E * g.stripes - 1) / (g.E * g.stripes);
     bands = bands < 1 ? 1 : bands > row_tiles ? row_tiles : bands;
     const int tiles_per_band = (row_tiles + bands - 1) / bands;
@@ -844,14 +848,18 @@ static DwGeom dw_geom(const lmnet_dw_dims* d, int th, int tw) {
 struct DwWs {
     size_t part, coef, pool_part, pfin, cb, du, total;
 };
+// CTAs per SM the TMA kernels are built for (__launch_bounds__ / shared memory): their grids are ONE wave
+constexpr int kStatsOcc = 4, kApplyOcc = 4, kReduceOcc = 3, kDxOcc = 2;
 static DwWs dw_ws_layout(const lmnet_dw_dims* d, size_t esize) {
-    DwGeom gf = dw_geom(d, kFwdTH, kFwdTW);
-    const size_t ncta = (size_t)gf.stripes * gf.bands;
+    size_t ncta = 0;
+    const DwGeom gs[5] = {dw_geom(d, kFwdTH, kFwdTW), dw_geom(d, kMmaTH, kMmaTW, kStatsOcc, kFwdShift), dw_geom(d, kMmaTH, kMmaTW, kReduceOcc, kFwdShift),
+                          dw_geom(d, kDxTH, kDxTW), dw_geom(d, kDxTH, kDxTW, kDxOcc, kDxShift)};
+    for (const DwGeom& gg : gs) ncta = std::max(ncta, (size_t)gg.stripes * gg.bands);
     DwWs w;
     size_t off = 0;
     w.part = off; off = dw_align(off + (size_t)d->E * ncta * 40 * sizeof(float));
     w.coef = off; off = dw_align(off + (size_t)d->E * 26 * sizeof(float));
-    w.pool_part = off; off = dw_align(off + (size_t)d->B * d->E * ncta * sizeof(float));
+    w.pool_part = off; off = dw_align(off + (size_t)d->B * d->E * ncta * kDwWarps * sizeof(float));
     w.pfin = off; off = dw_align(off + (size_t)d->E * 26 * sizeof(float));
     w.cb = off; off = dw_align(off + (size_t)d->E * 12 * sizeof(float));
     w.du = off; off = dw_align(off + (size_t)d->B * d->E * d->H * d->W * esize);
@@ -874,6 +882,17 @@ static bool dw_mma_ok(const lmnet_dw_dims* d, const void* x) {
     if (sizeof(T) != 2 || getenv("LMNET_DW_NO_MMA") != nullptr) return false;
     return (d->W % 2 == 0) && ((uintptr_t)x % 4 == 0);
 }
+// the TMA pipeline kernels additionally need 16-byte global strides (W % 8 == 0) and 16-byte aligned tensors
+template <typename T>
+static bool dw_tma_ok(const lmnet_dw_dims* d, std::initializer_list<const void*> ptrs) {
+    if (sizeof(T) != 2 || getenv("LMNET_DW_NO_MMA") != nullptr || getenv("LMNET_DW_NO_TMA") != nullptr) return false;
+    for (const void* q : ptrs)
+        if (!tma_planes_ok(q, (int64_t)d->B * d->E, d->H, d->W, sizeof(T))) return false;
+    return true;
+}
+template <typename Kern>
+static bool dw_tma_smem(Kern kern, size_t bytes, std::atomic<size_t>* granted) { return ensure_smem(kern, bytes, granted); }
+
 template <typename T, typename F>
 static int with_vec(int vec_bytes, F&& f) {
     // the loaders move 4, 2 or 1 elements per lane (one float4 / float2 / float shared store each)
@@ -901,6 +920,26 @@ static int dw_train_fwd(const void* x, const lmnet_dw_params* p, void* u, void* 
     const bool use_mma = dw_mma_ok<T>(d, x);
     int rc = LMNET_OK;
     if constexpr (sizeof(T) == 2) {
+        if (dw_tma_ok<T>(d, {x})) {
+            CUtensorMap tm_x;
+            if (!tma_make_planes_map(&tm_x, x, (int64_t)d->B * d->E, d->H, d->W, kMmaTileRows, kMmaPitch)) return LMNET_ERR_LAUNCH;
+            static std::atomic<size_t> granted_s[kMaxDevices], granted_a[kMaxDevices];
+            if (!dw_tma_smem(dw_stats_tma_kernel<T>, kStatsSmem, granted_s) || !dw_tma_smem(dw_apply_tma_kernel<T>, kApplySmem, granted_a))
+                return LMNET_ERR_LAUNCH;
+            const DwGeom gs = dw_geom(d, kMmaTH, kMmaTW, kStatsOcc, kFwdShift);
+            const int ncta_s = gs.stripes * gs.bands;
+            const dim3 grid_s(gs.stripes, gs.bands, gs.E);
+            LMNET_LAUNCH(KID_DW_STATS, st, 1 * t_bytes, (dw_stats_tma_kernel<T><<<grid_s, kTmaThreads, kStatsSmem, st>>>(tm_x, *p, part, gs)));
+            LMNET_LAUNCH(KID_DW_FIN_FWD, st, 0, (dw_fin_fwd_kernel<<<g.E, 32, 0, st>>>(part, ncta_s, *p, save_mean, save_rstd, coef, eps, momentum,
+                                                             nbt ? nbt[0] : nullptr, nbt ? nbt[1] : nullptr,
+                                                             nbt ? nbt[2] : nullptr, nbt ? nbt[3] : nullptr, g)));
+            LMNET_LAUNCH(KID_DW_APPLY, st, 2 * t_bytes, (dw_apply_tma_kernel<T><<<grid_s, kTmaThreads, kApplySmem, st>>>(tm_x, coef, (T*)u, (T*)z, pool ? pool_part : nullptr, gs)));
+            if (pool) {
+                const int n = g.B * g.E;
+                LMNET_LAUNCH(KID_DW_POOL_FIN, st, 0, (dw_pool_fin_kernel<<<(n + 127) / 128, 128, 0, st>>>(pool_part, ncta_s * kDwWarps, 1.f / ((float)g.H * g.W), pool, n)));
+            }
+            return LMNET_OK;
+        }
         if (use_mma) LMNET_LAUNCH(KID_DW_STATS, st, 1 * t_bytes, (dw_stats_mma_kernel<T><<<grid, kDwThreads, 0, st>>>((const T*)x, *p, part, g)));
     }
     if (!use_mma) rc = with_vec<T>(vb, [&](auto v) -> int {
@@ -945,6 +984,21 @@ static int dw_eval_fwd(const void* x, const lmnet_dw_params* p, const float* bia
     const bool use_mma = dw_mma_ok<T>(d, x);
     int rc = LMNET_OK;
     if constexpr (sizeof(T) == 2) {
+        if (dw_tma_ok<T>(d, {x})) {
+            CUtensorMap tm_x;
+            if (!tma_make_planes_map(&tm_x, x, (int64_t)d->B * d->E, d->H, d->W, kMmaTileRows, kMmaPitch)) return LMNET_ERR_LAUNCH;
+            static std::atomic<size_t> granted_a[kMaxDevices];
+            if (!dw_tma_smem(dw_apply_tma_kernel<T>, kApplySmem, granted_a)) return LMNET_ERR_LAUNCH;
+            const DwGeom gs = dw_geom(d, kMmaTH, kMmaTW, kApplyOcc, kFwdShift);
+            const int ncta_s = gs.stripes * gs.bands;
+            const dim3 grid_s(gs.stripes, gs.bands, gs.E);
+            LMNET_LAUNCH(KID_DW_APPLY, st, 2 * t_bytes, (dw_apply_tma_kernel<T><<<grid_s, kTmaThreads, kApplySmem, st>>>(tm_x, coef, (T*)nullptr, (T*)z, pool ? pool_part : nullptr, gs)));
+            if (pool) {
+                const int n = g.B * g.E;
+                LMNET_LAUNCH(KID_DW_POOL_FIN, st, 0, (dw_pool_fin_kernel<<<(n + 127) / 128, 128, 0, st>>>(pool_part, ncta_s * kDwWarps, 1.f / ((float)g.H * g.W), pool, n)));
+            }
+            return LMNET_OK;
+        }
         if (use_mma) LMNET_LAUNCH(KID_DW_APPLY, st, 2 * t_bytes, (dw_apply_mma_kernel<T><<<grid, kDwThreads, 0, st>>>((const T*)x, coef, (T*)nullptr, (T*)z, pool ? pool_part : nullptr, g)));
     }
     if (!use_mma) rc = with_vec<T>(vb, [&](auto v) -> int {
@@ -981,6 +1035,27 @@ static int dw_train_bwd(const void* x, const void* u, const void* dz, const floa
     const bool use_mma = dw_mma_ok<T>(d, x) && ((uintptr_t)u % 4 == 0) && ((uintptr_t)dz % 4 == 0);
     int rc = LMNET_OK;
     if constexpr (sizeof(T) == 2) {
+        if (dw_tma_ok<T>(d, {x, u, dz, (const void*)du, (const void*)dx})) {
+            const int64_t planes = (int64_t)d->B * d->E;
+            CUtensorMap tm_x, tm_u, tm_dz, tm_du;
+            if (!tma_make_planes_map(&tm_x, x, planes, d->H, d->W, kMmaTileRows, kMmaPitch) ||
+                !tma_make_planes_map(&tm_u, u, planes, d->H, d->W, kMmaTH, kMmaPitch) ||
+                !tma_make_planes_map(&tm_dz, dz, planes, d->H, d->W, kMmaTH, kMmaPitch) ||
+                !tma_make_planes_map(&tm_du, du, planes, d->H, d->W, kMmaTH, kMmaPitch))
+                return LMNET_ERR_LAUNCH;
+            static std::atomic<size_t> granted_r[kMaxDevices], granted_x[kMaxDevices];
+            if (!dw_tma_smem(dw_bwd_reduce_tma_kernel<T>, kReduceSmem, granted_r) || !dw_tma_smem(dw_bwd_dx_tma_kernel<T>, kDxTmaSmem, granted_x))
+                return LMNET_ERR_LAUNCH;
+            const DwGeom gr_ = dw_geom(d, kMmaTH, kMmaTW, kReduceOcc, kFwdShift);
+            const dim3 grid_r(gr_.stripes, gr_.bands, gr_.E);
+            LMNET_LAUNCH(KID_DW_BWD_REDUCE, st, 2 * t_bytes, (dw_bwd_reduce_tma_kernel<T><<<grid_r, kTmaThreads, kReduceSmem, st>>>(tm_x, tm_u, tm_dz, dpool, du, part, gr_)));
+            LMNET_LAUNCH(KID_DW_FIN_BWD, st, 0, (dw_fin_bwd_kernel<<<g.E, 32, 0, st>>>(part, gr_.stripes * gr_.bands, *p, save_mean, save_rstd, *gr, pfin, cb, g)));
+            const DwGeom gx = dw_geom(d, kDxTH, kDxTW, kDxOcc, kDxShift);
+            const dim3 grid_x(gx.stripes, gx.bands, gx.E);
+            LMNET_LAUNCH(KID_DW_BWD_DX, st, 3 * t_bytes, (dw_bwd_dx_tma_kernel<T><<<grid_x, kTmaThreads, kDxTmaSmem, st>>>(tm_x, tm_du, *p, cb, (T*)dx, part, gx)));
+            LMNET_LAUNCH(KID_DW_FIN_DW, st, 0, (dw_fin_dw_kernel<<<g.E, 64, 0, st>>>(part, gx.stripes * gx.bands, nullptr, cb, *gr, g.E)));
+            return LMNET_OK;
+        }
         if (use_mma) LMNET_LAUNCH(KID_DW_BWD_REDUCE, st, 2 * t_bytes, (dw_bwd_reduce_mma_kernel<T><<<grid, kDwThreads, 0, st>>>((const T*)x, (const T*)u, (const T*)dz, dpool, du, part, g)));
     }
     if (!use_mma) rc = with_vec<T>(vb, [&](auto v) -> int {

@@ -1,0 +1,124 @@
+// tma.cuh — Tensor Memory Accelerator + mbarrier primitives (inline PTX, sm_100a) and the host-side tensor-map encoder.
+//
+// Device side: one elected thread arms an mbarrier with the byte count of a tile (`arrive.expect_tx`) and issues
+// `cp.async.bulk.tensor` — the copy engine fetches the whole box (out-of-bounds elements, including negative
+// coordinates, arrive as zeros: the stencil halo for free) and completes the barrier's transaction count; consumers
+// wait on the barrier's phase parity.  No compute thread issues a load, computes an address or tests a bound.
+// SASS: UTMALDG / UTMASTG (tensor copies), UBLKCP (1-D bulk copies), SYNCS (mbarrier).
+//
+// Host side: tensor maps are encoded with the driver's cuTensorMapEncodeTiled, resolved through
+// cudaGetDriverEntryPoint so that the library keeps linking against the runtime only.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace lmnet {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+// make barrier initialisation visible to the async proxy (TMA) before the first use
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// order generic-proxy shared-memory writes before subsequent async-proxy (TMA store) reads
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+// blocks until the phase with the given parity has completed (try_wait suspends the thread in hardware)
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "LAB_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra LAB_WAIT;\n\t"
+        "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+// 3-D tiled load: box at coordinates (c0 innermost, c1, c2) -> dense shared-memory tile; completes `bar`'s tx count
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+        : "memory");
+}
+// 3-D tiled store: dense shared-memory tile -> box at (c0, c1, c2); elements outside the tensor are dropped
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(
+                     reinterpret_cast<uint64_t>(map)),
+                 "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(smem_src))
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until at most N committed store groups still READ their shared-memory source (the tile can be reused)
+template <int N> __device__ __forceinline__ void tma_store_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N> __device__ __forceinline__ void tma_store_wait_all() {
+    asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+// 1-D bulk copy global -> shared (16-byte aligned, size multiple of 16), completing `bar`'s tx count
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// named barrier among `nthreads` threads (ids 1..15; 0 is __syncthreads)
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host: tensor map of a [planes, H, W] tensor of 16-bit elements (NCHW planes), box = [1, box_h, box_w]
+// ---------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn tma_encode_fn() {
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess) {
+            (void)cudaGetLastError();
+            return nullptr;
+        }
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+
+// true when a [planes,H,W] tensor with `esize`-byte elements at `base` can be described to the TMA unit
+inline bool tma_planes_ok(const void* base, int64_t planes, int H, int W, size_t esize) {
+    return tma_encode_fn() != nullptr && ((uintptr_t)base % 16 == 0) && (((size_t)W * esize) % 16 == 0) && planes > 0 &&
+           planes < ((int64_t)1 << 31) && H > 0 && W > 0;
+}
+
+inline bool tma_make_planes_map(CUtensorMap* map, const void* base, int64_t planes, int H, int W, int box_h, int box_w,
+                                CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_NONE) {
+    EncodeTiledFn fn = tma_encode_fn();
+    if (fn == nullptr) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)planes};
+    const cuuint64_t strides[2] = {(cuuint64_t)W * 2, (cuuint64_t)W * H * 2};
+    const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace lmnet

@@ -54,6 +54,10 @@ class UpsampleDims(Structure):
     _fields_ = [("planes", c_int64), ("H", c_int32), ("W", c_int32)]
 
 
+class UpsampleClDims(Structure):
+    _fields_ = [("B", c_int64), ("H", c_int32), ("W", c_int32), ("C", c_int32)]
+
+
 class WgradDims(Structure):
     _fields_ = [("B", c_int32), ("M", c_int32), ("N1", c_int32), ("N2", c_int32), ("P", c_int64)]
 
@@ -116,6 +120,9 @@ def lib():
     pud = POINTER(UpsampleDims)
     L.lmnet_upsample2x_fwd.argtypes = [c_void_p, c_void_p, pud, c_int, c_void_p]
     L.lmnet_upsample2x_bwd.argtypes = [c_void_p, c_void_p, pud, c_int, c_void_p]
+    pucd = POINTER(UpsampleClDims)
+    L.lmnet_upsample2x_cl_fwd.argtypes = [c_void_p, c_void_p, pucd, c_int, c_void_p]
+    L.lmnet_upsample2x_cl_bwd.argtypes = [c_void_p, c_void_p, pucd, c_int, c_void_p]
     L.lmnet_profile_enable.argtypes = [c_int]
     L.lmnet_profile_kernel_name.restype = ctypes.c_char_p
     L.lmnet_profile_kernel_name.argtypes = [c_int]
@@ -224,4 +231,4 @@ def dw_grads(dw, dgamma, dbeta) -> DwGrads:
 
 
 __all__ = ["lib", "check", "dtype_code", "require_cuda", "stream_ptr", "ptr", "view5", "na_dims", "dw_params",
-           "dw_grads", "View5", "NADims", "DwParams", "DwGrads", "DwDims", "BnDims", "ACT_CODES", "WgradDims", "UpsampleDims", "byref", "launch_count", "LIB_PATH"]
+           "dw_grads", "View5", "NADims", "DwParams", "DwGrads", "DwDims", "BnDims", "ACT_CODES", "WgradDims", "UpsampleDims", "UpsampleClDims", "byref", "launch_count", "LIB_PATH"]

@@ -18,8 +18,9 @@ def branch_section(mod, x1):
     for br in (mod.large_conv, mod.square_conv, mod.ver_conv, mod.hor_conv):
         c, bn = br.conv, br.bn
         y = F.conv2d(x1, c.weight, None, c.stride, c.padding, 1, c.groups)
-        use_batch = mod.training or bn.running_mean is None
-        if mod.training and bn.running_mean is not None:
+        # nn.BatchNorm2d (which the reference calls through `self.large_conv(x1)` etc.) keys on ITS OWN .training flag
+        use_batch = bn.training or bn.running_mean is None
+        if bn.training and bn.running_mean is not None:
             bn.num_batches_tracked.add_(1)
         y = F.batch_norm(y, None if bn.running_mean is None else bn.running_mean,
                          None if bn.running_var is None else bn.running_var,

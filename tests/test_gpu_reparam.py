@@ -185,3 +185,76 @@ def test_no_grad_in_eval_mode_is_enforced():
         blk(x)
     with torch.no_grad():
         assert blk(x).shape == (1, 4, 16, 16)
+
+
+# shapes that take the TMA + mbarrier pipeline kernels (16-bit storage, W % 8 == 0): (B, E, H, W)
+TMA_SHAPES = [
+    (2, 16, 40, 72),      # two forward stripes (64 + 8), two dx stripes (56 + 16), ragged row tiles
+    (1, 8, 70, 136),      # three stripes, three row tiles (32, 32, 6), dx tiles of 28 rows
+    (2, 8, 33, 64),       # exactly one forward stripe; dx needs two (56 + 8)
+    (1, 6, 9, 8),         # plane smaller than the TMA box in both directions
+    (2, 24, 88, 88),      # LM-Net level-3 map
+    (3, 4, 64, 128),      # tiles align exactly with the image (no masks anywhere)
+    (1, 5, 120, 56),      # several row tiles per band, one dx stripe exactly
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("shape", TMA_SHAPES, ids=lambda s: "x".join(map(str, s)))
+def test_tma_pipeline_kernels_vs_oracle(shape, dtype):
+    """The fused op on the TMA path vs the fp64 oracle: z, pool, dx and EVERY parameter gradient (the depthwise weight
+    gradients come out of the dx kernel's Gram products), training-mode statistics, plus eval mode; and agreement with
+    the first-generation (non-TMA) kernels on the same inputs (LMNET_DW_NO_TMA=1)."""
+    from lmnet_b200.reparam import fused_dw_bn_gelu
+    from oracle.reparam_ref import dw_bn_gelu
+
+    B, E, H, W = shape
+    blk = _block(4, E, 4, seed=13)
+    ref = copy.deepcopy(blk).double().train()
+    g = torch.Generator().manual_seed(17)
+    x1 = torch.randn(B, E, H, W, generator=g).to(dtype)
+    gz = torch.randn(B, E, H, W, generator=g)
+    gp = torch.randn(B, E, generator=g)
+    xr = x1.double().requires_grad_()
+    zr, pr = dw_bn_gelu(ref, xr)
+    (zr * gz.double()).sum().add((pr * gp.double()).sum()).backward()
+    tol = 2e-2 if dtype == torch.bfloat16 else 5e-3
+
+    def run(no_tma):
+        if no_tma:
+            os.environ["LMNET_DW_NO_TMA"] = "1"
+        try:
+            m = copy.deepcopy(blk).cuda().train()
+            xc = x1.cuda().requires_grad_()
+            z, p = fused_dw_bn_gelu(m, xc)
+            (z.float() * gz.cuda()).sum().add((p * gp.cuda()).sum()).backward()
+            torch.cuda.synchronize()
+            return m, xc, z, p
+        finally:
+            os.environ.pop("LMNET_DW_NO_TMA", None)
+
+    m, xc, z, p = run(False)
+    assert rel_err(z.float().cpu(), zr) < tol
+    assert rel_err(p.cpu(), pr) < tol
+    assert rel_err(xc.grad.float().cpu(), xr.grad) < tol * 2
+    names = ("large_conv", "square_conv", "ver_conv", "hor_conv")
+    for n in names:
+        a, b = getattr(m, n), getattr(ref, n)
+        assert rel_err(a.conv.weight.grad.cpu(), b.conv.weight.grad) < tol * 3, n
+        assert rel_err(a.bn.weight.grad.cpu(), b.bn.weight.grad) < tol * 3, n
+        assert rel_err(a.bn.bias.grad.cpu(), b.bn.bias.grad) < tol * 3, n
+        assert torch.allclose(a.bn.running_mean.double().cpu(), b.bn.running_mean, rtol=5 * tol, atol=tol), n
+        assert torch.allclose(a.bn.running_var.double().cpu(), b.bn.running_var, rtol=5 * tol, atol=tol), n
+    m0, xc0, z0, p0 = run(True)
+    assert rel_err(z.float(), z0.float()) < 1e-2 and rel_err(p, p0) < 1e-3
+    assert rel_err(xc.grad.float(), xc0.grad.float()) < 2e-2
+    for n in names:
+        assert rel_err(getattr(m, n).conv.weight.grad, getattr(m0, n).conv.weight.grad) < 2e-2, n
+    # eval mode (running statistics folded into one 5x5 kernel)
+    ref.eval()
+    m.eval()
+    ref.load_state_dict({k: v.double().cpu() for k, v in m.state_dict().items()})
+    with torch.no_grad():
+        ze, pe = fused_dw_bn_gelu(m, x1.cuda())
+        zre, pre = dw_bn_gelu(ref, x1.double())
+    assert rel_err(ze.float().cpu(), zre) < tol and rel_err(pe.cpu(), pre) < tol
