@@ -217,6 +217,17 @@ size_t lmnet_wgrad_1x1_workspace_bytes(const lmnet_wgrad_dims* dims);
 int lmnet_wgrad_1x1(const void* A, const void* B1, const void* B2, float* dW, float* drow,
                     void* workspace, size_t workspace_bytes, const lmnet_wgrad_dims* dims, int dtype, void* stream);
 
+/* Mixed-layout variant: an operand flagged channels-last is [B, P, C] (C contiguous: the memory layout of the
+ * block's NHWC input / output tensors) instead of [B, C, P]; B2, when present (N2 > 0), is always channels-last.
+ * Used by the 1x1 convolutions of ReparamConv when the block runs on channels-last tensors (no transposed copies):
+ * expand (A = grad of the expanded planes, B1 = x channels-last) and pointwise + shortcut (A = grad_output
+ * channels-last, B1 = z planes, B2 = x channels-last).  /root/reference/core/modules.py:587, 598-599. */
+int lmnet_wgrad_1x1_cl_supported(const lmnet_wgrad_dims* dims, int a_channels_last, int b1_channels_last, int dtype);
+size_t lmnet_wgrad_1x1_cl_workspace_bytes(const lmnet_wgrad_dims* dims, int a_channels_last, int b1_channels_last);
+int lmnet_wgrad_1x1_cl(const void* A, const void* B1, const void* B2, float* dW, float* drow,
+                       void* workspace, size_t workspace_bytes, const lmnet_wgrad_dims* dims,
+                       int a_channels_last, int b1_channels_last, int dtype, void* stream);
+
 /* ---- bilinear x2 up-sampling, align_corners=True, NCHW (widening step f3) ----------------------
  * Replaces nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True) of the decoder and skip blocks
  * (/root/reference/core/LM_Net.py:58-74, /root/reference/core/modules.py:93-95, 129-131).

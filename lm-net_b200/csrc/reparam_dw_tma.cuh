@@ -326,7 +326,8 @@ dw_apply_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __res
                     const uint32_t up = MmaOp<T>::pack(acc[cb][2 * h], acc[cb][2 * h + 1]);
                     if (u_out != nullptr) *reinterpret_cast<uint32_t*>(u_out + off) = up;
                     const T* ur = reinterpret_cast<const T*>(&up);          // GELU of the value as stored
-                    const float z0 = gelu_f(to_f(ur[0])), z1 = gelu_f(to_f(ur[1]));
+                    float z0, z1;
+                    gelu_fast2(to_f(ur[0]), to_f(ur[1]), z0, z1);
                     const uint32_t zp = MmaOp<T>::pack(z0, z1);
                     *reinterpret_cast<uint32_t*>(z_out + off) = zp;
                     const T* zr = reinterpret_cast<const T*>(&zp);          // pool of the values as stored
@@ -425,9 +426,9 @@ dw_bwd_reduce_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_
                     const uint32_t zr = *reinterpret_cast<const uint32_t*>(s_dz + trow * kMmaPitch + bcol + 2);
                     const T* ue = reinterpret_cast<const T*>(&ur);
                     const T* ze = reinterpret_cast<const T*>(&zr);
-                    const float d0 = (to_f(ze[0]) + dp) * gelu_grad_f(to_f(ue[0]));
-                    const float d1 = (to_f(ze[1]) + dp) * gelu_grad_f(to_f(ue[1]));
-                    packed = MmaOp<T>::pack(d0, d1);
+                    float g0, g1;
+                    gelu_grad_fast2(to_f(ue[0]), to_f(ue[1]), g0, g1);
+                    packed = MmaOp<T>::pack((to_f(ze[0]) + dp) * g0, (to_f(ze[1]) + dp) * g1);
                     *reinterpret_cast<uint32_t*>(du_out + poff + (int64_t)(tr + trow) * g.W + c0 + bcol) = packed;
                     const T* de = reinterpret_cast<const T*>(&packed);
                     sdu += to_f(de[0]) + to_f(de[1]);             // exactly what the dx pass reads back

@@ -37,10 +37,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n\t.reg .pred P1;\n\t"
         "LAB_WAIT:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
         "@P1 bra DONE;\n\t"
         "bra LAB_WAIT;\n\t"
-        "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity)
+        "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680)      // suspend-time hint: sleep, do not spin
         : "memory");
 }
 

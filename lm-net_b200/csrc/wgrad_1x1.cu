@@ -181,18 +181,224 @@ wgrad_1x1_kernel(const T* __restrict__ A, const T* __restrict__ B1, const T* __r
 }
 
 // dW[b][m][n] (n < N1+N2) and drow[b][m] (the ones column) = sum over splits, fixed order
+// (partial column of output n: n < N1 -> n; N1 <= n < Ntot -> n2_off + n - N1; the ones column -> ones_col)
 __global__ void wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ dW, float* __restrict__ drow,
-                                    int B, int splits, int M, int Ntot, int ldn) {
+                                    int B, int splits, int M, int Ntot, int ldn, int N1, int n2_off, int ones_col) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t total = (int64_t)B * M * (Ntot + 1);
     if (idx >= total) return;
     const int n = (int)(idx % (Ntot + 1));
     const int m = (int)((idx / (Ntot + 1)) % M);
     const int b = (int)(idx / ((int64_t)(Ntot + 1) * M));
+    const int col = n < N1 ? n : n < Ntot ? n2_off + (n - N1) : ones_col;
     float a = 0.f;
-    for (int s = 0; s < splits; ++s) a += part[(((int64_t)b * splits + s) * M + m) * ldn + n];
+    for (int s = 0; s < splits; ++s) a += part[(((int64_t)b * splits + s) * M + m) * ldn + col];
     if (n < Ntot) dW[((int64_t)b * M + m) * Ntot + n] = a;
     else if (drow != nullptr) drow[(int64_t)b * M + m] = a;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Mixed-layout variant: operands may be channels-last ([B, P, C], C contiguous — the layout of the block's
+// input / output tensors) instead of NCHW planes ([B, C, P]).  A channels-last tile is staged as [64 pixels][C]
+// and read with ldmatrix.trans, so no transposed copy of the activation is ever made:
+//     expand:              dW[E, Cin]      = sum_p dy[e, p]   * x[p, cin]          A planes, B1 channels-last
+//     pointwise+shortcut:  dW[Cout, E+Cin] = sum_p dout[p, co] * (z[e, p] | x[p, cin])   A cl, B1 planes, B2 cl
+// B2 (when present) is always channels-last.  The all-ones column that yields the bias gradient lives with the last
+// operand.  Partials: part[b][split][M][(NT1 + NT2) * 8], B2's columns start at NT1 * 8.
+// ---------------------------------------------------------------------------------------------------
+struct WgGeomCl {
+    int B, M, N1, N2, NT1, NT2;
+    int pitchA, pitchB1, pitchB2;      // element pitch of the channels-last tiles (unused for plane operands)
+    int64_t P;
+    int splits, chunks_per_split;
+};
+
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem, bool valid) {
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+    const int sz = valid ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(s), "l"(gmem), "r"(sz));
+}
+__device__ __forceinline__ void wg_ldmatrix_x4_trans(uint32_t (&r)[4], const void* p) {
+    const uint32_t addr = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void wg_ldmatrix_x2_trans(uint32_t (&r)[2], const void* p) {
+    const uint32_t addr = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
+}
+
+// stage a channels-last operand tile: 64 pixel rows x C channels (16-byte vectors when C % 8 == 0, else 8-byte)
+template <typename T>
+__device__ __forceinline__ void wg_issue_cl(T* s, int pitch, const T* src, int C, int64_t p0, int64_t P) {
+    if ((C & 7) == 0) {
+        const int vpr = C >> 3;
+        for (int i = threadIdx.x; i < kWgKP * vpr; i += kWgThreads) {
+            const int r = i / vpr, v = i - r * vpr;
+            const bool ok = p0 + r < P;
+            cp_async16(s + r * pitch + v * 8, ok ? src + (p0 + r) * C + v * 8 : src, ok);
+        }
+    } else {
+        const int vpr = C >> 2;
+        for (int i = threadIdx.x; i < kWgKP * vpr; i += kWgThreads) {
+            const int r = i / vpr, v = i - r * vpr;
+            const bool ok = p0 + r < P;
+            cp_async8(s + r * pitch + v * 4, ok ? src + (p0 + r) * C + v * 4 : src, ok);
+        }
+    }
+}
+// stage a plane operand tile: `rows` channel rows x 64 pixels
+template <typename T>
+__device__ __forceinline__ void wg_issue_planes(T* s, const T* src, int rows, int64_t p0, int64_t P) {
+    constexpr int VPR = kWgKP / 8;
+    for (int i = threadIdx.x; i < rows * VPR; i += kWgThreads) {
+        const int r = i / VPR, v = i - r * VPR;
+        const int64_t p = p0 + v * 8;
+        const bool ok = p < P;                          // P % 8 == 0: a vector is all in or all out
+        cp_async16(s + r * kWgPitch + v * 8, ok ? src + (int64_t)r * P + p : src, ok);
+    }
+}
+
+template <typename T, int MT, int NTW, bool ACL, bool B1CL>
+__global__ void __launch_bounds__(kWgThreads)
+wgrad_1x1_cl_kernel(const T* __restrict__ A, const T* __restrict__ B1, const T* __restrict__ B2,
+                    float* __restrict__ part, WgGeomCl g) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int a_elems = ACL ? kWgKP * g.pitchA : MT * 16 * kWgPitch;
+    const int b1_elems = B1CL ? kWgKP * g.pitchB1 : g.NT1 * 8 * kWgPitch;
+    const int b2_elems = g.N2 > 0 ? kWgKP * g.pitchB2 : 0;
+    const int stage_elems = a_elems + b1_elems + b2_elems;
+    T* smem = reinterpret_cast<T*>(smem_raw);
+    const int b = blockIdx.y, split = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t chunk0 = (int64_t)split * g.chunks_per_split;
+    const int64_t nchunks_total = (g.P + kWgKP - 1) / kWgKP;
+    const int nchunks = (int)max((int64_t)0, min((int64_t)g.chunks_per_split, nchunks_total - chunk0));
+    const bool ones_in_b2 = g.N2 > 0;
+    const T one = wg_one<T>(), zero = from_f<T>(0.f);
+
+    // everything no copy ever touches: padding rows / columns are zero, the ones row / column is one (both stages)
+    for (int st = 0; st < 2; ++st) {
+        T* sa = smem + st * stage_elems;
+        T* sb1 = sa + a_elems;
+        T* sb2 = sb1 + b1_elems;
+        if (ACL) {
+            for (int i = threadIdx.x; i < kWgKP * g.pitchA; i += kWgThreads) sa[i] = zero;
+        } else {
+            for (int i = threadIdx.x; i < (MT * 16 - g.M) * kWgPitch; i += kWgThreads) sa[g.M * kWgPitch + i] = zero;
+        }
+        if (B1CL) {
+            for (int i = threadIdx.x; i < kWgKP * g.pitchB1; i += kWgThreads)
+                sb1[i] = (!ones_in_b2 && (i % g.pitchB1) == g.N1) ? one : zero;
+        } else {
+            for (int i = threadIdx.x; i < (g.NT1 * 8 - g.N1) * kWgPitch; i += kWgThreads)
+                sb1[g.N1 * kWgPitch + i] = (!ones_in_b2 && i < kWgPitch) ? one : zero;
+        }
+        for (int i = threadIdx.x; i < b2_elems; i += kWgThreads) sb2[i] = ((i % g.pitchB2) == g.N2) ? one : zero;
+    }
+    __syncthreads();       // the cp.async writes below must not race with the fills above
+
+    auto issue = [&](int c, int st) {
+        T* sa = smem + st * stage_elems;
+        T* sb1 = sa + a_elems;
+        T* sb2 = sb1 + b1_elems;
+        const int64_t p0 = (chunk0 + c) * kWgKP;
+        if (ACL) wg_issue_cl<T>(sa, g.pitchA, A + (int64_t)b * g.P * g.M, g.M, p0, g.P);
+        else wg_issue_planes<T>(sa, A + (int64_t)b * g.M * g.P, g.M, p0, g.P);
+        if (B1CL) wg_issue_cl<T>(sb1, g.pitchB1, B1 + (int64_t)b * g.P * g.N1, g.N1, p0, g.P);
+        else wg_issue_planes<T>(sb1, B1 + (int64_t)b * g.N1 * g.P, g.N1, p0, g.P);
+        if (g.N2 > 0) wg_issue_cl<T>(sb2, g.pitchB2, B2 + (int64_t)b * g.P * g.N2, g.N2, p0, g.P);
+        cp_async_commit();
+    };
+
+    float acc[MT][NTW][4];
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < NTW; ++j) acc[i][j][0] = acc[i][j][1] = acc[i][j][2] = acc[i][j][3] = 0.f;
+    const int nt0 = warp * NTW;
+    const int NT = g.NT1 + g.NT2;
+
+    if (nchunks > 0) issue(0, 0);
+    for (int c = 0; c < nchunks; ++c) {
+        const int st = c & 1;
+        if (c + 1 < nchunks) {
+            issue(c + 1, st ^ 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        T* sa = smem + st * stage_elems;
+        T* sb1 = sa + a_elems;
+        T* sb2 = sb1 + b1_elems;
+        const bool tail = (chunk0 + c + 1) * kWgKP > g.P;
+        if (tail) {            // the ones entries must only count real pixels of the tail chunk
+            const int valid = (int)(g.P - (chunk0 + c) * kWgKP);
+            for (int i = threadIdx.x; i < kWgKP; i += kWgThreads) {
+                const T v = i < valid ? one : zero;
+                if (ones_in_b2) sb2[i * g.pitchB2 + g.N2] = v;
+                else if (B1CL) sb1[i * g.pitchB1 + g.N1] = v;
+                else sb1[g.N1 * kWgPitch + i] = v;
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int kt = 0; kt < kWgKP / 16; ++kt) {
+            uint32_t bf[NTW][2];
+#pragma unroll
+            for (int j = 0; j < NTW; ++j) {
+                const int nt = nt0 + j;
+                if (nt < NT) {
+                    const int l = lane & 15;
+                    if (nt >= g.NT1) wg_ldmatrix_x2_trans(bf[j], sb2 + (kt * 16 + l) * g.pitchB2 + (nt - g.NT1) * 8);
+                    else if (B1CL) wg_ldmatrix_x2_trans(bf[j], sb1 + (kt * 16 + l) * g.pitchB1 + nt * 8);
+                    else wg_ldmatrix_x2(bf[j], sb1 + (nt * 8 + (l & 7)) * kWgPitch + kt * 16 + (l >> 3) * 8);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < MT; ++i) {
+                uint32_t af[4];
+                const int m = lane >> 3, rr = lane & 7;
+                if (ACL) wg_ldmatrix_x4_trans(af, sa + (kt * 16 + (m >> 1) * 8 + rr) * g.pitchA + i * 16 + (m & 1) * 8);
+                else wg_ldmatrix_x4(af, sa + (i * 16 + (m & 1) * 8 + rr) * kWgPitch + kt * 16 + (m >> 1) * 8);
+#pragma unroll
+                for (int j = 0; j < NTW; ++j)
+                    if (nt0 + j < NT) wg_mma<T>(acc[i][j], af, bf[j]);
+            }
+        }
+        __syncthreads();
+        if (tail) {            // restore the ones entries for the next use of this stage
+            for (int i = threadIdx.x; i < kWgKP; i += kWgThreads) {
+                if (ones_in_b2) sb2[i * g.pitchB2 + g.N2] = one;
+                else if (B1CL) sb1[i * g.pitchB1 + g.N1] = one;
+                else sb1[g.N1 * kWgPitch + i] = one;
+            }
+        }
+    }
+    const int ldn = NT * 8;
+    float* out = part + ((int64_t)b * g.splits + split) * g.M * ldn;
+    const int gq = lane >> 2, tq = lane & 3;
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < NTW; ++j) {
+            const int nt = nt0 + j;
+            if (nt < NT) {
+                const int n = nt * 8 + 2 * tq;
+                const int m0 = i * 16 + gq, m1 = m0 + 8;
+                if (m0 < g.M) *reinterpret_cast<float2*>(out + (int64_t)m0 * ldn + n) = make_float2(acc[i][j][0], acc[i][j][1]);
+                if (m1 < g.M) *reinterpret_cast<float2*>(out + (int64_t)m1 * ldn + n) = make_float2(acc[i][j][2], acc[i][j][3]);
+            }
+        }
+}
+
+// element pitch of a channels-last tile that must cover `cols` columns: multiple of 8, == 8 (mod 16) so that the
+// eight 16-byte rows of an ldmatrix land in distinct bank groups
+static int wg_cl_pitch(int cols) {
+    int p = (cols + 7) / 8 * 8;
+    if (p % 16 != 8) p += 8;
+    return p;
 }
 
 static bool wg_shape(int M, int N, int& MT, int& NTW, int& NT) {
@@ -250,9 +456,120 @@ static int wg_dispatch(int MT, int NTW, const void* A, const void* B1, const voi
     }
 }
 
+// ---- mixed-layout host side ----
+struct WgClPlan {
+    int MT, NTW;
+    WgGeomCl g;
+    size_t smem;
+};
+static bool wg_cl_plan(const lmnet_wgrad_dims* d, bool a_cl, bool b1_cl, WgClPlan& pl) {
+    if (d == nullptr || d->B <= 0 || d->M <= 0 || d->N1 <= 0 || d->N2 < 0 || d->P <= 0) return false;
+    if (d->P % 8 != 0) return false;                                   // plane operands: 16-byte pixel vectors
+    if (a_cl && d->M % 4 != 0) return false;                           // channels-last rows: 8-byte vectors at least
+    if (b1_cl && d->N1 % 4 != 0) return false;
+    if (d->N2 > 0 && (d->N2 % 4 != 0 || d->N1 % 8 != 0)) return false; // B2 tiles start at an 8-column boundary
+    WgGeomCl& g = pl.g;
+    g.B = d->B; g.M = d->M; g.N1 = d->N1; g.N2 = d->N2; g.P = d->P;
+    g.NT1 = (d->N1 + (d->N2 > 0 ? 0 : 1) + 7) / 8;
+    g.NT2 = d->N2 > 0 ? (d->N2 + 1 + 7) / 8 : 0;
+    pl.MT = (d->M + 15) / 16;
+    const int NT = g.NT1 + g.NT2;
+    pl.NTW = (NT + kWgWarps - 1) / kWgWarps;
+    const bool mt_ok = pl.MT == 1 || pl.MT == 2 || pl.MT == 3 || pl.MT == 6 || pl.MT == 12;
+    const bool nt_ok = pl.NTW == 1 || pl.NTW == 2 || pl.NTW == 3 || pl.NTW == 5;
+    if (!mt_ok || !nt_ok || pl.MT * pl.NTW > 30) return false;
+    g.pitchA = wg_cl_pitch(pl.MT * 16);
+    g.pitchB1 = wg_cl_pitch(g.NT1 * 8);
+    g.pitchB2 = g.N2 > 0 ? wg_cl_pitch(g.NT2 * 8) : 0;
+    const int64_t nchunks = (d->P + kWgKP - 1) / kWgKP;
+    int64_t splits = (4 * 148 + d->B - 1) / d->B;
+    if (splits > nchunks) splits = nchunks;
+    if (splits < 1) splits = 1;
+    g.chunks_per_split = (int)((nchunks + splits - 1) / splits);
+    g.splits = (int)((nchunks + g.chunks_per_split - 1) / g.chunks_per_split);
+    const size_t a_elems = a_cl ? (size_t)kWgKP * g.pitchA : (size_t)pl.MT * 16 * kWgPitch;
+    const size_t b1_elems = b1_cl ? (size_t)kWgKP * g.pitchB1 : (size_t)g.NT1 * 8 * kWgPitch;
+    const size_t b2_elems = g.N2 > 0 ? (size_t)kWgKP * g.pitchB2 : 0;
+    pl.smem = 2 * (a_elems + b1_elems + b2_elems) * 2;
+    return pl.smem <= 220 * 1024;
+}
+
+template <typename T, int MT, int NTW, bool ACL, bool B1CL>
+static int wg_cl_launch(const void* A, const void* B1, const void* B2, float* part, const WgClPlan& pl, cudaStream_t st) {
+    static std::atomic<size_t> granted[kMaxDevices];
+    if (!ensure_smem(wgrad_1x1_cl_kernel<T, MT, NTW, ACL, B1CL>, pl.smem, granted)) return LMNET_ERR_LAUNCH;
+    const WgGeomCl& g = pl.g;
+    const double bytes = (double)g.B * (g.M + g.N1 + g.N2) * g.P * sizeof(T);
+    dim3 grid(g.splits, g.B);
+    LMNET_LAUNCH(KID_WGRAD_1X1, st, bytes, (wgrad_1x1_cl_kernel<T, MT, NTW, ACL, B1CL><<<grid, kWgThreads, pl.smem, st>>>(
+        (const T*)A, (const T*)B1, (const T*)B2, part, g)));
+    return LMNET_OK;
+}
+template <typename T, int MT, bool ACL, bool B1CL>
+static int wg_cl_dispatch_n(const void* A, const void* B1, const void* B2, float* part, const WgClPlan& pl, cudaStream_t st) {
+    switch (pl.NTW) {
+        case 1: return wg_cl_launch<T, MT, 1, ACL, B1CL>(A, B1, B2, part, pl, st);
+        case 2: return wg_cl_launch<T, MT, 2, ACL, B1CL>(A, B1, B2, part, pl, st);
+        case 3: if constexpr (MT <= 6) return wg_cl_launch<T, MT, 3, ACL, B1CL>(A, B1, B2, part, pl, st); else return LMNET_ERR_UNSUPPORTED;
+        case 5: if constexpr (MT <= 6) return wg_cl_launch<T, MT, 5, ACL, B1CL>(A, B1, B2, part, pl, st); else return LMNET_ERR_UNSUPPORTED;
+        default: return LMNET_ERR_UNSUPPORTED;
+    }
+}
+template <typename T, bool ACL, bool B1CL>
+static int wg_cl_dispatch(const void* A, const void* B1, const void* B2, float* part, const WgClPlan& pl, cudaStream_t st) {
+    switch (pl.MT) {
+        case 1: return wg_cl_dispatch_n<T, 1, ACL, B1CL>(A, B1, B2, part, pl, st);
+        case 2: return wg_cl_dispatch_n<T, 2, ACL, B1CL>(A, B1, B2, part, pl, st);
+        case 3: return wg_cl_dispatch_n<T, 3, ACL, B1CL>(A, B1, B2, part, pl, st);
+        case 6: return wg_cl_dispatch_n<T, 6, ACL, B1CL>(A, B1, B2, part, pl, st);
+        case 12: return wg_cl_dispatch_n<T, 12, ACL, B1CL>(A, B1, B2, part, pl, st);
+        default: return LMNET_ERR_UNSUPPORTED;
+    }
+}
+template <typename T>
+static int wg_cl_layouts(bool a_cl, bool b1_cl, const void* A, const void* B1, const void* B2, float* part, const WgClPlan& pl, cudaStream_t st) {
+    if (a_cl && !b1_cl) return wg_cl_dispatch<T, true, false>(A, B1, B2, part, pl, st);
+    if (!a_cl && b1_cl) return wg_cl_dispatch<T, false, true>(A, B1, B2, part, pl, st);
+    if (a_cl && b1_cl) return wg_cl_dispatch<T, true, true>(A, B1, B2, part, pl, st);
+    return LMNET_ERR_UNSUPPORTED;      // all-plane operands: lmnet_wgrad_1x1
+}
+
 }  // namespace lmnet
 
 using namespace lmnet;
+
+extern "C" int lmnet_wgrad_1x1_cl_supported(const lmnet_wgrad_dims* d, int a_cl, int b1_cl, int dtype) {
+    if (dtype != LMNET_BF16 && dtype != LMNET_F16) return 0;
+    if (!a_cl && !b1_cl) return 0;
+    WgClPlan pl;
+    return wg_cl_plan(d, a_cl != 0, b1_cl != 0, pl) ? 1 : 0;
+}
+extern "C" size_t lmnet_wgrad_1x1_cl_workspace_bytes(const lmnet_wgrad_dims* d, int a_cl, int b1_cl) {
+    WgClPlan pl;
+    if (!wg_cl_plan(d, a_cl != 0, b1_cl != 0, pl)) return 0;
+    return (size_t)pl.g.B * pl.g.splits * pl.g.M * ((pl.g.NT1 + pl.g.NT2) * 8) * sizeof(float);
+}
+extern "C" int lmnet_wgrad_1x1_cl(const void* A, const void* B1, const void* B2, float* dW, float* drow,
+                                  void* workspace, size_t workspace_bytes, const lmnet_wgrad_dims* d, int a_cl, int b1_cl,
+                                  int dtype, void* stream) {
+    if (!lmnet_wgrad_1x1_cl_supported(d, a_cl, b1_cl, dtype)) return LMNET_ERR_UNSUPPORTED;
+    if (!A || !B1 || (d->N2 > 0 && !B2) || !dW || !workspace) return LMNET_ERR_INVALID_ARG;
+    if (workspace_bytes < lmnet_wgrad_1x1_cl_workspace_bytes(d, a_cl, b1_cl)) return LMNET_ERR_WORKSPACE;
+    if ((uintptr_t)A % 16 || (uintptr_t)B1 % 16 || (uintptr_t)B2 % 16) return LMNET_ERR_UNSUPPORTED;
+    WgClPlan pl;
+    wg_cl_plan(d, a_cl != 0, b1_cl != 0, pl);
+    cudaStream_t st = (cudaStream_t)stream;
+    float* part = (float*)workspace;
+    int rc = dtype == LMNET_BF16 ? wg_cl_layouts<__nv_bfloat16>(a_cl != 0, b1_cl != 0, A, B1, d->N2 > 0 ? B2 : B1, part, pl, st)
+                                 : wg_cl_layouts<__half>(a_cl != 0, b1_cl != 0, A, B1, d->N2 > 0 ? B2 : B1, part, pl, st);
+    if (rc != LMNET_OK) return rc;
+    const int Ntot = d->N1 + d->N2;
+    const int64_t total = (int64_t)d->B * d->M * (Ntot + 1);
+    const int ones_col = d->N2 > 0 ? pl.g.NT1 * 8 + d->N2 : d->N1;
+    LMNET_LAUNCH(KID_WGRAD_REDUCE, st, 0, (wgrad_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+        part, dW, drow, d->B, pl.g.splits, d->M, Ntot, (pl.g.NT1 + pl.g.NT2) * 8, d->N1, pl.g.NT1 * 8, ones_col)));
+    return LMNET_OK;
+}
 
 extern "C" int lmnet_wgrad_1x1_supported(const lmnet_wgrad_dims* d, int dtype) {
     if (d == nullptr || d->B <= 0 || d->M <= 0 || d->N1 <= 0 || d->N2 < 0 || d->P <= 0) return 0;
@@ -287,6 +604,6 @@ extern "C" int lmnet_wgrad_1x1(const void* A, const void* B1, const void* B2, fl
     const int Ntot = d->N1 + d->N2;
     const int64_t total = (int64_t)d->B * d->M * (Ntot + 1);
     LMNET_LAUNCH(KID_WGRAD_REDUCE, st, 0, (wgrad_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
-        part, dW, drow, d->B, g.splits, d->M, Ntot, NT * 8)));
+        part, dW, drow, d->B, g.splits, d->M, Ntot, NT * 8, d->N1, d->N1, Ntot)));
     return LMNET_OK;
 }
