@@ -187,6 +187,18 @@ int lmnet_bn_act_bwd(const void* y, const void* dout, const float* gamma, const 
                      const float* save_mean, const float* save_rstd, void* dy, float* dgamma, float* dbeta,
                      int act, void* workspace, size_t workspace_bytes, const lmnet_bn_dims* dims, int dtype,
                      void* stream);
+/* Channels-last variants: y / out / dout / dy are [B, HW, C] with C contiguous (the layout cuDNN's 16-bit
+ * convolutions produce), same semantics, same workspace query.  lmnet_bn_act_cl_supported(): B*HW*C must be a
+ * multiple of the 16-byte vector and lcm(C, vector) / vector <= 256. */
+int lmnet_bn_act_cl_supported(const lmnet_bn_dims* dims, int dtype);
+int lmnet_bn_act_cl_fwd(const void* y, const float* gamma, const float* beta, float* running_mean,
+                        float* running_var, int64_t* num_batches_tracked, void* out, float* save_mean,
+                        float* save_rstd, float eps, float momentum, int training, int act,
+                        void* workspace, size_t workspace_bytes, const lmnet_bn_dims* dims, int dtype, void* stream);
+int lmnet_bn_act_cl_bwd(const void* y, const void* dout, const float* gamma, const float* beta,
+                        const float* save_mean, const float* save_rstd, void* dy, float* dgamma, float* dbeta,
+                        int act, void* workspace, size_t workspace_bytes, const lmnet_bn_dims* dims, int dtype,
+                        void* stream);
 
 /* ---- LayerNorm over short channels-last rows (widening step f2, SURVEY.md §8 f) ------------------
  * Replaces nn.LayerNorm(C) as used twice per NeighborhoodTransformer

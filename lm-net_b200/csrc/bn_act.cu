@@ -245,6 +245,174 @@ bnact_bwd_apply_kernel(const T* __restrict__ y, const T* __restrict__ dout, cons
     });
 }
 
+// ================================================================================================
+// channels-last ([pixels, C], C contiguous) variants — the layout of cuDNN's 16-bit convolution outputs, so that
+// conv -> BatchNorm -> activation -> conv never changes layout.  A thread moves 16-byte vectors of the flat array;
+// its stride is a multiple of lcm(C, V) elements, so the V channels of its vector never change: per-channel
+// coefficients live in registers and the statistics are V running sums per thread.  Partials are combined in a
+// fixed order (thread table in shared memory, then one thread per channel): deterministic.
+// ================================================================================================
+struct BnGeomCl {
+    int C, VP, S;            // channels, vectors per channel period, active threads per CTA (multiple of VP)
+    int chunks;
+    int64_t nvec, vec_per_chunk;   // total vectors, vectors per CTA (multiple of VP)
+};
+
+template <typename T> struct ClVec { static constexpr int V = 16 / (int)sizeof(T); };
+
+template <typename T, typename Fn>
+__device__ __forceinline__ void for_chunk_cl(const BnGeomCl& g, Fn&& fn) {
+    if ((int)threadIdx.x >= g.S) return;
+    const int64_t lo = (int64_t)blockIdx.x * g.vec_per_chunk, hi = min(lo + g.vec_per_chunk, g.nvec);
+    for (int64_t v = lo + threadIdx.x; v < hi; v += g.S) fn(v * ClVec<T>::V);
+}
+// channel of slot j of this thread's vectors
+template <typename T> __device__ __forceinline__ int cl_channel(const BnGeomCl& g, int tid, int j) {
+    return (int)(((int64_t)(tid % g.VP) * ClVec<T>::V + j) % g.C);
+}
+
+// sums the per-thread slot values (two quantities) into per-channel totals; part[c][chunk][2]
+template <typename T>
+__device__ __forceinline__ void cl_block_reduce(const BnGeomCl& g, const float (&a)[ClVec<T>::V], const float (&b)[ClVec<T>::V],
+                                                float* s_tab /* [256][2V] */, float* __restrict__ part) {
+    constexpr int V = ClVec<T>::V;
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        s_tab[threadIdx.x * 2 * V + j] = a[j];
+        s_tab[threadIdx.x * 2 * V + V + j] = b[j];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < g.C; c += kBnThreads) {
+        float sa = 0.f, sb = 0.f;
+        for (int ph = 0; ph < g.VP; ++ph)
+            for (int j = 0; j < V; ++j)
+                if ((ph * V + j) % g.C == c)
+                    for (int t = ph; t < g.S; t += g.VP) {
+                        sa += s_tab[t * 2 * V + j];
+                        sb += s_tab[t * 2 * V + V + j];
+                    }
+        part[((int64_t)c * g.chunks + blockIdx.x) * 2] = sa;
+        part[((int64_t)c * g.chunks + blockIdx.x) * 2 + 1] = sb;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kBnThreads)
+bnact_stats_cl_kernel(const T* __restrict__ y, float* __restrict__ part, BnGeomCl g) {
+    constexpr int V = ClVec<T>::V;
+    extern __shared__ float s_tab[];
+    float s[V], ss[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) s[j] = ss[j] = 0.f;
+    for_chunk_cl<T>(g, [&](int64_t off) {
+        float f[V];
+        ld_elems<T, true>(y + off, f, V);
+#pragma unroll
+        for (int j = 0; j < V; ++j) { s[j] += f[j]; ss[j] = fmaf(f[j], f[j], ss[j]); }
+    });
+    cl_block_reduce<T>(g, s, ss, s_tab, part);
+}
+
+template <typename T, int ACT>
+__global__ void __launch_bounds__(kBnThreads)
+bnact_apply_cl_kernel(const T* __restrict__ y, const float2* __restrict__ coef, T* __restrict__ out, BnGeomCl g) {
+    constexpr int V = ClVec<T>::V;
+    float2 ab[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) ab[j] = __ldg(coef + cl_channel<T>(g, threadIdx.x, j));
+    for_chunk_cl<T>(g, [&](int64_t off) {
+        float f[V];
+        ld_elems<T, true>(y + off, f, V);
+#pragma unroll
+        for (int j = 0; j < V; ++j) f[j] = act_fwd<ACT, T>(to_f(from_f<T>(fmaf(f[j], ab[j].x, ab[j].y))));
+        st_elems<T, true>(out + off, f, V);
+    });
+}
+
+template <typename T, int ACT>
+__global__ void __launch_bounds__(kBnThreads)
+bnact_bwd_reduce_cl_kernel(const T* __restrict__ y, const T* __restrict__ dout, const float* __restrict__ gamma,
+                           const float* __restrict__ beta, const float* __restrict__ save_mean,
+                           const float* __restrict__ save_rstd, float* __restrict__ part, BnGeomCl g) {
+    constexpr int V = ClVec<T>::V;
+    extern __shared__ float s_tab[];
+    float mean[V], rstd[V], ga[V], be[V], s[V], sy[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        const int c = cl_channel<T>(g, threadIdx.x, j);
+        mean[j] = save_mean[c]; rstd[j] = save_rstd[c];
+        ga[j] = gamma != nullptr ? gamma[c] : 1.f; be[j] = beta != nullptr ? beta[c] : 0.f;
+        s[j] = sy[j] = 0.f;
+    }
+    for_chunk_cl<T>(g, [&](int64_t off) {
+        float f[V], d[V];
+        ld_elems<T, true>(y + off, f, V);
+        ld_elems<T, true>(dout + off, d, V);
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            const float yh = (f[j] - mean[j]) * rstd[j];
+            const float pre = to_f(from_f<T>(fmaf(yh, ga[j], be[j])));
+            const float dh = d[j] * act_bwd<ACT, T>(pre);
+            s[j] += dh;
+            sy[j] = fmaf(dh, yh, sy[j]);
+        }
+    });
+    cl_block_reduce<T>(g, s, sy, s_tab, part);
+}
+
+template <typename T, int ACT>
+__global__ void __launch_bounds__(kBnThreads)
+bnact_bwd_apply_cl_kernel(const T* __restrict__ y, const T* __restrict__ dout, const float* __restrict__ gamma,
+                          const float* __restrict__ beta, const float* __restrict__ save_mean,
+                          const float* __restrict__ save_rstd, const float2* __restrict__ cb, T* __restrict__ dy, BnGeomCl g) {
+    constexpr int V = ClVec<T>::V;
+    float mean[V], rstd[V], ga[V], be[V];
+    float2 m[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        const int c = cl_channel<T>(g, threadIdx.x, j);
+        mean[j] = save_mean[c]; rstd[j] = save_rstd[c];
+        ga[j] = gamma != nullptr ? gamma[c] : 1.f; be[j] = beta != nullptr ? beta[c] : 0.f;
+        m[j] = __ldg(cb + c);
+    }
+    for_chunk_cl<T>(g, [&](int64_t off) {
+        float f[V], d[V];
+        ld_elems<T, true>(y + off, f, V);
+        ld_elems<T, true>(dout + off, d, V);
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            const float yh = (f[j] - mean[j]) * rstd[j];
+            const float pre = to_f(from_f<T>(fmaf(yh, ga[j], be[j])));
+            const float dh = d[j] * act_bwd<ACT, T>(pre);
+            f[j] = ga[j] * rstd[j] * (dh - m[j].x - yh * m[j].y);
+        }
+        st_elems<T, true>(dy + off, f, V);
+    });
+}
+
+static int64_t bn_gcd(int64_t a, int64_t b) { return b == 0 ? a : bn_gcd(b, a % b); }
+// chunks is bounded by bn_geom's (the shared workspace layout), so the existing finalize kernels and workspace apply
+static bool bn_geom_cl(const lmnet_bn_dims* d, size_t es, BnGeomCl& g) {
+    const int64_t V = 16 / (int64_t)es;
+    const int64_t total = (int64_t)d->B * d->HW * d->C;
+    if (total % V != 0) return false;
+    const int64_t L = (int64_t)d->C / bn_gcd(d->C, V) * V;           // lcm(C, V) elements
+    g.C = d->C;
+    g.VP = (int)(L / V);
+    if (g.VP > kBnThreads) return false;
+    g.S = kBnThreads / g.VP * g.VP;
+    g.nvec = total / V;
+    int64_t chunks = 4 * 148;
+    const int64_t min_per = (int64_t)g.S * 4;
+    if (chunks > (g.nvec + min_per - 1) / min_per) chunks = (g.nvec + min_per - 1) / min_per;
+    if (chunks < 1) chunks = 1;
+    int64_t per = (g.nvec + chunks - 1) / chunks;
+    per = (per + g.VP - 1) / g.VP * g.VP;
+    g.vec_per_chunk = per;
+    g.chunks = (int)((g.nvec + per - 1) / per);
+    return true;
+}
+
 // ------------------------------------------------------------------------------------------------
 static int bn_validate(const lmnet_bn_dims* d) {
     if (d == nullptr || d->B <= 0 || d->C <= 0 || d->HW <= 0) return LMNET_ERR_INVALID_ARG;
@@ -282,6 +450,7 @@ static BnWs bn_ws(const lmnet_bn_dims* d) {
     BnGeom g = bn_geom(d, 2);   // the smaller element size gives the larger chunk count
     BnGeom g4 = bn_geom(d, 4);
     int chunks = g.chunks > g4.chunks ? g.chunks : g4.chunks;
+    if (chunks < 4 * 148) chunks = 4 * 148;      // the channels-last kernels use up to 4 x 148 CTAs
     BnWs w;
     w.part = 0;
     w.coef = ((size_t)d->C * chunks * 2 * sizeof(float) + 255) / 256 * 256;
@@ -326,6 +495,75 @@ static int bn_launch_bwd(const void* y, const void* dout, const float* gamma, co
     LMNET_LAUNCH(KID_BN_BWD_APPLY, st, 3 * t_bytes, (bnact_bwd_apply_kernel<T, VEC, ACT><<<grid, kBnThreads, 0, st>>>(
         (const T*)y, (const T*)dout, gamma, beta, save_mean, save_rstd, cb, (T*)dy, g)));
     return LMNET_OK;
+}
+
+template <typename T, int ACT>
+static int bn_launch_fwd_cl(bool train, const void* y, const float* gamma, const float* beta, float* rm, float* rv,
+                            int64_t* nbt, void* out, float* save_mean, float* save_rstd, float eps, float momentum,
+                            char* ws, const lmnet_bn_dims* d, cudaStream_t st) {
+    BnGeomCl gc;
+    if (!bn_geom_cl(d, sizeof(T), gc)) return LMNET_ERR_UNSUPPORTED;
+    BnGeom g = bn_geom(d, sizeof(T));
+    g.chunks = gc.chunks;                         // the finalize kernels sum `chunks` partials per channel
+    BnWs L = bn_ws(d);
+    float* part = (float*)(ws + L.part);
+    float2* coef = (float2*)(ws + L.coef);
+    const double t_bytes = (double)d->B * d->C * d->HW * sizeof(T);
+    const size_t tab = (size_t)kBnThreads * 2 * ClVec<T>::V * sizeof(float);
+    if (train) {
+        LMNET_LAUNCH(KID_BN_STATS, st, t_bytes, (bnact_stats_cl_kernel<T><<<gc.chunks, kBnThreads, tab, st>>>((const T*)y, part, gc)));
+        LMNET_LAUNCH(KID_BN_FIN_FWD, st, 0, (bnact_fin_fwd_kernel<<<(g.C + 127) / 128, 128, 0, st>>>(
+            part, gamma, beta, rm, rv, nbt, save_mean, save_rstd, coef, eps, momentum, g)));
+    } else {
+        LMNET_LAUNCH(KID_BN_FIN_FWD, st, 0, (bnact_coef_eval_kernel<<<(g.C + 127) / 128, 128, 0, st>>>(gamma, beta, rm, rv, coef, eps, g.C)));
+    }
+    LMNET_LAUNCH(KID_BN_APPLY, st, 2 * t_bytes, (bnact_apply_cl_kernel<T, ACT><<<gc.chunks, kBnThreads, 0, st>>>((const T*)y, coef, (T*)out, gc)));
+    return LMNET_OK;
+}
+
+template <typename T, int ACT>
+static int bn_launch_bwd_cl(const void* y, const void* dout, const float* gamma, const float* beta, const float* save_mean,
+                            const float* save_rstd, void* dy, float* dgamma, float* dbeta, char* ws,
+                            const lmnet_bn_dims* d, cudaStream_t st) {
+    BnGeomCl gc;
+    if (!bn_geom_cl(d, sizeof(T), gc)) return LMNET_ERR_UNSUPPORTED;
+    BnGeom g = bn_geom(d, sizeof(T));
+    g.chunks = gc.chunks;
+    BnWs L = bn_ws(d);
+    float* part = (float*)(ws + L.part);
+    float2* cb = (float2*)(ws + L.coef);
+    const double t_bytes = (double)d->B * d->C * d->HW * sizeof(T);
+    const size_t tab = (size_t)kBnThreads * 2 * ClVec<T>::V * sizeof(float);
+    LMNET_LAUNCH(KID_BN_BWD_REDUCE, st, 2 * t_bytes, (bnact_bwd_reduce_cl_kernel<T, ACT><<<gc.chunks, kBnThreads, tab, st>>>(
+        (const T*)y, (const T*)dout, gamma, beta, save_mean, save_rstd, part, gc)));
+    LMNET_LAUNCH(KID_BN_FIN_BWD, st, 0, (bnact_fin_bwd_kernel<<<(g.C + 127) / 128, 128, 0, st>>>(part, dgamma, dbeta, cb, g)));
+    LMNET_LAUNCH(KID_BN_BWD_APPLY, st, 3 * t_bytes, (bnact_bwd_apply_cl_kernel<T, ACT><<<gc.chunks, kBnThreads, 0, st>>>(
+        (const T*)y, (const T*)dout, gamma, beta, save_mean, save_rstd, cb, (T*)dy, gc)));
+    return LMNET_OK;
+}
+
+template <typename T>
+static int bn_fwd_cl_t(int act, bool train, const void* y, const float* gamma, const float* beta, float* rm, float* rv,
+                       int64_t* nbt, void* out, float* sm, float* sr, float eps, float mom, char* ws,
+                       const lmnet_bn_dims* d, cudaStream_t st) {
+    switch (act) {
+        case LMNET_ACT_NONE: return bn_launch_fwd_cl<T, LMNET_ACT_NONE>(train, y, gamma, beta, rm, rv, nbt, out, sm, sr, eps, mom, ws, d, st);
+        case LMNET_ACT_HARDSWISH: return bn_launch_fwd_cl<T, LMNET_ACT_HARDSWISH>(train, y, gamma, beta, rm, rv, nbt, out, sm, sr, eps, mom, ws, d, st);
+        case LMNET_ACT_GELU: return bn_launch_fwd_cl<T, LMNET_ACT_GELU>(train, y, gamma, beta, rm, rv, nbt, out, sm, sr, eps, mom, ws, d, st);
+        case LMNET_ACT_RELU: return bn_launch_fwd_cl<T, LMNET_ACT_RELU>(train, y, gamma, beta, rm, rv, nbt, out, sm, sr, eps, mom, ws, d, st);
+        default: return LMNET_ERR_UNSUPPORTED;
+    }
+}
+template <typename T>
+static int bn_bwd_cl_t(int act, const void* y, const void* dout, const float* gamma, const float* beta, const float* sm,
+                       const float* sr, void* dy, float* dgamma, float* dbeta, char* ws, const lmnet_bn_dims* d, cudaStream_t st) {
+    switch (act) {
+        case LMNET_ACT_NONE: return bn_launch_bwd_cl<T, LMNET_ACT_NONE>(y, dout, gamma, beta, sm, sr, dy, dgamma, dbeta, ws, d, st);
+        case LMNET_ACT_HARDSWISH: return bn_launch_bwd_cl<T, LMNET_ACT_HARDSWISH>(y, dout, gamma, beta, sm, sr, dy, dgamma, dbeta, ws, d, st);
+        case LMNET_ACT_GELU: return bn_launch_bwd_cl<T, LMNET_ACT_GELU>(y, dout, gamma, beta, sm, sr, dy, dgamma, dbeta, ws, d, st);
+        case LMNET_ACT_RELU: return bn_launch_bwd_cl<T, LMNET_ACT_RELU>(y, dout, gamma, beta, sm, sr, dy, dgamma, dbeta, ws, d, st);
+        default: return LMNET_ERR_UNSUPPORTED;
+    }
 }
 
 #define BN_DISPATCH_ACT(T, VEC, CALL)                                                      \
@@ -404,6 +642,53 @@ extern "C" int lmnet_bn_act_bwd(const void* y, const void* dout, const float* ga
         case LMNET_F32: return bn_bwd_t<float>(vec, act, y, dout, gamma, beta, save_mean, save_rstd, dy, dgamma, dbeta, (char*)workspace, dims, st);
         case LMNET_BF16: return bn_bwd_t<__nv_bfloat16>(vec, act, y, dout, gamma, beta, save_mean, save_rstd, dy, dgamma, dbeta, (char*)workspace, dims, st);
         case LMNET_F16: return bn_bwd_t<__half>(vec, act, y, dout, gamma, beta, save_mean, save_rstd, dy, dgamma, dbeta, (char*)workspace, dims, st);
+        default: return LMNET_ERR_UNSUPPORTED;
+    }
+}
+
+// ---- channels-last entry points: y / out / dout / dy are [B, HW, C] (C contiguous); same workspace query ----
+extern "C" int lmnet_bn_act_cl_supported(const lmnet_bn_dims* dims, int dtype) {
+    if (bn_validate(dims) != LMNET_OK) return 0;
+    BnGeomCl g;
+    return bn_geom_cl(dims, dtype == LMNET_F32 ? 4 : 2, g) ? 1 : 0;
+}
+
+extern "C" int lmnet_bn_act_cl_fwd(const void* y, const float* gamma, const float* beta, float* running_mean,
+                                   float* running_var, int64_t* num_batches_tracked, void* out, float* save_mean,
+                                   float* save_rstd, float eps, float momentum, int training, int act,
+                                   void* workspace, size_t workspace_bytes, const lmnet_bn_dims* dims, int dtype,
+                                   void* stream) {
+    int rc = bn_validate(dims);
+    if (rc != LMNET_OK) return rc;
+    if (!y || !out || !workspace) return LMNET_ERR_INVALID_ARG;
+    if (training && (!save_mean || !save_rstd)) return LMNET_ERR_INVALID_ARG;
+    if (!training && (!running_mean || !running_var)) return LMNET_ERR_INVALID_ARG;
+    if ((running_mean == nullptr) != (running_var == nullptr)) return LMNET_ERR_INVALID_ARG;
+    if (workspace_bytes < bn_ws(dims).total) return LMNET_ERR_WORKSPACE;
+    if ((uintptr_t)y % 16 || (uintptr_t)out % 16) return LMNET_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (dtype) {
+        case LMNET_F32: return bn_fwd_cl_t<float>(act, training != 0, y, gamma, beta, running_mean, running_var, num_batches_tracked, out, save_mean, save_rstd, eps, momentum, (char*)workspace, dims, st);
+        case LMNET_BF16: return bn_fwd_cl_t<__nv_bfloat16>(act, training != 0, y, gamma, beta, running_mean, running_var, num_batches_tracked, out, save_mean, save_rstd, eps, momentum, (char*)workspace, dims, st);
+        case LMNET_F16: return bn_fwd_cl_t<__half>(act, training != 0, y, gamma, beta, running_mean, running_var, num_batches_tracked, out, save_mean, save_rstd, eps, momentum, (char*)workspace, dims, st);
+        default: return LMNET_ERR_UNSUPPORTED;
+    }
+}
+
+extern "C" int lmnet_bn_act_cl_bwd(const void* y, const void* dout, const float* gamma, const float* beta,
+                                   const float* save_mean, const float* save_rstd, void* dy, float* dgamma,
+                                   float* dbeta, int act, void* workspace, size_t workspace_bytes,
+                                   const lmnet_bn_dims* dims, int dtype, void* stream) {
+    int rc = bn_validate(dims);
+    if (rc != LMNET_OK) return rc;
+    if (!y || !dout || !dy || !save_mean || !save_rstd || !workspace) return LMNET_ERR_INVALID_ARG;
+    if (workspace_bytes < bn_ws(dims).total) return LMNET_ERR_WORKSPACE;
+    if ((uintptr_t)y % 16 || (uintptr_t)dout % 16 || (uintptr_t)dy % 16) return LMNET_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (dtype) {
+        case LMNET_F32: return bn_bwd_cl_t<float>(act, y, dout, gamma, beta, save_mean, save_rstd, dy, dgamma, dbeta, (char*)workspace, dims, st);
+        case LMNET_BF16: return bn_bwd_cl_t<__nv_bfloat16>(act, y, dout, gamma, beta, save_mean, save_rstd, dy, dgamma, dbeta, (char*)workspace, dims, st);
+        case LMNET_F16: return bn_bwd_cl_t<__half>(act, y, dout, gamma, beta, save_mean, save_rstd, dy, dgamma, dbeta, (char*)workspace, dims, st);
         default: return LMNET_ERR_UNSUPPORTED;
     }
 }

@@ -849,7 +849,7 @@ struct DwWs {
     size_t part, coef, pool_part, pfin, cb, du, total;
 };
 // CTAs per SM the TMA kernels are built for (__launch_bounds__ / shared memory): their grids are ONE wave
-constexpr int kStatsOcc = 4, kApplyOcc = 4, kReduceOcc = 3, kDxOcc = 2;
+constexpr int kStatsOcc = 4, kApplyOcc = 4, kReduceOcc = 3, kDxOcc = LMNET_DX_OCC;
 static DwWs dw_ws_layout(const lmnet_dw_dims* d, size_t esize) {
     size_t ncta = 0;
     const DwGeom gs[5] = {dw_geom(d, kFwdTH, kFwdTW), dw_geom(d, kMmaTH, kMmaTW, kStatsOcc, kFwdShift), dw_geom(d, kMmaTH, kMmaTW, kReduceOcc, kFwdShift),
@@ -920,7 +920,7 @@ static int dw_train_fwd(const void* x, const lmnet_dw_params* p, void* u, void* 
     const bool use_mma = dw_mma_ok<T>(d, x);
     int rc = LMNET_OK;
     if constexpr (sizeof(T) == 2) {
-        if (dw_tma_ok<T>(d, {x})) {
+        if (dw_tma_ok<T>(d, {x, z, u ? u : z})) {
             CUtensorMap tm_x;
             if (!tma_make_planes_map(&tm_x, x, (int64_t)d->B * d->E, d->H, d->W, kMmaTileRows, kMmaPitch)) return LMNET_ERR_LAUNCH;
             static std::atomic<size_t> granted_s[kMaxDevices], granted_a[kMaxDevices];
@@ -933,7 +933,11 @@ static int dw_train_fwd(const void* x, const lmnet_dw_params* p, void* u, void* 
             LMNET_LAUNCH(KID_DW_FIN_FWD, st, 0, (dw_fin_fwd_kernel<<<g.E, 32, 0, st>>>(part, ncta_s, *p, save_mean, save_rstd, coef, eps, momentum,
                                                              nbt ? nbt[0] : nullptr, nbt ? nbt[1] : nullptr,
                                                              nbt ? nbt[2] : nullptr, nbt ? nbt[3] : nullptr, g)));
-            LMNET_LAUNCH(KID_DW_APPLY, st, 2 * t_bytes, (dw_apply_tma_kernel<T><<<grid_s, kTmaThreads, kApplySmem, st>>>(tm_x, coef, (T*)u, (T*)z, pool ? pool_part : nullptr, gs)));
+            CUtensorMap tm_u, tm_z;
+            if (!tma_make_planes_map(&tm_u, u ? u : z, (int64_t)d->B * d->E, d->H, d->W, kStageRows, kStageCols) ||
+                !tma_make_planes_map(&tm_z, z, (int64_t)d->B * d->E, d->H, d->W, kStageRows, kStageCols))
+                return LMNET_ERR_LAUNCH;
+            LMNET_LAUNCH(KID_DW_APPLY, st, 2 * t_bytes, (dw_apply_tma_kernel<T><<<grid_s, kTmaThreads, kApplySmem, st>>>(tm_x, tm_u, tm_z, coef, (T*)u, (T*)z, pool ? pool_part : nullptr, gs)));
             if (pool) {
                 const int n = g.B * g.E;
                 LMNET_LAUNCH(KID_DW_POOL_FIN, st, 0, (dw_pool_fin_kernel<<<(n + 127) / 128, 128, 0, st>>>(pool_part, ncta_s * kDwWarps, 1.f / ((float)g.H * g.W), pool, n)));
@@ -984,15 +988,17 @@ static int dw_eval_fwd(const void* x, const lmnet_dw_params* p, const float* bia
     const bool use_mma = dw_mma_ok<T>(d, x);
     int rc = LMNET_OK;
     if constexpr (sizeof(T) == 2) {
-        if (dw_tma_ok<T>(d, {x})) {
-            CUtensorMap tm_x;
-            if (!tma_make_planes_map(&tm_x, x, (int64_t)d->B * d->E, d->H, d->W, kMmaTileRows, kMmaPitch)) return LMNET_ERR_LAUNCH;
+        if (dw_tma_ok<T>(d, {x, z})) {
+            CUtensorMap tm_x, tm_z;
+            if (!tma_make_planes_map(&tm_x, x, (int64_t)d->B * d->E, d->H, d->W, kMmaTileRows, kMmaPitch) ||
+                !tma_make_planes_map(&tm_z, z, (int64_t)d->B * d->E, d->H, d->W, kStageRows, kStageCols))
+                return LMNET_ERR_LAUNCH;
             static std::atomic<size_t> granted_a[kMaxDevices];
             if (!dw_tma_smem(dw_apply_tma_kernel<T>, kApplySmem, granted_a)) return LMNET_ERR_LAUNCH;
             const DwGeom gs = dw_geom(d, kMmaTH, kMmaTW, kApplyOcc, kFwdShift);
             const int ncta_s = gs.stripes * gs.bands;
             const dim3 grid_s(gs.stripes, gs.bands, gs.E);
-            LMNET_LAUNCH(KID_DW_APPLY, st, 2 * t_bytes, (dw_apply_tma_kernel<T><<<grid_s, kTmaThreads, kApplySmem, st>>>(tm_x, coef, (T*)nullptr, (T*)z, pool ? pool_part : nullptr, gs)));
+            LMNET_LAUNCH(KID_DW_APPLY, st, 2 * t_bytes, (dw_apply_tma_kernel<T><<<grid_s, kTmaThreads, kApplySmem, st>>>(tm_x, tm_z, tm_z, coef, (T*)nullptr, (T*)z, pool ? pool_part : nullptr, gs)));
             if (pool) {
                 const int n = g.B * g.E;
                 LMNET_LAUNCH(KID_DW_POOL_FIN, st, 0, (dw_pool_fin_kernel<<<(n + 127) / 128, 128, 0, st>>>(pool_part, ncta_s * kDwWarps, 1.f / ((float)g.H * g.W), pool, n)));

@@ -233,19 +233,32 @@ dw_stats_tma_kernel(const __grid_constant__ CUtensorMap tm_x, lmnet_dw_params p,
 }
 
 // ---------------------------------------------------------------------------------------------------
-// apply pass: u = merged5x5(x) + bias, z = GELU(u), per-warp pool partial sums
+// apply pass: u = merged5x5(x) + bias, z = GELU(u), per-warp pool partial sums.
+//
+// Output path (ablation on B200: with fragment stores straight to global memory — 4 bytes per lane, 8 rows x 16 B per
+// instruction — each of the two output streams cost ~90 us of a 196 us kernel; the LSU store path, not HBM, was the
+// limit).  A warp's 16 x 32 output block starts 2 columns past a 16-byte boundary (the shifted stripe grid), so each
+// warp stages the three fully owned 16-byte chunks of every row (24 of its 32 columns) in shared memory and ONE lane
+// hands the 16 x 24 box to the TMA unit (cp.async.bulk.tensor store: full-line writes, no LSU work, clipped at the
+// image edge by the tensor map); the 6 + 2 boundary columns shared with the neighbouring warps / stripes keep the
+// narrow stores.  The staging boxes are double-buffered per warp; `cp.async.bulk.wait_group.read` guards their reuse.
 // ---------------------------------------------------------------------------------------------------
 constexpr int kApplyStages = 4;
-constexpr size_t kApplySmem = 128 + (size_t)kApplyStages * kXSlotBytes + 2 * kApplyStages * 8;
+constexpr int kStageCols = 24, kStageRows = 16;                                    // per-warp TMA-store box
+constexpr int kStageBoxBytes = kStageRows * kStageCols * 2;                        // 768 (a multiple of 128)
+constexpr int kApplyStagingBytes = kDwWarps * 2 /*buffers*/ * 2 /*u, z*/ * kStageBoxBytes;
+constexpr size_t kApplySmem = 128 + (size_t)kApplyStages * kXSlotBytes + kApplyStagingBytes + 2 * kApplyStages * 8;
 
 template <typename T>
 __global__ void __launch_bounds__(kTmaThreads, 4)
-dw_apply_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __restrict__ coef, T* __restrict__ u_out,
+dw_apply_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_u,
+                    const __grid_constant__ CUtensorMap tm_z, const float* __restrict__ coef, T* __restrict__ u_out,
                     T* __restrict__ z_out, float* __restrict__ pool_part /* [B*E][ncta*4] or null */, DwGeom g) {
     constexpr int S = kApplyStages;
     extern __shared__ unsigned char dw_smem_raw[];
     unsigned char* smem = align128(dw_smem_raw);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + S * kXSlotBytes);
+    unsigned char* s_stage = smem + S * kXSlotBytes;
+    uint64_t* full = reinterpret_cast<uint64_t*>(s_stage + kApplyStagingBytes);
     uint64_t* empty = full + S;
     const int e = blockIdx.z, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int c0 = blockIdx.x * kMmaTW - kFwdShift;
@@ -288,6 +301,13 @@ dw_apply_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __res
     const float bias = __ldg(coef + e * 26 + 25);
     const int gq = lane >> 2, tq = lane & 3;
     const int ncta = gridDim.x * gridDim.y, cta = blockIdx.y * gridDim.x + blockIdx.x;
+    const bool want_u = u_out != nullptr;
+    if (lane == 0) {
+        tma_prefetch_desc(&tm_z);
+        if (want_u) tma_prefetch_desc(&tm_u);
+    }
+    // this warp's staging boxes: [buffer][u | z][16][24]
+    T* stage_w = reinterpret_cast<T*>(s_stage + warp * 4 * kStageBoxBytes);
     float psum = 0.f;
     RingPos<S> pos;
     TileWalk tw;
@@ -300,7 +320,6 @@ dw_apply_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __res
         const int col_lo = c0 + 32 * wc + 2 * tq;
         const int64_t base = ((int64_t)b * g.E + e) * g.H * g.W + (int64_t)row_lo * g.W + col_lo;
         const int64_t row8 = (int64_t)8 * g.W;
-        const bool full_tile = tr + kMmaTH <= band1 && c0 >= 0 && c0 + kMmaTW <= g.W;
         float acc[4][4];
 #pragma unroll
         for (int cb = 0; cb < 4; ++cb) acc[cb][0] = acc[cb][1] = acc[cb][2] = acc[cb][3] = bias;
@@ -315,25 +334,63 @@ dw_apply_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __res
                 MmaOp<T>::run(acc[cb], A, Blo[a]);
             }
         __syncwarp();
-        if (lane == 0) mbar_arrive(empty + pos.slot);      // the tile is consumed: the epilogue overlaps the next copy
+        if (lane == 0) {
+            mbar_arrive(empty + pos.slot);      // the tile is consumed: the epilogue overlaps the next copy
+            tma_store_wait_read<1>();           // the store issued two tiles ago no longer reads this staging buffer
+        }
+        __syncwarp();
+        T* st_u = stage_w + (t & 1) * 2 * kStageRows * kStageCols;
+        T* st_z = st_u + kStageRows * kStageCols;
+        // columns 6..29 of the warp's block go through the staging box; the boundary columns 0..5 (block 0, tq < 3) and
+        // 30..31 (block 3, tq == 3) go straight to global memory, merged into ONE store per row half and tensor
+        uint32_t edge_u[2], edge_z[2];
 #pragma unroll
         for (int cb = 0; cb < 4; ++cb) {
-            const bool cok = full_tile || (col_lo + 8 * cb >= 0 && col_lo + 8 * cb < g.W);   // W even: pair in or out together
+            const bool staged = (cb == 1 || cb == 2) || (cb == 0 && tq == 3) || (cb == 3 && tq < 3);
+            const int scol = 8 * cb + 2 * tq - 6;
+            const bool cok = col_lo + 8 * cb >= 0 && col_lo + 8 * cb < g.W;     // W even: pair in or out together
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                if (cok && (full_tile || row_lo + 8 * h < band1)) {
-                    const int64_t off = base + 8 * cb + h * row8;
-                    const uint32_t up = MmaOp<T>::pack(acc[cb][2 * h], acc[cb][2 * h + 1]);
-                    if (u_out != nullptr) *reinterpret_cast<uint32_t*>(u_out + off) = up;
-                    const T* ur = reinterpret_cast<const T*>(&up);          // GELU of the value as stored
-                    float z0, z1;
-                    gelu_fast2(to_f(ur[0]), to_f(ur[1]), z0, z1);
-                    const uint32_t zp = MmaOp<T>::pack(z0, z1);
-                    *reinterpret_cast<uint32_t*>(z_out + off) = zp;
+                const uint32_t up = MmaOp<T>::pack(acc[cb][2 * h], acc[cb][2 * h + 1]);
+                const T* ur = reinterpret_cast<const T*>(&up);              // GELU of the value as stored
+                float z0, z1;
+                gelu_fast2(to_f(ur[0]), to_f(ur[1]), z0, z1);
+                const uint32_t zp = MmaOp<T>::pack(z0, z1);
+                if (staged) {
+                    const int so = (gq + 8 * h) * kStageCols + scol;
+                    *reinterpret_cast<uint32_t*>(st_u + so) = up;
+                    *reinterpret_cast<uint32_t*>(st_z + so) = zp;
+                } else {
+                    edge_u[h] = up;
+                    edge_z[h] = zp;
+                }
+                if (cok && row_lo + 8 * h < band1) {
                     const T* zr = reinterpret_cast<const T*>(&zp);          // pool of the values as stored
                     psum += to_f(zr[0]) + to_f(zr[1]);
                 }
             }
+        }
+        {
+            const int ecol = col_lo + (tq == 3 ? 24 : 0);                    // block 3 for tq == 3, block 0 otherwise
+            if (ecol >= 0 && ecol < g.W) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+                    if (row_lo + 8 * h < band1) {
+                        const int64_t off = base + (tq == 3 ? 24 : 0) + h * row8;
+                        if (want_u) *reinterpret_cast<uint32_t*>(u_out + off) = edge_u[h];
+                        *reinterpret_cast<uint32_t*>(z_out + off) = edge_z[h];
+                    }
+            }
+        }
+        fence_proxy_async();                    // generic-proxy writes -> visible to the TMA store
+        __syncwarp();
+        if (lane == 0) {
+            // rows beyond the image and columns beyond W are clipped by the tensor map; bands are multiples of the tile
+            // height, so rows >= band1 only occur at the bottom of the image
+            const int gc = c0 + 32 * wc + 6, gr = tr + 16 * wr, plane = b * g.E + e;
+            if (want_u) tma_store_3d(&tm_u, st_u, gc, gr, plane);
+            tma_store_3d(&tm_z, st_z, gc, gr, plane);
+            tma_store_commit();
         }
         if (last && pool_part != nullptr) {
             const float tsum = warp_sum(psum);
@@ -343,6 +400,7 @@ dw_apply_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __res
         pos.advance();
         tw.next(ntr);
     }
+    if (lane == 0) tma_store_wait_all<0>();     // shared memory must stay alive until the last stores have read it
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -429,7 +487,9 @@ dw_bwd_reduce_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_
                     float g0, g1;
                     gelu_grad_fast2(to_f(ue[0]), to_f(ue[1]), g0, g1);
                     packed = MmaOp<T>::pack((to_f(ze[0]) + dp) * g0, (to_f(ze[1]) + dp) * g1);
+#if !defined(LMNET_DBG_NO_DU)
                     *reinterpret_cast<uint32_t*>(du_out + poff + (int64_t)(tr + trow) * g.W + c0 + bcol) = packed;
+#endif
                     const T* de = reinterpret_cast<const T*>(&packed);
                     sdu += to_f(de[0]) + to_f(de[1]);             // exactly what the dx pass reads back
                 }
@@ -490,6 +550,9 @@ dw_bwd_reduce_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_
 //   named barrier over the 128 compute threads (the dy tiles are double-buffered: one barrier per tile);
 //   phase 2: dx by Toeplitz MMAs with the flipped taps over the four dy tiles.
 // ---------------------------------------------------------------------------------------------------
+#ifndef LMNET_DX_OCC
+#define LMNET_DX_OCC 2
+#endif
 constexpr int kDxStages = 3;
 constexpr int kDxSlotBytes = kXSlotBytes + kRTileBytes;                 // x | du
 constexpr int kDyTileElems = kMmaTileRows * kMmaPitch;                  // one branch: 36 x 72
@@ -498,7 +561,7 @@ constexpr size_t kDxTmaSmem = 128 + (size_t)kDxStages * kDxSlotBytes + 2 * kDySe
 static_assert(2 * kDySetBytes >= kDwWarps * 12 * 128 * 4, "the Gram fragments are staged in the dy tiles after the loop");
 
 template <typename T>
-__global__ void __launch_bounds__(kTmaThreads, 2)
+__global__ void __launch_bounds__(kTmaThreads, LMNET_DX_OCC)
 dw_bwd_dx_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_du, lmnet_dw_params p,
                      const float* __restrict__ cb, T* __restrict__ dx, float* __restrict__ part /* [E][ncta][40] */, DwGeom g) {
     constexpr int S = kDxStages;
@@ -674,9 +737,13 @@ dw_bwd_dx_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {
                             const int r = 16 * wr + gq + 8 * h, row = tr + r;
+#if !defined(LMNET_DBG_NO_DX)
                             if (r < kDxTH && row < band1)
                                 *reinterpret_cast<uint32_t*>(dx + poff + (int64_t)row * g.W + col) =
                                     MmaOp<T>::pack(acc[cbk][2 * h], acc[cbk][2 * h + 1]);
+#else
+                            if (r < kDxTH && row < band1 && acc[cbk][2 * h] == 123.456f) dx[0] = from_f<T>(1.f);
+#endif
                         }
                     }
                 }

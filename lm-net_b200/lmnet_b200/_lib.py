@@ -107,6 +107,13 @@ def lib():
     L.lmnet_bn_act_workspace_bytes.argtypes = [pbd]
     L.lmnet_bn_act_fwd.argtypes = [c_void_p] * 9 + [c_float, c_float, c_int, c_int, c_void_p, c_size_t, pbd, c_int, c_void_p]
     L.lmnet_bn_act_bwd.argtypes = [c_void_p] * 9 + [c_int, c_void_p, c_size_t, pbd, c_int, c_void_p]
+    L.lmnet_bn_act_cl_supported.argtypes = [pbd, c_int]
+    L.lmnet_bn_act_cl_fwd.argtypes = L.lmnet_bn_act_fwd.argtypes
+    L.lmnet_bn_act_cl_bwd.argtypes = L.lmnet_bn_act_bwd.argtypes
+    L.lmnet_wgrad_1x1_cl_supported.argtypes = [POINTER(WgradDims), c_int, c_int, c_int]
+    L.lmnet_wgrad_1x1_cl_workspace_bytes.restype = c_size_t
+    L.lmnet_wgrad_1x1_cl_workspace_bytes.argtypes = [POINTER(WgradDims), c_int, c_int]
+    L.lmnet_wgrad_1x1_cl.argtypes = [c_void_p] * 5 + [c_void_p, c_size_t, POINTER(WgradDims), c_int, c_int, c_int, c_void_p]
     L.lmnet_layer_norm_supported.argtypes = [c_int]
     L.lmnet_layer_norm_workspace_bytes.restype = c_size_t
     L.lmnet_layer_norm_workspace_bytes.argtypes = [c_int64, c_int]

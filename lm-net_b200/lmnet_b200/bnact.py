@@ -32,23 +32,37 @@ def _f32(t):
     return t if (t.dtype == torch.float32 and t.is_contiguous()) else t.float().contiguous()
 
 
+def _is_cl(t: torch.Tensor) -> bool:
+    return t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last) and not t.is_contiguous()
+
+
+def _cl_ok(y) -> bool:
+    """channels-last tensor that the channels-last kernels cover (otherwise: NCHW kernels on a contiguous copy)."""
+    if not _is_cl(y) or y.dtype not in L._DTYPES:
+        return False
+    return bool(L.lib().lmnet_bn_act_cl_supported(L.byref(_dims(y)), L._DTYPES[y.dtype]))
+
+
 class _BNActTrain(torch.autograd.Function):
     @staticmethod
     @custom_fwd(device_type="cuda")
     def forward(ctx, y, gamma, beta, running, eps, momentum, act):
         L.require_cuda(y)
-        y = y.contiguous()
+        ctx.cl = _cl_ok(y)
+        if not ctx.cl:
+            y = y.contiguous()
         g32, b32 = _f32(gamma), _f32(beta)
         rmean, rvar, nbt = running
         C = y.shape[1]
         dims = _dims(y)
-        out = torch.empty_like(y)
+        out = torch.empty_like(y)          # preserves the memory format (channels-last stays channels-last)
         save_mean = torch.empty(C, dtype=torch.float32, device=y.device)
         save_rstd = torch.empty(C, dtype=torch.float32, device=y.device)
         ws = _ws(dims, y.device)
-        rc = L.lib().lmnet_bn_act_fwd(L.ptr(y), L.ptr(g32), L.ptr(b32), L.ptr(rmean), L.ptr(rvar), L.ptr(nbt),
-                                      L.ptr(out), L.ptr(save_mean), L.ptr(save_rstd), float(eps), float(momentum),
-                                      1, act, L.ptr(ws), ws.numel(), L.byref(dims), L.dtype_code(y), L.stream_ptr())
+        fn = L.lib().lmnet_bn_act_cl_fwd if ctx.cl else L.lib().lmnet_bn_act_fwd
+        rc = fn(L.ptr(y), L.ptr(g32), L.ptr(b32), L.ptr(rmean), L.ptr(rvar), L.ptr(nbt),
+                L.ptr(out), L.ptr(save_mean), L.ptr(save_rstd), float(eps), float(momentum),
+                1, act, L.ptr(ws), ws.numel(), L.byref(dims), L.dtype_code(y), L.stream_ptr())
         L.check(rc, "bn_act_fwd")
         ctx.save_for_backward(y, g32, b32, save_mean, save_rstd)
         ctx.act = act
@@ -61,14 +75,16 @@ class _BNActTrain(torch.autograd.Function):
         y, g32, b32, save_mean, save_rstd = ctx.saved_tensors
         dims = _dims(y)
         C = y.shape[1]
-        dout = dout.to(y.dtype).contiguous()
+        dout = dout.to(y.dtype)
+        dout = dout.contiguous(memory_format=torch.channels_last) if ctx.cl else dout.contiguous()
         dy = torch.empty_like(y)
         dgamma = torch.empty(C, dtype=torch.float32, device=y.device)
         dbeta = torch.empty(C, dtype=torch.float32, device=y.device)
         ws = _ws(dims, y.device)
-        rc = L.lib().lmnet_bn_act_bwd(L.ptr(y), L.ptr(dout), L.ptr(g32), L.ptr(b32), L.ptr(save_mean),
-                                      L.ptr(save_rstd), L.ptr(dy), L.ptr(dgamma), L.ptr(dbeta), ctx.act,
-                                      L.ptr(ws), ws.numel(), L.byref(dims), L.dtype_code(y), L.stream_ptr())
+        fn = L.lib().lmnet_bn_act_cl_bwd if ctx.cl else L.lib().lmnet_bn_act_bwd
+        rc = fn(L.ptr(y), L.ptr(dout), L.ptr(g32), L.ptr(b32), L.ptr(save_mean),
+                L.ptr(save_rstd), L.ptr(dy), L.ptr(dgamma), L.ptr(dbeta), ctx.act,
+                L.ptr(ws), ws.numel(), L.byref(dims), L.dtype_code(y), L.stream_ptr())
         L.check(rc, "bn_act_bwd")
         gd, bd = ctx.meta
         return (dy, None if gd is None else dgamma.to(gd), None if bd is None else dbeta.to(bd), None, None, None, None)
@@ -96,13 +112,16 @@ def bn_act(bn: torch.nn.BatchNorm2d, y: torch.Tensor, act: str = "none") -> torc
     if torch.is_grad_enabled() and (y.requires_grad or (bn.weight is not None and bn.weight.requires_grad)):
         raise NotImplementedError("gradients through eval-mode fused BatchNorm are not implemented; use torch.no_grad()")
     L.require_cuda(y)
-    y = y.contiguous()
+    cl = _cl_ok(y)
+    if not cl:
+        y = y.contiguous()
     dims = _dims(y)
     out = torch.empty_like(y)
     ws = _ws(dims, y.device)
-    rc = L.lib().lmnet_bn_act_fwd(L.ptr(y), L.ptr(_f32(bn.weight)), L.ptr(_f32(bn.bias)), L.ptr(_f32(bn.running_mean)),
-                                  L.ptr(_f32(bn.running_var)), None, L.ptr(out), None, None, float(bn.eps), 0.0, 0, code,
-                                  L.ptr(ws), ws.numel(), L.byref(dims), L.dtype_code(y), L.stream_ptr())
+    fn = L.lib().lmnet_bn_act_cl_fwd if cl else L.lib().lmnet_bn_act_fwd
+    rc = fn(L.ptr(y), L.ptr(_f32(bn.weight)), L.ptr(_f32(bn.bias)), L.ptr(_f32(bn.running_mean)),
+            L.ptr(_f32(bn.running_var)), None, L.ptr(out), None, None, float(bn.eps), 0.0, 0, code,
+            L.ptr(ws), ws.numel(), L.byref(dims), L.dtype_code(y), L.stream_ptr())
     L.check(rc, "bn_act_fwd")
     return out
 

@@ -111,18 +111,156 @@ class _PointwiseShortcut(torch.autograd.Function):
         return dz, dgate, dx, dwpw, dwsc, dbias
 
 
+def _wgrad_cl(A, B1, B2, a_cl, b1_cl):
+    """Mixed-layout weight gradient.  A: planes [B,M,P] or channels-last [B,P,M]; B1 likewise with N1; B2 (or None) is
+    channels-last [B,P,N2].  Returns (dW [B,M,N1+N2] fp32, drow [B,M] fp32)."""
+    Bn = A.shape[0]
+    M, P = (A.shape[2], A.shape[1]) if a_cl else (A.shape[1], A.shape[2])
+    N1 = B1.shape[2] if b1_cl else B1.shape[1]
+    N2 = 0 if B2 is None else B2.shape[2]
+    dims = L.WgradDims(Bn, M, N1, N2, P)
+    dW = torch.empty(Bn, M, N1 + N2, dtype=torch.float32, device=A.device)
+    drow = torch.empty(Bn, M, dtype=torch.float32, device=A.device)
+    n = L.lib().lmnet_wgrad_1x1_cl_workspace_bytes(L.byref(dims), int(a_cl), int(b1_cl))
+    ws = torch.empty(max(int(n), 16), dtype=torch.uint8, device=A.device)
+    rc = L.lib().lmnet_wgrad_1x1_cl(L.ptr(A), L.ptr(B1), L.ptr(B2), L.ptr(dW), L.ptr(drow), L.ptr(ws), ws.numel(),
+                                    L.byref(dims), int(a_cl), int(b1_cl), L.dtype_code(A), L.stream_ptr())
+    L.check(rc, "wgrad_1x1_cl")
+    return dW, drow
+
+
+def wgrad_cl_supported(B, M, N1, N2, P, a_cl, b1_cl, dtype) -> bool:
+    if dtype not in (torch.bfloat16, torch.float16):
+        return False
+    dims = L.WgradDims(B, M, N1, N2, P)
+    return bool(L.lib().lmnet_wgrad_1x1_cl_supported(L.byref(dims), int(a_cl), int(b1_cl), L._DTYPES[dtype]))
+
+
+def is_channels_last(t: torch.Tensor) -> bool:
+    return t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last) and not t.is_contiguous()
+
+
+def _pixels(x_cl):
+    """[B,C,H,W] channels-last tensor -> its memory as [B, H*W, C] (a view)."""
+    B, C, H, W = x_cl.shape
+    return x_cl.permute(0, 2, 3, 1).reshape(B, H * W, C)
+
+
+def _as_cl(t_bpc, H, W):
+    """[B, H*W, C] contiguous -> logical [B,C,H,W] in channels-last memory (a view)."""
+    B, P, C = t_bpc.shape
+    return t_bpc.view(B, H, W, C).permute(0, 3, 1, 2)
+
+
+class _Expand1x1Cl(torch.autograd.Function):
+    """x channels-last [B,K,H,W] -> y[b] = W @ x[b]^T + bias as NCHW planes [B,M,H,W] (what the fused BatchNorm and
+    the depthwise section read).  The layout change rides on the GEMM's operand order: no transposed copy exists."""
+
+    @staticmethod
+    @custom_fwd(device_type="cuda")
+    def forward(ctx, x, w, bias):
+        B, K, H, Wd = x.shape
+        M = w.shape[0]
+        xp = _pixels(x)                                                    # [B, P, K]
+        wc = w.to(x.dtype).unsqueeze(0).expand(B, M, K)
+        xt = xp.transpose(1, 2)                                            # [B, K, P] view
+        y = torch.baddbmm(bias.to(x.dtype).view(1, M, 1), wc, xt) if bias is not None else torch.bmm(wc, xt)
+        ctx.save_for_backward(x, w)
+        ctx.has_bias = bias is not None
+        ctx.bias_dtype = None if bias is None else bias.dtype
+        return y.view(B, M, H, Wd)
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        B, K, H, Wd = x.shape
+        M = w.shape[0]
+        dyf = dy.to(x.dtype).contiguous().view(B, M, H * Wd)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = _as_cl(torch.bmm(dyf.transpose(1, 2), w.to(x.dtype).unsqueeze(0).expand(B, M, K)), H, Wd)
+        dW, drow = _wgrad_cl(dyf, _pixels(x), None, False, True)
+        dw = dW.sum(0).to(w.dtype)
+        db = drow.sum(0).to(ctx.bias_dtype) if ctx.has_bias else None
+        return dx, dw, db
+
+
+class _PointwiseShortcutCl(torch.autograd.Function):
+    """out = (Wpw * gate[b]) @ z[b] + Wsc @ x[b] + bias with z as NCHW planes, x and out channels-last."""
+
+    @staticmethod
+    @custom_fwd(device_type="cuda")
+    def forward(ctx, z, gate, x, wpw, wsc, bias):
+        B, E, H, Wd = z.shape
+        Cin, Cout = x.shape[1], wpw.shape[0]
+        P = H * Wd
+        dt = z.dtype
+        wg = (wpw.float().unsqueeze(0) * gate.float().unsqueeze(1)).to(dt)            # [B, Cout, E]
+        xp = _pixels(x)                                                                # [B, P, Cin]
+        out = torch.baddbmm(bias.to(dt).view(1, 1, Cout), xp, wsc.to(dt).t().unsqueeze(0).expand(B, Cin, Cout))
+        out = torch.baddbmm(out, z.view(B, E, P).transpose(1, 2), wg.transpose(1, 2))  # [B, P, Cout]
+        ctx.save_for_backward(z, gate, x, wpw, wsc, wg)
+        ctx.bias_dtype = bias.dtype
+        return _as_cl(out, H, Wd)
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, dout):
+        z, gate, x, wpw, wsc, wg = ctx.saved_tensors
+        B, E, H, Wd = z.shape
+        Cin, Cout = x.shape[1], wpw.shape[0]
+        P = H * Wd
+        dt = z.dtype
+        do = _pixels(dout.to(dt).contiguous(memory_format=torch.channels_last))        # [B, P, Cout]
+        dz = torch.bmm(wg.transpose(1, 2), do.transpose(1, 2)).view(B, E, H, Wd)       # planes
+        dx = None
+        if ctx.needs_input_grad[2]:
+            dx = _as_cl(torch.bmm(do, wsc.to(dt).unsqueeze(0).expand(B, Cout, Cin)), H, Wd)
+        dW, drow = _wgrad_cl(do, z.view(B, E, P), _pixels(x), True, False)             # [B, Cout, E + Cin]
+        dWg = dW[:, :, :E]
+        dwpw = (dWg * gate.float().unsqueeze(1)).sum(0).to(wpw.dtype)
+        dgate = (dWg * wpw.float().unsqueeze(0)).sum(1).to(gate.dtype)                # [B, E]
+        dwsc = dW[:, :, E:].sum(0).to(wsc.dtype)
+        dbias = drow.sum(0).to(ctx.bias_dtype)
+        return dz, dgate, dx, dwpw, dwsc, dbias
+
+
+def _pad_channels(x, w, mult=4):
+    """Zero-pad the channel dimension of x [B,K,H,W] and the matching weight columns [M,K] to a multiple of `mult`
+    (the RGB input of the first block: 3 -> 4 channels, so that a pixel is one 8-byte vector)."""
+    K = x.shape[1]
+    pad = (-K) % mult
+    if pad == 0:
+        return x, w
+    return torch.nn.functional.pad(x, (0, 0, 0, 0, 0, pad)), torch.nn.functional.pad(w, (0, pad))
+
+
 def _compute_dtype(x):
     if torch.is_autocast_enabled("cuda"):
         return torch.get_autocast_dtype("cuda")
     return x.dtype
 
 
+def to_channels_last(x: torch.Tensor, dt=None) -> torch.Tensor:
+    dt = x.dtype if dt is None else dt
+    return x.to(dt).contiguous(memory_format=torch.channels_last)
+
+
 def expand_1x1(conv: torch.nn.Conv2d, x: torch.Tensor) -> torch.Tensor:
-    """conv(x) for a 1x1 convolution on a CUDA NCHW tensor (cuDNN through the module for uncovered shapes)."""
+    """conv(x) for a 1x1 convolution on a CUDA tensor; returns NCHW planes.  Channels-last inputs take the mixed-layout
+    path (no transposed copy); plain NCHW inputs the plane-wise one; cuDNN through the module for uncovered shapes."""
     L.require_cuda(x)
     dt = _compute_dtype(x)
     B, K, H, W = x.shape
     M = conv.out_channels
+    if is_channels_last(x) or (x.dim() == 4 and K == 1 and False):
+        w = conv.weight.view(M, K)
+        xpad, wpad = _pad_channels(x.to(dt), w)
+        if wgrad_cl_supported(B, M, xpad.shape[1], 0, H * W, False, True, dt):
+            if xpad is not x:
+                xpad = xpad.contiguous(memory_format=torch.channels_last)
+            return _Expand1x1Cl.apply(xpad, wpad, conv.bias)
     if wgrad_supported(B, M, K, 0, H * W, dt):
         return _Expand1x1.apply(x.to(dt).contiguous(), conv.weight.view(M, K), conv.bias)
     return conv(x)
@@ -134,6 +272,14 @@ def pointwise_shortcut(pw: torch.nn.Conv2d, sc: torch.nn.Conv2d, z, gate, x):
     dt = _compute_dtype(z)
     B, E, H, W = z.shape
     Cin, Cout = x.shape[1], pw.out_channels
+    if pw.bias is not None and sc.bias is not None and is_channels_last(x) and z.is_contiguous():
+        wsc = sc.weight.view(Cout, Cin)
+        xpad, wscpad = _pad_channels(x.to(dt), wsc)
+        if wgrad_cl_supported(B, Cout, E, xpad.shape[1], H * W, True, False, dt):
+            if xpad is not x:
+                xpad = xpad.contiguous(memory_format=torch.channels_last)
+            return _PointwiseShortcutCl.apply(z.to(dt), gate.reshape(B, E), xpad, pw.weight.view(Cout, E), wscpad,
+                                              pw.bias + sc.bias)
     if pw.bias is not None and sc.bias is not None and wgrad_supported(B, Cout, E, Cin, H * W, dt):
         bias = pw.bias + sc.bias
         return _PointwiseShortcut.apply(z.to(dt).contiguous(), gate.reshape(B, E), x.to(dt).contiguous(),

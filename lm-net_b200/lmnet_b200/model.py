@@ -153,7 +153,8 @@ class NeighborhoodTransformer(nn.Module):
         emb = self.patchembedding(_cl(x))          # NHWC conv output: the permute below is then a free view
         att = self.att1(layer_norm(self.norm1, emb)) + emb
         y = self.mlp(layer_norm(self.norm2, att)) + att
-        return y.permute(0, 3, 1, 2).contiguous()
+        # logical NCHW, channels-last memory: a free view (the consumers are channels-last as well)
+        return y.permute(0, 3, 1, 2) if y.is_cuda else y.permute(0, 3, 1, 2).contiguous()
 
 
 def _up2():
@@ -236,7 +237,8 @@ class GFT(nn.Module):
         emb = self.patchembedding(x)
         att = self.attention(self.norm1(emb)) + emb
         y = self.mlp(self.norm2(att)) + att
-        return self.conv(y.reshape(B, H, W, -1).permute(0, 3, 1, 2).contiguous())
+        y = y.reshape(B, H, W, -1).permute(0, 3, 1, 2)          # channels-last memory already: a free view on CUDA
+        return self.conv(y if y.is_cuda else y.contiguous())
 
 
 class PyramidPool(nn.Module):

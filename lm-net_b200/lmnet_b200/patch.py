@@ -31,7 +31,7 @@ def _natt_forward(self, x):
     emb = self.patchembedding(_cl(x))
     att = self.att1(layer_norm(self.norm1, emb)) + emb
     y = self.mlp(layer_norm(self.norm2, att)) + att
-    return y.permute(0, 3, 1, 2).contiguous()
+    return y.permute(0, 3, 1, 2) if y.is_cuda else y.permute(0, 3, 1, 2).contiguous()
 
 
 def _m3skip_forward(self, xl, xm, xs):

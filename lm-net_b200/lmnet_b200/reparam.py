@@ -22,7 +22,7 @@ from torch.amp import custom_bwd, custom_fwd
 
 from . import _lib as L
 from .bnact import bn_act, conv_bn_act
-from .conv1x1 import expand_1x1, pointwise_shortcut
+from .conv1x1 import _compute_dtype, expand_1x1, is_channels_last, pointwise_shortcut, to_channels_last
 
 
 def _dims(x):
@@ -206,7 +206,14 @@ def _is_1x1(conv) -> bool:
 
 
 def reparam_forward(self, x):
-    """Replacement for ReparamConv.forward (/root/reference/core/modules.py:586-600)."""
+    """Replacement for ReparamConv.forward (/root/reference/core/modules.py:586-600).
+
+    Layout: with 16-bit compute (autocast) the block takes and returns CHANNELS-LAST tensors — the layout cuDNN's 16-bit
+    3x3 convolutions and the neighbourhood-attention blocks on either side work in — while the expanded tensor inside the
+    block lives as NCHW planes (what the BatchNorm / depthwise kernels want).  Both layout changes ride on the 1x1 GEMMs'
+    operand order, so no transposed copy of any activation is made.  An NCHW input is converted once at entry."""
+    if x.is_cuda and x.dim() == 4 and _compute_dtype(x) in (torch.bfloat16, torch.float16) and not is_channels_last(x):
+        x = to_channels_last(x, _compute_dtype(x))
     ec = self.expand_conv
     if len(ec) == 3 and _is_1x1(ec[0]) and type(ec[1]) is torch.nn.BatchNorm2d and type(ec[2]) is torch.nn.Hardswish:
         x1 = bn_act(ec[1], expand_1x1(ec[0], x), "hardswish")     # plane-wise GEMM + fused BatchNorm + Hardswish

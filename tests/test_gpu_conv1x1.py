@@ -76,3 +76,68 @@ def test_fp32_inputs_take_the_module_path():
     conv = torch.nn.Conv2d(12, 24, 1).cuda()
     x = torch.randn(2, 12, 8, 8, device="cuda")
     assert torch.equal(expand_1x1(conv, x), conv(x))
+
+
+@pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "x".join(map(str, s)))
+def test_raw_mixed_layout_wgrad_kernel_vs_einsum(shape):
+    """csrc/wgrad_1x1.cu mixed-layout kernel: channels-last operands are read through ldmatrix.trans, no transposes."""
+    from lmnet_b200.conv1x1 import _wgrad_cl, wgrad_cl_supported
+
+    B, Cin, E, Cout, H, W = shape
+    Cin = (Cin + 3) // 4 * 4                     # the host pads the 3-channel stem to 4
+    P = H * W
+    g = torch.Generator().manual_seed(0)
+    dy = torch.randn(B, E, P, generator=g).to(torch.bfloat16)          # planes
+    x = torch.randn(B, P, Cin, generator=g).to(torch.bfloat16)         # channels-last
+    do = torch.randn(B, P, Cout, generator=g).to(torch.bfloat16)       # channels-last
+    z = torch.randn(B, E, P, generator=g).to(torch.bfloat16)           # planes
+    # expand: A planes, B1 channels-last
+    assert wgrad_cl_supported(B, E, Cin, 0, P, False, True, torch.bfloat16)
+    dW, drow = _wgrad_cl(dy.cuda(), x.cuda(), None, False, True)
+    assert rel_err(dW.cpu(), torch.einsum("bmp,bpn->bmn", dy.double(), x.double())) < 1e-5
+    assert rel_err(drow.cpu(), dy.double().sum(-1)) < 1e-5
+    # pointwise + shortcut: A channels-last, B1 planes, B2 channels-last
+    assert wgrad_cl_supported(B, Cout, E, Cin, P, True, False, torch.bfloat16)
+    dW, drow = _wgrad_cl(do.cuda(), z.cuda(), x.cuda(), True, False)
+    ref = torch.cat([torch.einsum("bpm,bnp->bmn", do.double(), z.double()),
+                     torch.einsum("bpm,bpn->bmn", do.double(), x.double())], dim=2)
+    assert rel_err(dW.cpu(), ref) < 1e-5
+    assert rel_err(drow.cpu(), do.double().sum(1)) < 1e-5
+
+
+@pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "x".join(map(str, s)))
+def test_channels_last_expand_and_pointwise_shortcut_vs_modules(shape):
+    """Same comparison as above with a CHANNELS-LAST block input: the expand output must come back as NCHW planes, the
+    block output and the input gradient as channels-last, all without a layout copy of any activation."""
+    from lmnet_b200.conv1x1 import expand_1x1, is_channels_last, pointwise_shortcut
+
+    B, Cin, E, Cout, H, W = shape
+    torch.manual_seed(1)
+    ex, pw, sc = torch.nn.Conv2d(Cin, E, 1), torch.nn.Conv2d(E, Cout, 1), torch.nn.Conv2d(Cin, Cout, 1)
+    rex, rpw, rsc = (copy.deepcopy(m).double() for m in (ex, pw, sc))
+    x = torch.randn(B, Cin, H, W)
+    z = torch.randn(B, E, H, W)
+    gate = torch.rand(B, E, 1, 1)
+    go1, go2 = torch.randn(B, E, H, W), torch.randn(B, Cout, H, W)
+    xr, zr, gr = (t.to(torch.bfloat16).double().requires_grad_() for t in (x, z, gate))
+    y1 = rex(xr)
+    y2 = rpw(gr * zr) + rsc(xr)
+    (y1 * go1.double()).sum().add((y2 * go2.double()).sum()).backward()
+
+    ex, pw, sc = ex.cuda(), pw.cuda(), sc.cuda()
+    xc = x.to(torch.bfloat16).cuda().contiguous(memory_format=torch.channels_last).requires_grad_()
+    zc, gc = (t.cuda().requires_grad_() for t in (z.to(torch.bfloat16), gate))
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        o1 = expand_1x1(ex, xc)
+        o2 = pointwise_shortcut(pw, sc, zc, gc, xc)
+    assert o1.is_contiguous() and o1.dtype == torch.bfloat16
+    assert is_channels_last(o2) or Cout == 1
+    (o1.float() * go1.cuda()).sum().add((o2.float() * go2.cuda()).sum()).backward()
+    tol = 2e-2
+    assert rel_err(o1.float().cpu(), y1) < tol and rel_err(o2.float().cpu(), y2) < tol
+    assert rel_err(xc.grad.float().cpu(), xr.grad) < tol
+    assert rel_err(zc.grad.float().cpu(), zr.grad) < tol
+    assert rel_err(gc.grad.cpu(), gr.grad) < tol
+    for m, r in ((ex, rex), (pw, rpw), (sc, rsc)):
+        assert rel_err(m.weight.grad.cpu(), r.weight.grad) < tol
+        assert rel_err(m.bias.grad.cpu(), r.bias.grad) < tol
