@@ -240,6 +240,33 @@ int lmnet_wgrad_1x1_cl(const void* A, const void* B1, const void* B2, float* dW,
                        void* workspace, size_t workspace_bytes, const lmnet_wgrad_dims* dims,
                        int a_channels_last, int b1_channels_last, int dtype, void* stream);
 
+/* ---- 1x1 convolutions as small-K GEMMs over pixels (widening step f1: forward + input gradients) -----------
+ * out[b] = W1[b or shared] . in1[b]  (+ W2 . in2[b])  (+ bias)   for every batch image b and pixel.
+ * Replaces expand_conv[0], pointwise_conv[0](gate * z) + shortcut[0](x) and their input gradients
+ * (/root/reference/core/modules.py:537, 576-584, 587, 598-599).  Operand layouts: "planes" = [B, C, P] (NCHW),
+ * "channels-last" = [B, P, C].  in2 (K2 > 0) is always channels-last and requires a channels-last output; a planes
+ * output requires a channels-last in1.  Weights are [N, K] row-major in `dtype` (w1: [B, N, K1] when
+ * w1_per_batch); bias fp32 [N] or NULL.  stats_part (planes output only, or NULL): per-CTA partial sums
+ * [N][ctas][2] (sum, sum of squares of the stored output) in the layout of lmnet_bn_act_fwd_stats;
+ * ctas = lmnet_pixel_gemm_stats_ctas().  16-bit dtypes, P % 8 == 0, channel counts % 4 == 0. */
+typedef struct lmnet_pgemm_dims {
+    int32_t B;
+    int64_t P;
+    int32_t N, K1, K2;
+} lmnet_pgemm_dims;
+int lmnet_pixel_gemm_supported(const lmnet_pgemm_dims* dims, int in1_channels_last, int out_channels_last,
+                               int want_stats, int dtype);
+int lmnet_pixel_gemm_stats_ctas(const lmnet_pgemm_dims* dims, int in1_channels_last, int out_channels_last);
+int lmnet_pixel_gemm(const void* in1, int in1_channels_last, const void* w1, int w1_per_batch, const void* in2,
+                     const void* w2, const float* bias, void* out, int out_channels_last, float* stats_part,
+                     const lmnet_pgemm_dims* dims, int dtype, void* stream);
+/* BatchNorm + activation forward (training, NCHW planes) whose statistics pass already happened elsewhere:
+ * stats_part = [C][nchunks][2] partial (sum, sum of squares) over all B*HW elements of each channel. */
+int lmnet_bn_act_fwd_stats(const void* y, const float* stats_part, int nchunks, const float* gamma, const float* beta,
+                           float* running_mean, float* running_var, int64_t* num_batches_tracked, void* out,
+                           float* save_mean, float* save_rstd, float eps, float momentum, int act,
+                           void* workspace, size_t workspace_bytes, const lmnet_bn_dims* dims, int dtype, void* stream);
+
 /* ---- bilinear x2 up-sampling, align_corners=True, NCHW (widening step f3) ----------------------
  * Replaces nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True) of the decoder and skip blocks
  * (/root/reference/core/LM_Net.py:58-74, /root/reference/core/modules.py:93-95, 129-131).

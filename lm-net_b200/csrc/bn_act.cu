@@ -282,15 +282,23 @@ __device__ __forceinline__ void cl_block_reduce(const BnGeomCl& g, const float (
         s_tab[threadIdx.x * 2 * V + V + j] = b[j];
     }
     __syncthreads();
+    // tree over the thread rows, pairing rows a multiple of VP apart (same channel phase); fixed order => deterministic
+    constexpr int W2 = 2 * V;
+    int n = g.S;                                    // live rows, always a multiple of VP
+    while (n > g.VP) {
+        const int m = ((n / g.VP + 1) / 2) * g.VP;  // rows [m, n) fold onto rows [0, n - m)
+        for (int i = threadIdx.x; i < (n - m) * W2; i += kBnThreads) s_tab[i] += s_tab[i + m * W2];
+        __syncthreads();
+        n = m;
+    }
     for (int c = threadIdx.x; c < g.C; c += kBnThreads) {
         float sa = 0.f, sb = 0.f;
         for (int ph = 0; ph < g.VP; ++ph)
             for (int j = 0; j < V; ++j)
-                if ((ph * V + j) % g.C == c)
-                    for (int t = ph; t < g.S; t += g.VP) {
-                        sa += s_tab[t * 2 * V + j];
-                        sb += s_tab[t * 2 * V + V + j];
-                    }
+                if ((ph * V + j) % g.C == c) {
+                    sa += s_tab[ph * W2 + j];
+                    sb += s_tab[ph * W2 + V + j];
+                }
         part[((int64_t)c * g.chunks + blockIdx.x) * 2] = sa;
         part[((int64_t)c * g.chunks + blockIdx.x) * 2 + 1] = sb;
     }
@@ -642,6 +650,66 @@ extern "C" int lmnet_bn_act_bwd(const void* y, const void* dout, const float* ga
         case LMNET_F32: return bn_bwd_t<float>(vec, act, y, dout, gamma, beta, save_mean, save_rstd, dy, dgamma, dbeta, (char*)workspace, dims, st);
         case LMNET_BF16: return bn_bwd_t<__nv_bfloat16>(vec, act, y, dout, gamma, beta, save_mean, save_rstd, dy, dgamma, dbeta, (char*)workspace, dims, st);
         case LMNET_F16: return bn_bwd_t<__half>(vec, act, y, dout, gamma, beta, save_mean, save_rstd, dy, dgamma, dbeta, (char*)workspace, dims, st);
+        default: return LMNET_ERR_UNSUPPORTED;
+    }
+}
+
+// training forward with the statistics pass done by the producer (pixel_gemm's epilogue): finalize + apply only
+namespace lmnet {
+template <typename T, bool VEC, int ACT>
+static int bn_launch_fwd_stats(const void* y, const float* part, int nchunks, const float* gamma, const float* beta, float* rm,
+                               float* rv, int64_t* nbt, void* out, float* save_mean, float* save_rstd, float eps, float momentum,
+                               char* ws, const lmnet_bn_dims* d, cudaStream_t st) {
+    BnGeom g = bn_geom(d, sizeof(T));
+    BnWs L = bn_ws(d);
+    float2* coef = (float2*)(ws + L.coef);
+    dim3 grid(g.chunks, g.C);
+    const double t_bytes = (double)d->B * d->C * d->HW * sizeof(T);
+    BnGeom gs = g;
+    gs.chunks = nchunks;
+    LMNET_LAUNCH(KID_BN_FIN_FWD, st, 0, (bnact_fin_fwd_kernel<<<(g.C + 127) / 128, 128, 0, st>>>(
+        part, gamma, beta, rm, rv, nbt, save_mean, save_rstd, coef, eps, momentum, gs)));
+    LMNET_LAUNCH(KID_BN_APPLY, st, 2 * t_bytes, (bnact_apply_kernel<T, VEC, ACT><<<grid, kBnThreads, 0, st>>>((const T*)y, coef, (T*)out, g)));
+    return LMNET_OK;
+}
+template <typename T, bool VEC>
+static int bn_fwd_stats_act(int act, const void* y, const float* part, int nchunks, const float* gamma, const float* beta, float* rm,
+                            float* rv, int64_t* nbt, void* out, float* sm, float* sr, float eps, float mom, char* ws,
+                            const lmnet_bn_dims* d, cudaStream_t st) {
+    switch (act) {
+        case LMNET_ACT_NONE: return bn_launch_fwd_stats<T, VEC, LMNET_ACT_NONE>(y, part, nchunks, gamma, beta, rm, rv, nbt, out, sm, sr, eps, mom, ws, d, st);
+        case LMNET_ACT_HARDSWISH: return bn_launch_fwd_stats<T, VEC, LMNET_ACT_HARDSWISH>(y, part, nchunks, gamma, beta, rm, rv, nbt, out, sm, sr, eps, mom, ws, d, st);
+        case LMNET_ACT_GELU: return bn_launch_fwd_stats<T, VEC, LMNET_ACT_GELU>(y, part, nchunks, gamma, beta, rm, rv, nbt, out, sm, sr, eps, mom, ws, d, st);
+        case LMNET_ACT_RELU: return bn_launch_fwd_stats<T, VEC, LMNET_ACT_RELU>(y, part, nchunks, gamma, beta, rm, rv, nbt, out, sm, sr, eps, mom, ws, d, st);
+        default: return LMNET_ERR_UNSUPPORTED;
+    }
+}
+template <typename T>
+static int bn_fwd_stats_t(bool vec, int act, const void* y, const float* part, int nchunks, const float* gamma, const float* beta,
+                          float* rm, float* rv, int64_t* nbt, void* out, float* sm, float* sr, float eps, float mom, char* ws,
+                          const lmnet_bn_dims* d, cudaStream_t st) {
+    return vec ? bn_fwd_stats_act<T, true>(act, y, part, nchunks, gamma, beta, rm, rv, nbt, out, sm, sr, eps, mom, ws, d, st)
+               : bn_fwd_stats_act<T, false>(act, y, part, nchunks, gamma, beta, rm, rv, nbt, out, sm, sr, eps, mom, ws, d, st);
+}
+}  // namespace lmnet
+
+extern "C" int lmnet_bn_act_fwd_stats(const void* y, const float* stats_part, int nchunks, const float* gamma,
+                                      const float* beta, float* running_mean, float* running_var,
+                                      int64_t* num_batches_tracked, void* out, float* save_mean, float* save_rstd,
+                                      float eps, float momentum, int act, void* workspace, size_t workspace_bytes,
+                                      const lmnet_bn_dims* dims, int dtype, void* stream) {
+    int rc = bn_validate(dims);
+    if (rc != LMNET_OK) return rc;
+    if (!y || !out || !workspace || !stats_part || nchunks <= 0 || !save_mean || !save_rstd) return LMNET_ERR_INVALID_ARG;
+    if ((running_mean == nullptr) != (running_var == nullptr)) return LMNET_ERR_INVALID_ARG;
+    if (workspace_bytes < bn_ws(dims).total) return LMNET_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t es = dtype == LMNET_F32 ? 4 : 2;
+    const bool vec = bn_vec_ok(dims, es, {y, out});
+    switch (dtype) {
+        case LMNET_F32: return bn_fwd_stats_t<float>(vec, act, y, stats_part, nchunks, gamma, beta, running_mean, running_var, num_batches_tracked, out, save_mean, save_rstd, eps, momentum, (char*)workspace, dims, st);
+        case LMNET_BF16: return bn_fwd_stats_t<__nv_bfloat16>(vec, act, y, stats_part, nchunks, gamma, beta, running_mean, running_var, num_batches_tracked, out, save_mean, save_rstd, eps, momentum, (char*)workspace, dims, st);
+        case LMNET_F16: return bn_fwd_stats_t<__half>(vec, act, y, stats_part, nchunks, gamma, beta, running_mean, running_var, num_batches_tracked, out, save_mean, save_rstd, eps, momentum, (char*)workspace, dims, st);
         default: return LMNET_ERR_UNSUPPORTED;
     }
 }

@@ -28,9 +28,11 @@ def _cl(t):
 
 
 def _natt_forward(self, x):
-    emb = self.patchembedding(_cl(x))
+    """NeighborhoodTransformer.forward (core/modules.py:514-521): 3x3 conv embed -> LN -> NA -> +res -> LN -> MLP -> +res."""
+    emb = self.patchembedding(_cl(x))              # NHWC conv output: its [B,H,W,C] permute is a free view
     att = self.att1(layer_norm(self.norm1, emb)) + emb
     y = self.mlp(layer_norm(self.norm2, att)) + att
+    # logical NCHW on channels-last memory: a free view (every consumer is channels-last as well)
     return y.permute(0, 3, 1, 2) if y.is_cuda else y.permute(0, 3, 1, 2).contiguous()
 
 

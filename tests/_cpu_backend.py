@@ -52,7 +52,7 @@ def apply(setattr_fn):
         setattr_fn(na_ops, name, fn)
     import torch.nn.functional as F
 
-    from lmnet_b200 import bnact, model
+    from lmnet_b200 import bnact
 
     def bn_act_ref(bn, y, act="none"):
         out = bn(y)
@@ -62,7 +62,6 @@ def apply(setattr_fn):
     setattr_fn(reparam, "bn_act", bn_act_ref)
     setattr_fn(reparam, "expand_1x1", lambda conv, x: conv(x))
     setattr_fn(reparam, "pointwise_shortcut", lambda pw, sc, z, gate, x: pw(gate * z) + sc(x))
-    setattr_fn(model, "layer_norm", lambda ln, x: ln(x))
     from lmnet_b200 import patch
 
     setattr_fn(patch, "layer_norm", lambda ln, x: ln(x))

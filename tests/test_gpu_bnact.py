@@ -14,11 +14,15 @@ TOL = {torch.float32: 1e-4, torch.bfloat16: 2e-2}
 ACTS = {"none": lambda t: t, "hardswish": F.hardswish, "gelu": F.gelu, "relu": F.relu}
 
 
+@pytest.mark.parametrize("channels_last", [False, True], ids=["nchw", "nhwc"])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("act", ["hardswish", "gelu", "none", "relu"])
-@pytest.mark.parametrize("shape", [(4, 24, 40, 36), (2, 7, 9, 11), (3, 192, 11, 11), (1, 5, 3, 1000)])
-def test_bn_act_train_eval(shape, act, dtype):
-    from lmnet_b200.bnact import bn_act
+@pytest.mark.parametrize("shape", [(4, 24, 40, 36), (2, 7, 9, 11), (3, 192, 11, 11), (1, 5, 3, 1000), (2, 12, 16, 20),
+                                   (2, 96, 12, 12), (3, 48, 10, 8)])
+def test_bn_act_train_eval(shape, act, dtype, channels_last):
+    """channels_last=True feeds channels-last tensors: shapes whose element count is a multiple of the 16-byte vector run
+    the channels-last kernels (output / gradient stay channels-last), the others fall back to the NCHW kernels."""
+    from lmnet_b200.bnact import _cl_ok, bn_act
 
     B, C, H, W = shape
     g = torch.Generator().manual_seed(3)
@@ -43,9 +47,14 @@ def test_bn_act_train_eval(shape, act, dtype):
     near_kink = ((pre.detach().abs() - 3).abs() < 0.05) if act == "hardswish" else torch.zeros_like(pre, dtype=torch.bool)
 
     bn = bn.cuda().train()
-    yc = y.cuda().requires_grad_()
+    yc = y.cuda()
+    if channels_last:
+        yc = yc.contiguous(memory_format=torch.channels_last)
+    yc = yc.requires_grad_()
     out = bn_act(bn, yc, act)
     assert out.dtype == dtype
+    if channels_last and _cl_ok(yc):
+        assert out.is_contiguous(memory_format=torch.channels_last)
     out.backward(go.cuda())
     tol = TOL[dtype]
     assert rel_err(out.float().cpu(), outr) < tol

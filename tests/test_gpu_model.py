@@ -204,3 +204,47 @@ def test_cfg1_size_fp32_logits_and_masks_match_reference():
         if e > worst:
             worst, worst_name = e, str(name)
     assert worst < 2e-3, (worst, worst_name)
+
+
+def test_patched_reference_like_classes_share_the_code_path():
+    """VERDICT r1 item 1d.  `patch_reference_modules` applied to a namespace of reference-like classes (same
+    constructors / sub-module names as core/modules.py, stock-torch forwards) must install exactly the forwards
+    lmnet_b200.model uses — same function objects — and a patched instance must reproduce the model's class bit for
+    bit with the same number of library launches on the GPU."""
+    import types
+
+    from lmnet_b200 import _lib, model as M
+    from lmnet_b200.patch import patch_reference_modules, unpatch_reference_modules
+    from oracle.lmnet_ref import _m2skip_forward_ref, _m3skip_forward_ref, _transformer_forward_ref
+    from oracle.reparam_ref import reparam_forward_ref
+
+    ns = types.SimpleNamespace(
+        ReparamConv=type("ReparamConv", (M.ReparamConv,), {"forward": reparam_forward_ref}),
+        NeighborhoodTransformer=type("NeighborhoodTransformer", (M.NeighborhoodTransformer,), {"forward": _transformer_forward_ref}),
+        M3Skip=type("M3Skip", (M.M3Skip,), {"forward": _m3skip_forward_ref}),
+        M2Skip=type("M2Skip", (M.M2Skip,), {"forward": _m2skip_forward_ref}))
+    originals = patch_reference_modules(ns)
+    try:
+        for name in ("ReparamConv", "NeighborhoodTransformer", "M3Skip", "M2Skip"):
+            assert getattr(ns, name).forward is getattr(M, name).forward, name
+        torch.manual_seed(0)
+        cases = [(ns.ReparamConv(12, 24, 12), M.ReparamConv(12, 24, 12), [torch.randn(2, 12, 24, 40)]),
+                 (ns.NeighborhoodTransformer(24), M.NeighborhoodTransformer(24), [torch.randn(2, 24, 16, 24)]),
+                 (ns.M3Skip([12, 24, 48]), M.M3Skip([12, 24, 48]),
+                  [torch.randn(2, 12, 32, 32), torch.randn(2, 24, 16, 16), torch.randn(2, 48, 8, 8)]),
+                 (ns.M2Skip([12, 24], "top"), M.M2Skip([12, 24], "top"), [torch.randn(2, 12, 16, 16), torch.randn(2, 24, 8, 8)])]
+        for patched, ours, inputs in cases:
+            fill_deterministic(ours, seed=9)
+            patched.load_state_dict(ours.state_dict())
+            patched, ours = patched.cuda().train(), ours.cuda().train()
+            xs = [t.cuda() for t in inputs]
+            outs, counts = [], []
+            for mod in (patched, ours):
+                before = _lib.launch_count()
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    outs.append(mod(*xs))
+                counts.append(_lib.launch_count() - before)
+            assert torch.equal(outs[0], outs[1]), type(ours).__name__
+            assert counts[0] == counts[1] > 0, (type(ours).__name__, counts)
+    finally:
+        unpatch_reference_modules(ns, originals)
