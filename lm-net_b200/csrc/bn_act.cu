@@ -117,18 +117,33 @@ bnact_stats_kernel(const T* __restrict__ y, float* __restrict__ part /* [C][chun
 }
 
 // coef[c] = (a, b) with out = act(a*y + b)
-__global__ void bnact_fin_fwd_kernel(const float* __restrict__ part, const float* __restrict__ gamma,
-                                     const float* __restrict__ beta, float* running_mean, float* running_var,
-                                     int64_t* nbt, float* __restrict__ save_mean, float* __restrict__ save_rstd,
-                                     float2* __restrict__ coef, float eps, float momentum, BnGeom g) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per channel: lanes stride over the per-CTA partials, then a fixed-order butterfly (deterministic)
+__device__ __forceinline__ double bn_warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+constexpr int kBnFinThreads = 128;
+static inline int bn_fin_blocks(int C) { return (C + kBnFinThreads / 32 - 1) / (kBnFinThreads / 32); }
+
+__global__ void __launch_bounds__(kBnFinThreads)
+bnact_fin_fwd_kernel(const float* __restrict__ part, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, float* running_mean, float* running_var,
+                     int64_t* nbt, float* __restrict__ save_mean, float* __restrict__ save_rstd,
+                     float2* __restrict__ coef, float eps, float momentum, BnGeom g) {
+    const int c = blockIdx.x * (kBnFinThreads / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (c >= g.C) return;
     const double n = (double)g.B * (double)g.HW;
     double s = 0, ss = 0;
-    for (int k = 0; k < g.chunks; ++k) {
-        s += part[((int64_t)c * g.chunks + k) * 2];
-        ss += part[((int64_t)c * g.chunks + k) * 2 + 1];
+    const float2* pc = reinterpret_cast<const float2*>(part) + (int64_t)c * g.chunks;
+    for (int k = lane; k < g.chunks; k += 32) {
+        const float2 v = __ldg(pc + k);
+        s += v.x;
+        ss += v.y;
     }
+    s = bn_warp_sum(s);
+    ss = bn_warp_sum(ss);
+    if (lane != 0) return;
     const double mean = s / n;
     double var = ss / n - mean * mean;
     if (var < 0) var = 0;
@@ -205,16 +220,22 @@ bnact_bwd_reduce_kernel(const T* __restrict__ y, const T* __restrict__ dout, con
 }
 
 // cb[c] = (m1, m2) = (sum dh / n, sum dh*yhat / n); also writes dgamma, dbeta
-__global__ void bnact_fin_bwd_kernel(const float* __restrict__ part, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                     float2* __restrict__ cb, BnGeom g) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(kBnFinThreads)
+bnact_fin_bwd_kernel(const float* __restrict__ part, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                     float2* __restrict__ cb, BnGeom g) {
+    const int c = blockIdx.x * (kBnFinThreads / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (c >= g.C) return;
     const double n = (double)g.B * (double)g.HW;
     double s = 0, sy = 0;
-    for (int k = 0; k < g.chunks; ++k) {
-        s += part[((int64_t)c * g.chunks + k) * 2];
-        sy += part[((int64_t)c * g.chunks + k) * 2 + 1];
+    const float2* pc = reinterpret_cast<const float2*>(part) + (int64_t)c * g.chunks;
+    for (int k = lane; k < g.chunks; k += 32) {
+        const float2 v = __ldg(pc + k);
+        s += v.x;
+        sy += v.y;
     }
+    s = bn_warp_sum(s);
+    sy = bn_warp_sum(sy);
+    if (lane != 0) return;
     if (dgamma != nullptr) dgamma[c] = (float)sy;
     if (dbeta != nullptr) dbeta[c] = (float)s;
     cb[c] = make_float2((float)(s / n), (float)(sy / n));
@@ -478,7 +499,7 @@ static int bn_launch_fwd(bool train, const void* y, const float* gamma, const fl
     const double t_bytes = (double)d->B * d->C * d->HW * sizeof(T);
     if (train) {
         LMNET_LAUNCH(KID_BN_STATS, st, t_bytes, (bnact_stats_kernel<T, VEC><<<grid, kBnThreads, 0, st>>>((const T*)y, part, g)));
-        LMNET_LAUNCH(KID_BN_FIN_FWD, st, 0, (bnact_fin_fwd_kernel<<<(g.C + 127) / 128, 128, 0, st>>>(
+        LMNET_LAUNCH(KID_BN_FIN_FWD, st, 0, (bnact_fin_fwd_kernel<<<bn_fin_blocks(g.C), kBnFinThreads, 0, st>>>(
             part, gamma, beta, rm, rv, nbt, save_mean, save_rstd, coef, eps, momentum, g)));
     } else {
         LMNET_LAUNCH(KID_BN_FIN_FWD, st, 0, (bnact_coef_eval_kernel<<<(g.C + 127) / 128, 128, 0, st>>>(gamma, beta, rm, rv, coef, eps, g.C)));
@@ -499,7 +520,7 @@ static int bn_launch_bwd(const void* y, const void* dout, const float* gamma, co
     const double t_bytes = (double)d->B * d->C * d->HW * sizeof(T);
     LMNET_LAUNCH(KID_BN_BWD_REDUCE, st, 2 * t_bytes, (bnact_bwd_reduce_kernel<T, VEC, ACT><<<grid, kBnThreads, 0, st>>>(
         (const T*)y, (const T*)dout, gamma, beta, save_mean, save_rstd, part, g)));
-    LMNET_LAUNCH(KID_BN_FIN_BWD, st, 0, (bnact_fin_bwd_kernel<<<(g.C + 127) / 128, 128, 0, st>>>(part, dgamma, dbeta, cb, g)));
+    LMNET_LAUNCH(KID_BN_FIN_BWD, st, 0, (bnact_fin_bwd_kernel<<<bn_fin_blocks(g.C), kBnFinThreads, 0, st>>>(part, dgamma, dbeta, cb, g)));
     LMNET_LAUNCH(KID_BN_BWD_APPLY, st, 3 * t_bytes, (bnact_bwd_apply_kernel<T, VEC, ACT><<<grid, kBnThreads, 0, st>>>(
         (const T*)y, (const T*)dout, gamma, beta, save_mean, save_rstd, cb, (T*)dy, g)));
     return LMNET_OK;
@@ -520,7 +541,7 @@ static int bn_launch_fwd_cl(bool train, const void* y, const float* gamma, const
     const size_t tab = (size_t)kBnThreads * 2 * ClVec<T>::V * sizeof(float);
     if (train) {
         LMNET_LAUNCH(KID_BN_STATS, st, t_bytes, (bnact_stats_cl_kernel<T><<<gc.chunks, kBnThreads, tab, st>>>((const T*)y, part, gc)));
-        LMNET_LAUNCH(KID_BN_FIN_FWD, st, 0, (bnact_fin_fwd_kernel<<<(g.C + 127) / 128, 128, 0, st>>>(
+        LMNET_LAUNCH(KID_BN_FIN_FWD, st, 0, (bnact_fin_fwd_kernel<<<bn_fin_blocks(g.C), kBnFinThreads, 0, st>>>(
             part, gamma, beta, rm, rv, nbt, save_mean, save_rstd, coef, eps, momentum, g)));
     } else {
         LMNET_LAUNCH(KID_BN_FIN_FWD, st, 0, (bnact_coef_eval_kernel<<<(g.C + 127) / 128, 128, 0, st>>>(gamma, beta, rm, rv, coef, eps, g.C)));
@@ -544,7 +565,7 @@ static int bn_launch_bwd_cl(const void* y, const void* dout, const float* gamma,
     const size_t tab = (size_t)kBnThreads * 2 * ClVec<T>::V * sizeof(float);
     LMNET_LAUNCH(KID_BN_BWD_REDUCE, st, 2 * t_bytes, (bnact_bwd_reduce_cl_kernel<T, ACT><<<gc.chunks, kBnThreads, tab, st>>>(
         (const T*)y, (const T*)dout, gamma, beta, save_mean, save_rstd, part, gc)));
-    LMNET_LAUNCH(KID_BN_FIN_BWD, st, 0, (bnact_fin_bwd_kernel<<<(g.C + 127) / 128, 128, 0, st>>>(part, dgamma, dbeta, cb, g)));
+    LMNET_LAUNCH(KID_BN_FIN_BWD, st, 0, (bnact_fin_bwd_kernel<<<bn_fin_blocks(g.C), kBnFinThreads, 0, st>>>(part, dgamma, dbeta, cb, g)));
     LMNET_LAUNCH(KID_BN_BWD_APPLY, st, 3 * t_bytes, (bnact_bwd_apply_cl_kernel<T, ACT><<<gc.chunks, kBnThreads, 0, st>>>(
         (const T*)y, (const T*)dout, gamma, beta, save_mean, save_rstd, cb, (T*)dy, gc)));
     return LMNET_OK;
@@ -667,7 +688,7 @@ static int bn_launch_fwd_stats(const void* y, const float* part, int nchunks, co
     const double t_bytes = (double)d->B * d->C * d->HW * sizeof(T);
     BnGeom gs = g;
     gs.chunks = nchunks;
-    LMNET_LAUNCH(KID_BN_FIN_FWD, st, 0, (bnact_fin_fwd_kernel<<<(g.C + 127) / 128, 128, 0, st>>>(
+    LMNET_LAUNCH(KID_BN_FIN_FWD, st, 0, (bnact_fin_fwd_kernel<<<bn_fin_blocks(g.C), kBnFinThreads, 0, st>>>(
         part, gamma, beta, rm, rv, nbt, save_mean, save_rstd, coef, eps, momentum, gs)));
     LMNET_LAUNCH(KID_BN_APPLY, st, 2 * t_bytes, (bnact_apply_kernel<T, VEC, ACT><<<grid, kBnThreads, 0, st>>>((const T*)y, coef, (T*)out, g)));
     return LMNET_OK;

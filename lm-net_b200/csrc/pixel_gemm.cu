@@ -35,6 +35,7 @@ constexpr int kPgMaxAcc = 12;          // 16x8 accumulators per warp
 
 struct PgGeom {
     int B, N, K1, K2;                  // real sizes
+    int NC;                            // output channels per CTA (grid.z chunks of a channels-last output; N otherwise)
     int K1p, K2p;                      // padded to 16
     int64_t P;                         // pixels per image
     int PT;                            // pixels per CTA tile
@@ -146,19 +147,20 @@ pixel_gemm_kernel(const T* __restrict__ in1, const T* __restrict__ w1, const T* 
     float* s_stat = s_bias + n_pad;                                          // [8 warps][n_pad][2] (planes output only)
     const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gq = lane >> 2, tq = lane & 3;
+    const int n0 = blockIdx.z * g.NC;                                        // first output channel of this CTA
     const T zero = from_f<T>(0.f);
 
     // ---- one-time: weights (zero padded), bias, zero the padding of the input stages
     for (int i = threadIdx.x; i < n_pad * g.w_pitch; i += kPgThreads) {
         const int n = i / g.w_pitch, k = i - n * g.w_pitch;
         T v = zero;
-        if (n < g.N) {
-            if (k < g.K1) v = w1[((int64_t)(g.w1_per_batch ? b : 0) * g.N + n) * g.K1 + k];
-            else if (HAS_IN2 && k >= g.K1p && k - g.K1p < g.K2) v = w2[(int64_t)n * g.K2 + (k - g.K1p)];
+        if (n < g.NC) {
+            if (k < g.K1) v = w1[((int64_t)(g.w1_per_batch ? b : 0) * g.N + n0 + n) * g.K1 + k];
+            else if (HAS_IN2 && k >= g.K1p && k - g.K1p < g.K2) v = w2[(int64_t)(n0 + n) * g.K2 + (k - g.K1p)];
         }
         s_w[i] = v;
     }
-    for (int i = threadIdx.x; i < n_pad; i += kPgThreads) s_bias[i] = (bias != nullptr && i < g.N) ? bias[i] : 0.f;
+    for (int i = threadIdx.x; i < n_pad; i += kPgThreads) s_bias[i] = (bias != nullptr && i < g.NC) ? bias[n0 + i] : 0.f;
     for (int i = threadIdx.x; i < 2 * stage_elems; i += kPgThreads) s_in[i] = zero;
     __syncthreads();
 
@@ -242,17 +244,17 @@ pixel_gemm_kernel(const T* __restrict__ in1, const T* __restrict__ w1, const T* 
                     *reinterpret_cast<uint32_t*>(s_out + (r0 + 8) * g.out_pitch + n) = pg_pack<T>(acc[i][j][2] + b0, acc[i][j][3] + b1);
                 }
             __syncthreads();
-            // staging -> global: the tile is one contiguous chunk of PT x N elements
+            // staging -> global: PT pixel rows of NC channels (one contiguous chunk when NC == N)
             const int64_t valid = min((int64_t)g.PT, g.P - p0);
-            T* dst = out_b + p0 * g.N;
-            if ((g.N & 7) == 0) {
-                const int vpr = g.N >> 3;
+            T* dst = out_b + p0 * g.N + n0;
+            if ((g.NC & 7) == 0 && (g.N & 7) == 0) {
+                const int vpr = g.NC >> 3;
                 for (int i = threadIdx.x; i < (int)valid * vpr; i += kPgThreads) {
                     const int r = i / vpr, v = i - r * vpr;
                     *reinterpret_cast<uint4*>(dst + (int64_t)r * g.N + v * 8) = *reinterpret_cast<const uint4*>(s_out + r * g.out_pitch + v * 8);
                 }
             } else {
-                const int vpr = g.N >> 2;
+                const int vpr = g.NC >> 2;
                 for (int i = threadIdx.x; i < (int)valid * vpr; i += kPgThreads) {
                     const int r = i / vpr, v = i - r * vpr;
                     *reinterpret_cast<uint2*>(dst + (int64_t)r * g.N + v * 4) = *reinterpret_cast<const uint2*>(s_out + r * g.out_pitch + v * 4);
@@ -371,8 +373,13 @@ static bool pg_plan(const lmnet_pgemm_dims* d, bool in1_cl, bool out_cl, bool st
     g.K2p = d->K2 > 0 ? (d->K2 + 15) / 16 * 16 : 0;
     g.w_pitch = pg_pitch(g.K1p + g.K2p);
     g.w1_per_batch = 0;
+    g.NC = d->N;
+    int nchunks = 1;
     if (out_cl) {
-        pl.TB = (d->N + 7) / 8;                                  // n-tiles of 8 channels
+        nchunks = (d->N + 8 * kPgMaxAcc - 1) / (8 * kPgMaxAcc);  // wide outputs: grid.z chunks of <= 96 channels
+        if (d->N % nchunks != 0 || (d->N / nchunks) % 4 != 0) return false;
+        g.NC = d->N / nchunks;
+        pl.TB = (g.NC + 7) / 8;                                  // n-tiles of 8 channels
         if (pl.TB > kPgMaxAcc) return false;
         pl.TA = kPgMaxAcc / pl.TB;
         if (pl.TA > 4) pl.TA = 4;
@@ -400,12 +407,12 @@ static bool pg_plan(const lmnet_pgemm_dims* d, bool in1_cl, bool out_cl, bool st
               (stats ? (size_t)kPgWarps * n_pad * 2 * 4 : 0) + 16;
     if (pl.smem > 200 * 1024) return false;
     g.tiles = (int)((d->P + g.PT - 1) / g.PT);
-    int ctas_x = (2 * 148 + d->B - 1) / d->B;                    // ~2 CTAs per SM over the whole grid
+    int ctas_x = (2 * 148 + d->B * nchunks - 1) / (d->B * nchunks);   // ~2 CTAs per SM over the whole grid
     if (ctas_x > g.tiles) ctas_x = g.tiles;
     if (ctas_x < 1) ctas_x = 1;
     g.tiles_per_cta = (g.tiles + ctas_x - 1) / ctas_x;
     g.ctas_x = (g.tiles + g.tiles_per_cta - 1) / g.tiles_per_cta;
-    pl.grid = dim3((unsigned)g.ctas_x, (unsigned)d->B);
+    pl.grid = dim3((unsigned)g.ctas_x, (unsigned)d->B, (unsigned)nchunks);
     return true;
 }
 

@@ -62,6 +62,10 @@ class WgradDims(Structure):
     _fields_ = [("B", c_int32), ("M", c_int32), ("N1", c_int32), ("N2", c_int32), ("P", c_int64)]
 
 
+class PgemmDims(Structure):
+    _fields_ = [("B", c_int32), ("P", c_int64), ("N", c_int32), ("K1", c_int32), ("K2", c_int32)]
+
+
 _lib = None
 
 
@@ -124,6 +128,13 @@ def lib():
     L.lmnet_wgrad_1x1_workspace_bytes.restype = c_size_t
     L.lmnet_wgrad_1x1_workspace_bytes.argtypes = [pwd]
     L.lmnet_wgrad_1x1.argtypes = [c_void_p] * 5 + [c_void_p, c_size_t, pwd, c_int, c_void_p]
+    ppg = POINTER(PgemmDims)
+    L.lmnet_pixel_gemm_supported.argtypes = [ppg, c_int, c_int, c_int, c_int]
+    L.lmnet_pixel_gemm_stats_ctas.argtypes = [ppg, c_int, c_int]
+    L.lmnet_pixel_gemm.argtypes = [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                   c_void_p, ppg, c_int, c_void_p]
+    L.lmnet_bn_act_fwd_stats.argtypes = [c_void_p, c_void_p, c_int] + [c_void_p] * 8 + [c_float, c_float, c_int, c_void_p,
+                                                                                      c_size_t, pbd, c_int, c_void_p]
     pud = POINTER(UpsampleDims)
     L.lmnet_upsample2x_fwd.argtypes = [c_void_p, c_void_p, pud, c_int, c_void_p]
     L.lmnet_upsample2x_bwd.argtypes = [c_void_p, c_void_p, pud, c_int, c_void_p]
@@ -238,4 +249,4 @@ def dw_grads(dw, dgamma, dbeta) -> DwGrads:
 
 
 __all__ = ["lib", "check", "dtype_code", "require_cuda", "stream_ptr", "ptr", "view5", "na_dims", "dw_params",
-           "dw_grads", "View5", "NADims", "DwParams", "DwGrads", "DwDims", "BnDims", "ACT_CODES", "WgradDims", "UpsampleDims", "UpsampleClDims", "byref", "launch_count", "LIB_PATH"]
+           "dw_grads", "View5", "NADims", "DwParams", "DwGrads", "DwDims", "BnDims", "ACT_CODES", "WgradDims", "PgemmDims", "UpsampleDims", "UpsampleClDims", "byref", "launch_count", "LIB_PATH"]

@@ -46,7 +46,7 @@ def _cl_ok(y) -> bool:
 class _BNActTrain(torch.autograd.Function):
     @staticmethod
     @custom_fwd(device_type="cuda")
-    def forward(ctx, y, gamma, beta, running, eps, momentum, act):
+    def forward(ctx, y, gamma, beta, running, eps, momentum, act, stats=None):
         L.require_cuda(y)
         ctx.cl = _cl_ok(y)
         if not ctx.cl:
@@ -59,10 +59,19 @@ class _BNActTrain(torch.autograd.Function):
         save_mean = torch.empty(C, dtype=torch.float32, device=y.device)
         save_rstd = torch.empty(C, dtype=torch.float32, device=y.device)
         ws = _ws(dims, y.device)
-        fn = L.lib().lmnet_bn_act_cl_fwd if ctx.cl else L.lib().lmnet_bn_act_fwd
-        rc = fn(L.ptr(y), L.ptr(g32), L.ptr(b32), L.ptr(rmean), L.ptr(rvar), L.ptr(nbt),
-                L.ptr(out), L.ptr(save_mean), L.ptr(save_rstd), float(eps), float(momentum),
-                1, act, L.ptr(ws), ws.numel(), L.byref(dims), L.dtype_code(y), L.stream_ptr())
+        if stats is not None and not ctx.cl:
+            # the producer's epilogue already reduced (sum, sum of squares) per CTA: finalize + apply only
+            if stats.dim() != 3 or stats.shape[0] != C or stats.shape[2] != 2 or stats.dtype != torch.float32:
+                raise ValueError("stats must be fp32 [C, chunks, 2] partial sums")
+            rc = L.lib().lmnet_bn_act_fwd_stats(
+                L.ptr(y), L.ptr(stats.contiguous()), int(stats.shape[1]), L.ptr(g32), L.ptr(b32), L.ptr(rmean), L.ptr(rvar),
+                L.ptr(nbt), L.ptr(out), L.ptr(save_mean), L.ptr(save_rstd), float(eps), float(momentum), act,
+                L.ptr(ws), ws.numel(), L.byref(dims), L.dtype_code(y), L.stream_ptr())
+        else:
+            fn = L.lib().lmnet_bn_act_cl_fwd if ctx.cl else L.lib().lmnet_bn_act_fwd
+            rc = fn(L.ptr(y), L.ptr(g32), L.ptr(b32), L.ptr(rmean), L.ptr(rvar), L.ptr(nbt),
+                    L.ptr(out), L.ptr(save_mean), L.ptr(save_rstd), float(eps), float(momentum),
+                    1, act, L.ptr(ws), ws.numel(), L.byref(dims), L.dtype_code(y), L.stream_ptr())
         L.check(rc, "bn_act_fwd")
         ctx.save_for_backward(y, g32, b32, save_mean, save_rstd)
         ctx.act = act
@@ -87,11 +96,13 @@ class _BNActTrain(torch.autograd.Function):
                 L.ptr(ws), ws.numel(), L.byref(dims), L.dtype_code(y), L.stream_ptr())
         L.check(rc, "bn_act_bwd")
         gd, bd = ctx.meta
-        return (dy, None if gd is None else dgamma.to(gd), None if bd is None else dbeta.to(bd), None, None, None, None)
+        return (dy, None if gd is None else dgamma.to(gd), None if bd is None else dbeta.to(bd), None, None, None, None, None)
 
 
-def bn_act(bn: torch.nn.BatchNorm2d, y: torch.Tensor, act: str = "none") -> torch.Tensor:
-    """activation(bn(y)) in one pass pair.  `act` in {"none", "hardswish", "gelu", "relu"}."""
+def bn_act(bn: torch.nn.BatchNorm2d, y: torch.Tensor, act: str = "none", stats=None) -> torch.Tensor:
+    """activation(bn(y)) in one pass pair.  `act` in {"none", "hardswish", "gelu", "relu"}.  `stats`: optional fp32
+    [C, chunks, 2] per-chunk (sum, sum of squares) of y already reduced by its producer (conv1x1.expand_1x1); used in
+    training mode on NCHW planes, where it replaces the statistics pass."""
     code = L.ACT_CODES[act]
     if y.dim() < 2 or y.shape[1] != bn.num_features:
         raise ValueError(f"expected {bn.num_features} channels, got input of shape {tuple(y.shape)}")
@@ -108,7 +119,7 @@ def bn_act(bn: torch.nn.BatchNorm2d, y: torch.Tensor, act: str = "none") -> torc
             if bn.num_batches_tracked is not None and bn.num_batches_tracked.dtype != torch.int64:
                 raise NotImplementedError("num_batches_tracked must be int64")
         running = (bn.running_mean, bn.running_var, bn.num_batches_tracked) if update else (None, None, None)
-        return _BNActTrain.apply(y, bn.weight, bn.bias, running, bn.eps, bn.momentum, code)
+        return _BNActTrain.apply(y, bn.weight, bn.bias, running, bn.eps, bn.momentum, code, stats)
     if torch.is_grad_enabled() and (y.requires_grad or (bn.weight is not None and bn.weight.requires_grad)):
         raise NotImplementedError("gradients through eval-mode fused BatchNorm are not implemented; use torch.no_grad()")
     L.require_cuda(y)

@@ -136,6 +136,44 @@ def wgrad_cl_supported(B, M, N1, N2, P, a_cl, b1_cl, dtype) -> bool:
     return bool(L.lib().lmnet_wgrad_1x1_cl_supported(L.byref(dims), int(a_cl), int(b1_cl), L._DTYPES[dtype]))
 
 
+def _pgemm_dims(B, P, N, K1, K2):
+    return L.PgemmDims(B, P, N, K1, K2)
+
+
+def pgemm_supported(B, P, N, K1, K2, in1_cl, out_cl, stats, dtype) -> bool:
+    if dtype not in (torch.bfloat16, torch.float16):
+        return False
+    return bool(L.lib().lmnet_pixel_gemm_supported(L.byref(_pgemm_dims(B, P, N, K1, K2)), int(in1_cl), int(out_cl),
+                                                   int(stats), L._DTYPES[dtype]))
+
+
+def pixel_gemm(in1, in1_cl, w1, in2=None, w2=None, bias=None, out_cl=True, stats=False):
+    """out[b] = W1 . in1[b] (+ W2 . in2[b]) (+ bias) over the pixels of every image (csrc/pixel_gemm.cu).
+
+    in1: [B,P,K1] (in1_cl) or [B,K1,P] planes; w1: [N,K1] or per-image [B,N,K1]; in2: [B,P,K2] channels-last with
+    w2 [N,K2]; bias fp32 [N].  Returns out ([B,P,N] if out_cl else [B,N,P]) and, with stats=True, the per-CTA
+    (sum, sum of squares) partials [N, ctas, 2] of the stored output for lmnet_bn_act_fwd_stats."""
+    B = in1.shape[0]
+    P, K1 = (in1.shape[1], in1.shape[2]) if in1_cl else (in1.shape[2], in1.shape[1])
+    N = w1.shape[-2]
+    K2 = 0 if in2 is None else in2.shape[2]
+    dt = in1.dtype
+    dims = _pgemm_dims(B, P, N, K1, K2)
+    w1 = w1.to(dt).contiguous()
+    w2 = None if w2 is None else w2.to(dt).contiguous()
+    bias = None if bias is None else bias.detach().float().contiguous()
+    out = torch.empty((B, P, N) if out_cl else (B, N, P), dtype=dt, device=in1.device)
+    part = None
+    if stats:
+        ctas = L.lib().lmnet_pixel_gemm_stats_ctas(L.byref(dims), int(in1_cl), int(out_cl))
+        part = torch.empty(N, ctas, 2, dtype=torch.float32, device=in1.device)
+    rc = L.lib().lmnet_pixel_gemm(L.ptr(in1), int(in1_cl), L.ptr(w1), int(w1.dim() == 3), L.ptr(in2), L.ptr(w2),
+                                  L.ptr(bias), L.ptr(out), int(out_cl), L.ptr(part), L.byref(dims), L.dtype_code(in1),
+                                  L.stream_ptr())
+    L.check(rc, "pixel_gemm")
+    return out, part
+
+
 def is_channels_last(t: torch.Tensor) -> bool:
     return t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last) and not t.is_contiguous()
 
@@ -154,36 +192,48 @@ def _as_cl(t_bpc, H, W):
 
 class _Expand1x1Cl(torch.autograd.Function):
     """x channels-last [B,K,H,W] -> y[b] = W @ x[b]^T + bias as NCHW planes [B,M,H,W] (what the fused BatchNorm and
-    the depthwise section read).  The layout change rides on the GEMM's operand order: no transposed copy exists."""
+    the depthwise section read).  The layout change rides on the GEMM's operand order: no transposed copy exists.
+    Second output: BatchNorm (sum, sum of squares) partials of y from the GEMM's epilogue (or None)."""
 
     @staticmethod
     @custom_fwd(device_type="cuda")
-    def forward(ctx, x, w, bias):
+    def forward(ctx, x, w, bias, want_stats):
         B, K, H, Wd = x.shape
         M = w.shape[0]
+        P = H * Wd
         xp = _pixels(x)                                                    # [B, P, K]
-        wc = w.to(x.dtype).unsqueeze(0).expand(B, M, K)
-        xt = xp.transpose(1, 2)                                            # [B, K, P] view
-        y = torch.baddbmm(bias.to(x.dtype).view(1, M, 1), wc, xt) if bias is not None else torch.bmm(wc, xt)
+        part = None
+        if pgemm_supported(B, P, M, K, 0, True, False, want_stats, x.dtype):
+            y, part = pixel_gemm(xp, True, w, bias=bias, out_cl=False, stats=want_stats)
+        else:
+            wc = w.to(x.dtype).unsqueeze(0).expand(B, M, K)
+            xt = xp.transpose(1, 2)                                        # [B, K, P] view
+            y = torch.baddbmm(bias.to(x.dtype).view(1, M, 1), wc, xt) if bias is not None else torch.bmm(wc, xt)
         ctx.save_for_backward(x, w)
         ctx.has_bias = bias is not None
         ctx.bias_dtype = None if bias is None else bias.dtype
-        return y.view(B, M, H, Wd)
+        if part is not None:
+            ctx.mark_non_differentiable(part)
+        return y.view(B, M, H, Wd), part
 
     @staticmethod
     @custom_bwd(device_type="cuda")
-    def backward(ctx, dy):
+    def backward(ctx, dy, _dpart=None):
         x, w = ctx.saved_tensors
         B, K, H, Wd = x.shape
         M = w.shape[0]
-        dyf = dy.to(x.dtype).contiguous().view(B, M, H * Wd)
+        P = H * Wd
+        dyf = dy.to(x.dtype).contiguous().view(B, M, P)
         dx = None
         if ctx.needs_input_grad[0]:
-            dx = _as_cl(torch.bmm(dyf.transpose(1, 2), w.to(x.dtype).unsqueeze(0).expand(B, M, K)), H, Wd)
+            if pgemm_supported(B, P, K, M, 0, False, True, False, x.dtype):
+                dx = _as_cl(pixel_gemm(dyf, False, w.t(), out_cl=True)[0], H, Wd)
+            else:
+                dx = _as_cl(torch.bmm(dyf.transpose(1, 2), w.to(x.dtype).unsqueeze(0).expand(B, M, K)), H, Wd)
         dW, drow = _wgrad_cl(dyf, _pixels(x), None, False, True)
         dw = dW.sum(0).to(w.dtype)
         db = drow.sum(0).to(ctx.bias_dtype) if ctx.has_bias else None
-        return dx, dw, db
+        return dx, dw, db, None
 
 
 class _PointwiseShortcutCl(torch.autograd.Function):
@@ -198,8 +248,11 @@ class _PointwiseShortcutCl(torch.autograd.Function):
         dt = z.dtype
         wg = (wpw.float().unsqueeze(0) * gate.float().unsqueeze(1)).to(dt)            # [B, Cout, E]
         xp = _pixels(x)                                                                # [B, P, Cin]
-        out = torch.baddbmm(bias.to(dt).view(1, 1, Cout), xp, wsc.to(dt).t().unsqueeze(0).expand(B, Cin, Cout))
-        out = torch.baddbmm(out, z.view(B, E, P).transpose(1, 2), wg.transpose(1, 2))  # [B, P, Cout]
+        if pgemm_supported(B, P, Cout, E, Cin, False, True, False, dt):
+            out = pixel_gemm(z.view(B, E, P), False, wg, xp, wsc, bias, out_cl=True)[0]
+        else:
+            out = torch.baddbmm(bias.to(dt).view(1, 1, Cout), xp, wsc.to(dt).t().unsqueeze(0).expand(B, Cin, Cout))
+            out = torch.baddbmm(out, z.view(B, E, P).transpose(1, 2), wg.transpose(1, 2))  # [B, P, Cout]
         ctx.save_for_backward(z, gate, x, wpw, wsc, wg)
         ctx.bias_dtype = bias.dtype
         return _as_cl(out, H, Wd)
@@ -213,10 +266,16 @@ class _PointwiseShortcutCl(torch.autograd.Function):
         P = H * Wd
         dt = z.dtype
         do = _pixels(dout.to(dt).contiguous(memory_format=torch.channels_last))        # [B, P, Cout]
-        dz = torch.bmm(wg.transpose(1, 2), do.transpose(1, 2)).view(B, E, H, Wd)       # planes
+        if pgemm_supported(B, P, E, Cout, 0, True, False, False, dt):
+            dz = pixel_gemm(do, True, wg.transpose(1, 2), out_cl=False)[0].view(B, E, H, Wd)
+        else:
+            dz = torch.bmm(wg.transpose(1, 2), do.transpose(1, 2)).view(B, E, H, Wd)   # planes
         dx = None
         if ctx.needs_input_grad[2]:
-            dx = _as_cl(torch.bmm(do, wsc.to(dt).unsqueeze(0).expand(B, Cout, Cin)), H, Wd)
+            if pgemm_supported(B, P, Cin, Cout, 0, True, True, False, dt):
+                dx = _as_cl(pixel_gemm(do, True, wsc.t(), out_cl=True)[0], H, Wd)
+            else:
+                dx = _as_cl(torch.bmm(do, wsc.to(dt).unsqueeze(0).expand(B, Cout, Cin)), H, Wd)
         dW, drow = _wgrad_cl(do, z.view(B, E, P), _pixels(x), True, False)             # [B, Cout, E + Cin]
         dWg = dW[:, :, :E]
         dwpw = (dWg * gate.float().unsqueeze(1)).sum(0).to(wpw.dtype)
@@ -247,23 +306,28 @@ def to_channels_last(x: torch.Tensor, dt=None) -> torch.Tensor:
     return x.to(dt).contiguous(memory_format=torch.channels_last)
 
 
-def expand_1x1(conv: torch.nn.Conv2d, x: torch.Tensor) -> torch.Tensor:
+def expand_1x1(conv: torch.nn.Conv2d, x: torch.Tensor, want_stats: bool = False):
     """conv(x) for a 1x1 convolution on a CUDA tensor; returns NCHW planes.  Channels-last inputs take the mixed-layout
-    path (no transposed copy); plain NCHW inputs the plane-wise one; cuDNN through the module for uncovered shapes."""
+    path (no transposed copy); plain NCHW inputs the plane-wise one; cuDNN through the module for uncovered shapes.
+    With want_stats=True returns (y, partials): BatchNorm (sum, sum of squares) partials of y out of the GEMM's epilogue
+    for bnact.bn_act(..., stats=partials), or None where the producing kernel does not emit them."""
     L.require_cuda(x)
     dt = _compute_dtype(x)
     B, K, H, W = x.shape
     M = conv.out_channels
-    if is_channels_last(x) or (x.dim() == 4 and K == 1 and False):
+    if is_channels_last(x):
         w = conv.weight.view(M, K)
         xpad, wpad = _pad_channels(x.to(dt), w)
         if wgrad_cl_supported(B, M, xpad.shape[1], 0, H * W, False, True, dt):
             if xpad is not x:
                 xpad = xpad.contiguous(memory_format=torch.channels_last)
-            return _Expand1x1Cl.apply(xpad, wpad, conv.bias)
+            y, part = _Expand1x1Cl.apply(xpad, wpad, conv.bias, want_stats)
+            return (y, part) if want_stats else y
     if wgrad_supported(B, M, K, 0, H * W, dt):
-        return _Expand1x1.apply(x.to(dt).contiguous(), conv.weight.view(M, K), conv.bias)
-    return conv(x)
+        y = _Expand1x1.apply(x.to(dt).contiguous(), conv.weight.view(M, K), conv.bias)
+    else:
+        y = conv(x)
+    return (y, None) if want_stats else y
 
 
 def pointwise_shortcut(pw: torch.nn.Conv2d, sc: torch.nn.Conv2d, z, gate, x):

@@ -19,6 +19,7 @@ import torch
 
 from .bnact import conv_bn_act
 from .layernorm import layer_norm
+from .linear import linear
 from .reparam import patch_reparam_conv
 from .upsample import Upsample2x
 
@@ -27,11 +28,18 @@ def _cl(t):
     return t.contiguous(memory_format=torch.channels_last) if t.is_cuda else t
 
 
+def _mlp_forward(mlp, x):
+    """Mlp.forward (core/modules.py:50-56) with fc1 / fc2 on the pixel-GEMM kernels; GELU and Dropout as in the module."""
+    if not (type(mlp.fc1) is torch.nn.Linear and type(mlp.fc2) is torch.nn.Linear) or not x.is_cuda:
+        return mlp(x)
+    return mlp.dropout(linear(mlp.fc2, mlp.dropout(mlp.act_fn(linear(mlp.fc1, x)))))
+
+
 def _natt_forward(self, x):
     """NeighborhoodTransformer.forward (core/modules.py:514-521): 3x3 conv embed -> LN -> NA -> +res -> LN -> MLP -> +res."""
     emb = self.patchembedding(_cl(x))              # NHWC conv output: its [B,H,W,C] permute is a free view
     att = self.att1(layer_norm(self.norm1, emb)) + emb
-    y = self.mlp(layer_norm(self.norm2, att)) + att
+    y = _mlp_forward(self.mlp, layer_norm(self.norm2, att)) + att
     # logical NCHW on channels-last memory: a free view (every consumer is channels-last as well)
     return y.permute(0, 3, 1, 2) if y.is_cuda else y.permute(0, 3, 1, 2).contiguous()
 

@@ -216,7 +216,11 @@ def reparam_forward(self, x):
         x = to_channels_last(x, _compute_dtype(x))
     ec = self.expand_conv
     if len(ec) == 3 and _is_1x1(ec[0]) and type(ec[1]) is torch.nn.BatchNorm2d and type(ec[2]) is torch.nn.Hardswish:
-        x1 = bn_act(ec[1], expand_1x1(ec[0], x), "hardswish")     # plane-wise GEMM + fused BatchNorm + Hardswish
+        # pixel GEMM (BatchNorm sum / sum^2 from its epilogue in training) + fused BatchNorm + Hardswish
+        batch_stats = ec[1].training or ec[1].running_mean is None
+        y = expand_1x1(ec[0], x, want_stats=batch_stats)
+        y, part = y if batch_stats else (y, None)
+        x1 = bn_act(ec[1], y, "hardswish", stats=part)
     else:
         x1 = conv_bn_act(ec, x)
     if self.deploy:

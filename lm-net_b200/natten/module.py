@@ -12,6 +12,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from lmnet_b200 import na_ops
+from lmnet_b200.linear import linear
 
 
 class NeighborhoodAttention2D(nn.Module):
@@ -52,7 +53,7 @@ class NeighborhoodAttention2D(nn.Module):
             pad_b = max(0, self.window_size - H)
             x = F.pad(x, (0, 0, 0, pad_r, 0, pad_b))
             _, H, W, _ = x.shape
-        qkv = self.qkv(x).view(B, H, W, 3, self.num_heads, self.head_dim)
+        qkv = linear(self.qkv, x).view(B, H, W, 3, self.num_heads, self.head_dim)
         if self.training and self.attn_drop.p > 0.0:
             q, k, v = qkv.permute(3, 0, 4, 1, 2, 5).unbind(0)
             attn = na_ops.na2d_qk(q * self.scale, k, self.kernel_size, self.dilation, rel_pos_bias=self.rpb)
@@ -63,7 +64,7 @@ class NeighborhoodAttention2D(nn.Module):
         o = o.reshape(B, H, W, C)
         if pad_r or pad_b:
             o = o[:, :Hp, :Wp, :]
-        return self.proj_drop(self.proj(o))
+        return self.proj_drop(linear(self.proj, o))
 
     def extra_repr(self):
         return (f"head_dim={self.head_dim}, num_heads={self.num_heads}, kernel_size={self.kernel_size}, "

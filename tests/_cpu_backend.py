@@ -54,13 +54,13 @@ def apply(setattr_fn):
 
     from lmnet_b200 import bnact
 
-    def bn_act_ref(bn, y, act="none"):
+    def bn_act_ref(bn, y, act="none", stats=None):
         out = bn(y)
         return {"none": lambda t: t, "hardswish": F.hardswish, "gelu": F.gelu, "relu": F.relu}[act](out)
 
     setattr_fn(bnact, "bn_act", bn_act_ref)
     setattr_fn(reparam, "bn_act", bn_act_ref)
-    setattr_fn(reparam, "expand_1x1", lambda conv, x: conv(x))
+    setattr_fn(reparam, "expand_1x1", lambda conv, x, want_stats=False: (conv(x), None) if want_stats else conv(x))
     setattr_fn(reparam, "pointwise_shortcut", lambda pw, sc, z, gate, x: pw(gate * z) + sc(x))
     from lmnet_b200 import patch
 

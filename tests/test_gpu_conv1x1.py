@@ -141,3 +141,75 @@ def test_channels_last_expand_and_pointwise_shortcut_vs_modules(shape):
     for m, r in ((ex, rex), (pw, rpw), (sc, rsc)):
         assert rel_err(m.weight.grad.cpu(), r.weight.grad) < tol
         assert rel_err(m.bias.grad.cpu(), r.bias.grad) < tol
+
+
+# (B, P, N, K1, K2): the five roles of csrc/pixel_gemm.cu at LM-Net's channel counts, incl. a ragged last tile
+PG_CASES = [(2, 960, 24, 12, 0), (2, 352, 24, 4, 0), (2, 1000, 48, 24, 0), (3, 136, 96, 48, 0), (2, 64, 192, 96, 0),
+            (1, 123904, 24, 12, 0)]
+
+
+@pytest.mark.parametrize("case", PG_CASES, ids=lambda s: "x".join(map(str, s)))
+def test_raw_pixel_gemm_all_roles_vs_einsum(case):
+    """out = W1.in1 (+ W2.in2) (+ bias) for every operand-layout combination the block uses; fp64 einsum of the same
+    bf16-rounded operands, so the only error is the fp32 accumulation order and the final rounding to bf16."""
+    from lmnet_b200.conv1x1 import pgemm_supported, pixel_gemm
+
+    B, P, E, C, _ = case                       # E = expanded channels, C = block channels
+    g = torch.Generator().manual_seed(5)
+    bf = torch.bfloat16
+
+    def rnd(*shape):
+        return torch.randn(*shape, generator=g).to(bf)
+
+    def close(got, want):
+        assert rel_err(got.float().cpu(), want) < 6e-3      # one bf16 rounding of the output (2^-9) + accumulation order
+
+    x_cl, dy_pl, z_pl, do_cl = rnd(B, P, C), rnd(B, E, P), rnd(B, E, P), rnd(B, P, C)
+    w_ex, w_pw, w_sc = rnd(E, C), rnd(B, C, E), rnd(C, C)
+    bias_e, bias_c = torch.randn(E, generator=g), torch.randn(C, generator=g)
+    # expand forward: channels-last -> planes, with BatchNorm partial sums
+    assert pgemm_supported(B, P, E, C, 0, True, False, True, bf)
+    y, part = pixel_gemm(x_cl.cuda(), True, w_ex.cuda(), bias=bias_e.cuda(), out_cl=False, stats=True)
+    want = torch.einsum("nk,bpk->bnp", w_ex.double(), x_cl.double()) + bias_e.double().view(1, E, 1)
+    close(y, want)
+    yd = y.double().cpu()
+    tot = part.double().sum(1).cpu()
+    assert rel_err(tot[:, 0], yd.sum((0, 2))) < 1e-5 and rel_err(tot[:, 1], (yd * yd).sum((0, 2))) < 1e-5
+    # expand input gradient: planes -> channels-last
+    if pgemm_supported(B, P, C, E, 0, False, True, False, bf):
+        dx, _ = pixel_gemm(dy_pl.cuda(), False, w_ex.t().cuda(), out_cl=True)
+        close(dx, torch.einsum("nk,bnp->bpk", w_ex.double(), dy_pl.double()))
+    # pointwise (per-image weights, planes) + shortcut (channels-last) -> channels-last
+    if pgemm_supported(B, P, C, E, C, False, True, False, bf):
+        o, _ = pixel_gemm(z_pl.cuda(), False, w_pw.cuda(), x_cl.cuda(), w_sc.cuda(), bias_c.cuda(), out_cl=True)
+        want = (torch.einsum("bne,bep->bpn", w_pw.double(), z_pl.double()) +
+                torch.einsum("nk,bpk->bpn", w_sc.double(), x_cl.double()) + bias_c.double().view(1, 1, C))
+        close(o, want)
+    # pointwise input gradient: channels-last, per-image weights -> planes
+    assert pgemm_supported(B, P, E, C, 0, True, False, False, bf)
+    dz, _ = pixel_gemm(do_cl.cuda(), True, w_pw.transpose(1, 2).cuda(), out_cl=False)
+    close(dz, torch.einsum("bne,bpn->bep", w_pw.double(), do_cl.double()))
+    # shortcut input gradient: channels-last -> channels-last
+    assert pgemm_supported(B, P, C, C, 0, True, True, False, bf)
+    dxs, _ = pixel_gemm(do_cl.cuda(), True, w_sc.t().cuda(), out_cl=True)
+    close(dxs, torch.einsum("nk,bpn->bpk", w_sc.double(), do_cl.double()))
+
+
+def test_expand_bn_hardswish_with_epilogue_statistics_matches_separate_statistics_pass():
+    """BatchNorm driven by the GEMM epilogue's partial sums == BatchNorm with its own statistics pass (same y)."""
+    from lmnet_b200.bnact import bn_act
+    from lmnet_b200.conv1x1 import expand_1x1
+
+    torch.manual_seed(2)
+    conv = torch.nn.Conv2d(12, 24, 1).cuda()
+    bn1, bn2 = torch.nn.BatchNorm2d(24).cuda().train(), torch.nn.BatchNorm2d(24).cuda().train()
+    x = torch.randn(4, 12, 40, 36, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y, part = expand_1x1(conv, x, want_stats=True)
+        assert part is not None and part.shape[0] == 24
+        a = bn_act(bn1, y, "hardswish", stats=part)
+        b = bn_act(bn2, y, "hardswish")
+    assert rel_err(a.float(), b.float()) < 1e-6 * 0 + 4e-3       # coefficients differ by fp32 summation order only
+    assert torch.allclose(bn1.running_mean, bn2.running_mean, rtol=1e-5, atol=1e-7)
+    assert torch.allclose(bn1.running_var, bn2.running_var, rtol=1e-5, atol=1e-7)
+    assert int(bn1.num_batches_tracked) == 1
