@@ -267,6 +267,27 @@ int lmnet_bn_act_fwd_stats(const void* y, const float* stats_part, int nchunks, 
                            float* save_mean, float* save_rstd, float eps, float momentum, int act,
                            void* workspace, size_t workspace_bytes, const lmnet_bn_dims* dims, int dtype, void* stream);
 
+/* ---- dense 3x3 convolution, padding 1, stride 1 or 2, channels-last (widening step f3) ---------------------
+ * Replaces the nn.Conv2d(.., 3, stride, 1) layers of LM-Net outside ReparamConv: down1-4 / up1-4
+ * (/root/reference/core/LM_Net.py:14-39, 58-74), M2Skip / M3Skip (/root/reference/core/modules.py:83-143) and the
+ * OverlapPatchEmbed of the neighbourhood transformers (/root/reference/core/modules.py:30-39), where the channel counts
+ * fit the resident-weights kernel (lmnet_conv3x3_*_supported); cuDNN keeps the wide, low-resolution layers.
+ * x: [B, H, W, Cin], y / dy: [B, Ho, Wo, Cout] with Ho = (H - 1) / stride + 1; 16-bit dtypes; Cin, Cout % 4 == 0.
+ * w_packed: [9][Cout][Cin] in `dtype` (tap = ky * 3 + kx, i.e. weight.permute(2, 3, 0, 1)); bias fp32 [Cout] or NULL.
+ * The stride-1 input gradient is the same call on dy with w_packed[tap][ci][co] = weight[co][ci][2 - ky][2 - kx].
+ * wgrad: dW fp32 in torch layout [Cout][Cin][3][3], dbias fp32 [Cout] (or NULL); deterministic (per-CTA partials in the
+ * workspace + fixed-order reduction). */
+typedef struct lmnet_conv3x3_dims {
+    int32_t B, H, W, Cin, Cout, stride;
+} lmnet_conv3x3_dims;
+int lmnet_conv3x3_fwd_supported(const lmnet_conv3x3_dims* dims, int dtype);
+int lmnet_conv3x3_fwd(const void* x, const void* w_packed, const float* bias, void* y, const lmnet_conv3x3_dims* dims,
+                      int dtype, void* stream);
+int lmnet_conv3x3_wgrad_supported(const lmnet_conv3x3_dims* dims, int dtype);
+size_t lmnet_conv3x3_wgrad_workspace_bytes(const lmnet_conv3x3_dims* dims);
+int lmnet_conv3x3_wgrad(const void* x, const void* dy, float* dW, float* dbias, void* workspace, size_t workspace_bytes,
+                        const lmnet_conv3x3_dims* dims, int dtype, void* stream);
+
 /* ---- bilinear x2 up-sampling, align_corners=True, NCHW (widening step f3) ----------------------
  * Replaces nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True) of the decoder and skip blocks
  * (/root/reference/core/LM_Net.py:58-74, /root/reference/core/modules.py:93-95, 129-131).

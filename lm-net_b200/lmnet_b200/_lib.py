@@ -66,6 +66,10 @@ class PgemmDims(Structure):
     _fields_ = [("B", c_int32), ("P", c_int64), ("N", c_int32), ("K1", c_int32), ("K2", c_int32)]
 
 
+class Conv3x3Dims(Structure):
+    _fields_ = [("B", c_int32), ("H", c_int32), ("W", c_int32), ("Cin", c_int32), ("Cout", c_int32), ("stride", c_int32)]
+
+
 _lib = None
 
 
@@ -135,6 +139,13 @@ def lib():
                                    c_void_p, ppg, c_int, c_void_p]
     L.lmnet_bn_act_fwd_stats.argtypes = [c_void_p, c_void_p, c_int] + [c_void_p] * 8 + [c_float, c_float, c_int, c_void_p,
                                                                                       c_size_t, pbd, c_int, c_void_p]
+    pcv = POINTER(Conv3x3Dims)
+    L.lmnet_conv3x3_fwd_supported.argtypes = [pcv, c_int]
+    L.lmnet_conv3x3_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, pcv, c_int, c_void_p]
+    L.lmnet_conv3x3_wgrad_supported.argtypes = [pcv, c_int]
+    L.lmnet_conv3x3_wgrad_workspace_bytes.restype = c_size_t
+    L.lmnet_conv3x3_wgrad_workspace_bytes.argtypes = [pcv]
+    L.lmnet_conv3x3_wgrad.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, pcv, c_int, c_void_p]
     pud = POINTER(UpsampleDims)
     L.lmnet_upsample2x_fwd.argtypes = [c_void_p, c_void_p, pud, c_int, c_void_p]
     L.lmnet_upsample2x_bwd.argtypes = [c_void_p, c_void_p, pud, c_int, c_void_p]
@@ -249,4 +260,4 @@ def dw_grads(dw, dgamma, dbeta) -> DwGrads:
 
 
 __all__ = ["lib", "check", "dtype_code", "require_cuda", "stream_ptr", "ptr", "view5", "na_dims", "dw_params",
-           "dw_grads", "View5", "NADims", "DwParams", "DwGrads", "DwDims", "BnDims", "ACT_CODES", "WgradDims", "PgemmDims", "UpsampleDims", "UpsampleClDims", "byref", "launch_count", "LIB_PATH"]
+           "dw_grads", "View5", "NADims", "DwParams", "DwGrads", "DwDims", "BnDims", "ACT_CODES", "WgradDims", "PgemmDims", "Conv3x3Dims", "UpsampleDims", "UpsampleClDims", "byref", "launch_count", "LIB_PATH"]

@@ -24,6 +24,7 @@ from torch import nn
 
 from natten import NeighborhoodAttention2D
 
+from .conv3x3 import Conv3x3
 from .patch import _cl, _m2skip_forward, _m3skip_forward, _natt_forward
 from .reparam import reparam_forward
 from .upsample import Upsample2x
@@ -118,7 +119,7 @@ class OverlapPatchEmbed(nn.Module):
     def __init__(self, patch, channels_in, channels_out, stride, channels_last: bool):
         super().__init__()
         self.channels_last = channels_last
-        self.patch_embeddings = nn.Conv2d(channels_in, channels_out, patch, stride, patch // 2)
+        self.patch_embeddings = (Conv3x3 if patch == 3 else nn.Conv2d)(channels_in, channels_out, patch, stride, patch // 2)
 
     def forward(self, x):
         x = self.patch_embeddings(x)
@@ -159,10 +160,10 @@ class M3Skip(nn.Module):
     def __init__(self, ch):
         super().__init__()
         lo, mid, hi = ch
-        self.convl = nn.Sequential(nn.Conv2d(lo, mid, 3, 2, 1))
-        self.convm = nn.Sequential(nn.Conv2d(mid, mid, 3, 1, 1))
-        self.convs = nn.Sequential(_up2(), nn.Conv2d(hi, mid, 3, 1, 1))
-        self.fuse_conv = nn.Sequential(nn.Conv2d(3 * mid, mid, 3, 1, 1), nn.BatchNorm2d(mid), nn.GELU())
+        self.convl = nn.Sequential(Conv3x3(lo, mid, 3, 2, 1))
+        self.convm = nn.Sequential(Conv3x3(mid, mid, 3, 1, 1))
+        self.convs = nn.Sequential(_up2(), Conv3x3(hi, mid, 3, 1, 1))
+        self.fuse_conv = nn.Sequential(Conv3x3(3 * mid, mid, 3, 1, 1), nn.BatchNorm2d(mid), nn.GELU())
 
     forward = _m3skip_forward
 
@@ -175,14 +176,14 @@ class M2Skip(nn.Module):
         big, small = ch
         self.model_type = model_type
         if model_type == "bottom":
-            self.convl = nn.Sequential(nn.Conv2d(big, small, 3, 2, 1))
-            self.convs = nn.Sequential(nn.Conv2d(small, small, 3, 1, 1))
+            self.convl = nn.Sequential(Conv3x3(big, small, 3, 2, 1))
+            self.convs = nn.Sequential(Conv3x3(small, small, 3, 1, 1))
             width = small
         else:
-            self.convl = nn.Sequential(nn.Conv2d(big, big, 3, 1, 1))
-            self.convs = nn.Sequential(_up2(), nn.Conv2d(small, big, 3, 1, 1))
+            self.convl = nn.Sequential(Conv3x3(big, big, 3, 1, 1))
+            self.convs = nn.Sequential(_up2(), Conv3x3(small, big, 3, 1, 1))
             width = big
-        self.fuse_conv = nn.Sequential(nn.Conv2d(2 * width, width, 3, 1, 1), nn.BatchNorm2d(width), nn.GELU())
+        self.fuse_conv = nn.Sequential(Conv3x3(2 * width, width, 3, 1, 1), nn.BatchNorm2d(width), nn.GELU())
 
     forward = _m2skip_forward
 
@@ -252,10 +253,10 @@ class LM_Net(nn.Module):
             return nn.Sequential(ReparamConv(cin, 2 * width, width), ReparamConv(width, 2 * width, width))
 
         def down(cin, cout):
-            return nn.Sequential(nn.Conv2d(cin, cout, 3, 2, 1))
+            return nn.Sequential(Conv3x3(cin, cout, 3, 2, 1))
 
         def up(cin, cout):
-            return nn.Sequential(_up2(), nn.Conv2d(cin, cout, 3, 1, 1))
+            return nn.Sequential(_up2(), Conv3x3(cin, cout, 3, 1, 1))
 
         # registration order follows the reference so that state_dict() enumerates identically
         self.conv1, self.down1 = stage(channel, f[0]), down(f[0], f[1])

@@ -2,15 +2,16 @@
 
     import sys; sys.path.insert(0, ".../lm-net_b200")       # `import natten` now resolves to the drop-in
     import core.modules, core.LM_Net
-    from lmnet_b200.patch import patch_reference_modules, convert_upsample
+    from lmnet_b200.patch import patch_reference_modules, convert_model
     patch_reference_modules(core.modules)                    # class-level forward swaps, nothing else changes
-    model = convert_upsample(core.LM_Net.LM_Net(3, 2).cuda())
+    model = convert_model(core.LM_Net.LM_Net(3, 2).cuda())   # re-classes nn.Upsample / 3x3 nn.Conv2d instances in place
 
 What is swapped (constructors, sub-module names and therefore checkpoints stay untouched):
   ReparamConv.forward            core/modules.py:586-600   -> lmnet_b200.reparam.reparam_forward
   NeighborhoodTransformer.forward core/modules.py:514-521  -> fused LayerNorm + channels-last patch embedding
   M3Skip.forward / M2Skip.forward core/modules.py:101-107, 138-143 -> fused BatchNorm+GELU, channels-last 3x3 convs
   nn.Upsample(scale_factor=2, bilinear, align_corners=True) instances -> lmnet_b200.upsample.Upsample2x
+  nn.Conv2d(.., 3, stride 1|2, padding 1) instances -> lmnet_b200.conv3x3.Conv3x3 (same parameters / state_dict keys)
 NeighborhoodAttention2D itself comes from the drop-in `natten` package.
 """
 from __future__ import annotations
@@ -18,6 +19,7 @@ from __future__ import annotations
 import torch
 
 from .bnact import conv_bn_act
+from .conv3x3 import convert_conv3x3
 from .layernorm import layer_norm
 from .linear import linear
 from .reparam import patch_reparam_conv
@@ -76,3 +78,8 @@ def convert_upsample(model: torch.nn.Module) -> torch.nn.Module:
                     and child.scale_factor in (2, 2.0, (2, 2), (2.0, 2.0)):
                 setattr(parent, name, Upsample2x())
     return model
+
+
+def convert_model(model: torch.nn.Module) -> torch.nn.Module:
+    """Everything instance-level in one call: bilinear x2 up-sampling and the dense 3x3 convolutions (in place)."""
+    return convert_conv3x3(convert_upsample(model))
