@@ -23,115 +23,9 @@
 //   * per-CTA partials + a fixed-order reduction kernel: deterministic, no atomics.
 // mma.sync rather than tcgen05: N = 12 .. 48 output channels and K = 12 .. 72 per tap are far below a 128 x N x 16 UMMA
 // tile, and the kernels are bounded by HBM / issue, not by the tensor pipe.
-#include "common.cuh"
+#include "conv3x3.cuh"
 
 namespace lmnet {
-
-constexpr int kCvThreads = 256;
-constexpr int kCvWarps = 8;
-constexpr int kCvWgThreads = 288;      // weight gradient: one warp per tap
-constexpr int kCvTW = 16;              // output pixels per tile row = one MMA M tile
-
-struct CvGeom {
-    int B, H, W, Ho, Wo, Cin, Cout, S;
-    int pitch_x, pitch_w, pitch_o;     // element pitches: staged input pixel, weight row, staged output pixel
-    int TH, IH, IW;                    // output rows per tile; staged input rows / pixels per row
-    int tiles_x, tiles_y, tiles;
-    int ksteps;                        // ceil(Cin / 16)
-    int ncta;
-};
-
-__device__ __forceinline__ void cv_cp16(void* smem, const void* gmem, bool valid) {
-    const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
-    const int sz = valid ? 16 : 0;
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(sz));
-}
-__device__ __forceinline__ void cv_cp8(void* smem, const void* gmem, bool valid) {
-    const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
-    const int sz = valid ? 8 : 0;
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(s), "l"(gmem), "r"(sz));
-}
-__device__ __forceinline__ void cv_commit() { asm volatile("cp.async.commit_group;"); }
-template <int N> __device__ __forceinline__ void cv_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
-
-__device__ __forceinline__ void cv_ldsm_x4(uint32_t (&r)[4], const void* p) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"((uint32_t)__cvta_generic_to_shared(p)));
-}
-__device__ __forceinline__ void cv_ldsm_x4_t(uint32_t (&r)[4], const void* p) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"((uint32_t)__cvta_generic_to_shared(p)));
-}
-__device__ __forceinline__ void cv_ldsm_x2(uint32_t (&r)[2], const void* p) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];"
-                 : "=r"(r[0]), "=r"(r[1]) : "r"((uint32_t)__cvta_generic_to_shared(p)));
-}
-__device__ __forceinline__ void cv_ldsm_x2_t(uint32_t (&r)[2], const void* p) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];"
-                 : "=r"(r[0]), "=r"(r[1]) : "r"((uint32_t)__cvta_generic_to_shared(p)));
-}
-template <typename T> __device__ __forceinline__ void cv_mma(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]);
-template <> __device__ __forceinline__ void cv_mma<__nv_bfloat16>(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
-}
-template <> __device__ __forceinline__ void cv_mma<__half>(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
-}
-template <typename T> __device__ __forceinline__ uint32_t cv_pack(float lo, float hi);
-template <> __device__ __forceinline__ uint32_t cv_pack<__nv_bfloat16>(float lo, float hi) {
-    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-    return *reinterpret_cast<uint32_t*>(&v);
-}
-template <> __device__ __forceinline__ uint32_t cv_pack<__half>(float lo, float hi) {
-    __half2 v = __floats2half2_rn(lo, hi);
-    return *reinterpret_cast<uint32_t*>(&v);
-}
-template <typename T> __device__ __forceinline__ uint32_t cv_ones();
-template <> __device__ __forceinline__ uint32_t cv_ones<__nv_bfloat16>() { return 0x3f803f80u; }
-template <> __device__ __forceinline__ uint32_t cv_ones<__half>() { return 0x3c003c00u; }
-
-struct CvTile {
-    int b, oy0, ox0;
-};
-__device__ __forceinline__ CvTile cv_tile(const CvGeom& g, int t) {
-    CvTile r;
-    const int per_img = g.tiles_x * g.tiles_y;
-    r.b = t / per_img;
-    const int k = t - r.b * per_img;
-    const int ty = k / g.tiles_x;
-    r.oy0 = ty * g.TH;
-    r.ox0 = (k - ty * g.tiles_x) * kCvTW;
-    return r;
-}
-
-// stage the input tile of output tile `tl`: IH x IW pixels starting at (oy0*S - 1, ox0*S - 1), zero outside the image
-template <typename T, int NTHREADS>
-__device__ __forceinline__ void cv_issue_x(T* s, const T* __restrict__ x, const CvGeom& g, const CvTile& tl) {
-    const int iy0 = tl.oy0 * g.S - 1, ix0 = tl.ox0 * g.S - 1;
-    const T* xb = x + (int64_t)tl.b * g.H * g.W * g.Cin;
-    const int npix = g.IH * g.IW;
-    if ((g.Cin & 7) == 0) {
-        const int vpp = g.Cin >> 3;
-        for (int i = threadIdx.x; i < npix * vpp; i += NTHREADS) {
-            const int pix = i / vpp, v = i - pix * vpp;
-            const int r = pix / g.IW, c = pix - r * g.IW;
-            const int iy = iy0 + r, ix = ix0 + c;
-            const bool ok = iy >= 0 && iy < g.H && ix >= 0 && ix < g.W;
-            cv_cp16(s + pix * g.pitch_x + v * 8, ok ? xb + ((int64_t)iy * g.W + ix) * g.Cin + v * 8 : x, ok);
-        }
-    } else {
-        const int vpp = g.Cin >> 2;
-        for (int i = threadIdx.x; i < npix * vpp; i += NTHREADS) {
-            const int pix = i / vpp, v = i - pix * vpp;
-            const int r = pix / g.IW, c = pix - r * g.IW;
-            const int iy = iy0 + r, ix = ix0 + c;
-            const bool ok = iy >= 0 && iy < g.H && ix >= 0 && ix < g.W;
-            cv_cp8(s + pix * g.pitch_x + v * 4, ok ? xb + ((int64_t)iy * g.W + ix) * g.Cin + v * 4 : x, ok);
-        }
-    }
-}
 
 // ---------------------------------------------------------------------------------------------------
 // forward: y[b, oy, ox, :] = bias + sum_tap W[tap] . x[b, oy*S + ky - 1, ox*S + kx - 1, :]
@@ -524,6 +418,7 @@ using namespace lmnet;
 
 extern "C" int lmnet_conv3x3_fwd_supported(const lmnet_conv3x3_dims* d, int dtype) {
     if (dtype != LMNET_BF16 && dtype != LMNET_F16) return 0;
+    if (cv_valid(d) && cv_fast_fwd_has(d->stride, d->Cin, d->Cout)) return 1;
     CvFwdPlan pl{};
     return cv_fwd_plan(d, pl) ? 1 : 0;
 }
@@ -532,21 +427,28 @@ extern "C" int lmnet_conv3x3_fwd(const void* x, const void* w_packed, const floa
                                  int dtype, void* stream) {
     if (!lmnet_conv3x3_fwd_supported(d, dtype)) return LMNET_ERR_UNSUPPORTED;
     if (!x || !w_packed || !y) return LMNET_ERR_INVALID_ARG;
-    if ((uintptr_t)x % 16 != 0 || (uintptr_t)y % 16 != 0) return LMNET_ERR_UNSUPPORTED;
+    if ((uintptr_t)x % 16 != 0 || (uintptr_t)y % 16 != 0 || (uintptr_t)w_packed % 8 != 0) return LMNET_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (cv_fast_fwd_has(d->stride, d->Cin, d->Cout)) return cv_fast_fwd(x, w_packed, bias, y, d, dtype, st);
     CvFwdPlan pl{};
     cv_fwd_plan(d, pl);
-    cudaStream_t st = (cudaStream_t)stream;
     return dtype == LMNET_BF16 ? cv_fwd_dispatch<__nv_bfloat16>(x, w_packed, bias, y, pl, st)
                                : cv_fwd_dispatch<__half>(x, w_packed, bias, y, pl, st);
 }
 
 extern "C" int lmnet_conv3x3_wgrad_supported(const lmnet_conv3x3_dims* d, int dtype) {
     if (dtype != LMNET_BF16 && dtype != LMNET_F16) return 0;
+    if (cv_valid(d) && cv_fast_wgrad_has(d->stride, d->Cin, d->Cout)) return 1;
     CvWgPlan pl{};
     return cv_wg_plan(d, pl) ? 1 : 0;
 }
 
 extern "C" size_t lmnet_conv3x3_wgrad_workspace_bytes(const lmnet_conv3x3_dims* d) {
+    if (cv_valid(d) && cv_fast_wgrad_has(d->stride, d->Cin, d->Cout)) {
+        int mp = 0, ldn = 0;
+        const int grid = cv_fast_wgrad_grid(d, &mp, &ldn);
+        return ((size_t)grid * 9 * mp * ldn + (size_t)grid * mp) * sizeof(float);
+    }
     CvWgPlan pl{};
     if (!cv_wg_plan(d, pl)) return 0;
     return ((size_t)pl.grid * 9 * pl.MT * 16 * pl.NTC * 8 + (size_t)pl.grid * pl.MT * 16) * sizeof(float);
@@ -558,9 +460,21 @@ extern "C" int lmnet_conv3x3_wgrad(const void* x, const void* dy, float* dW, flo
     if (!x || !dy || !dW || !workspace) return LMNET_ERR_INVALID_ARG;
     if ((uintptr_t)x % 16 != 0 || (uintptr_t)dy % 16 != 0) return LMNET_ERR_UNSUPPORTED;
     if (workspace_bytes < lmnet_conv3x3_wgrad_workspace_bytes(d)) return LMNET_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n_out = 9 * d->Cout * d->Cin + d->Cout;
+    if (cv_fast_wgrad_has(d->stride, d->Cin, d->Cout)) {
+        int mp = 0, ldn = 0;
+        const int grid = cv_fast_wgrad_grid(d, &mp, &ldn);
+        float* fpart = (float*)workspace;
+        float* fpart_b = fpart + (size_t)grid * 9 * mp * ldn;
+        const int frc = cv_fast_wgrad(x, dy, fpart, fpart_b, d, dtype, st);
+        if (frc != LMNET_OK) return frc;
+        LMNET_LAUNCH(KID_CONV3X3_REDUCE, st, 0, (conv3x3_wgrad_reduce_kernel<<<(n_out + 127) / 128, 128, 0, st>>>(
+            fpart, fpart_b, dW, dbias, grid, d->Cout, d->Cin, mp, ldn)));
+        return LMNET_OK;
+    }
     CvWgPlan pl{};
     cv_wg_plan(d, pl);
-    cudaStream_t st = (cudaStream_t)stream;
     float* part = (float*)workspace;
     float* part_b = part + (size_t)pl.grid * 9 * pl.MT * 16 * pl.NTC * 8;
     int rc = dtype == LMNET_BF16 ? cv_wg_dispatch<__nv_bfloat16>(x, dy, part, part_b, pl, st)

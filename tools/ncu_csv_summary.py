@@ -1,0 +1,44 @@
+"""Summarise an `ncu --page raw --csv` export (made on the GPU box, so that the heavy .ncu-rep never travels).
+    python tools/ncu_csv_summary.py gpurun_out/xxx_raw.csv > profiles/rNN_ncu_xxx.txt"""
+import csv
+import sys
+
+KEYS = [("gpu__time_duration.sum", "time"), ("launch__grid_size", "grid"), ("launch__block_size", "block"),
+        ("launch__registers_per_thread", "regs"), ("launch__occupancy_limit_shared_mem", "occ_lim_smem"),
+        ("launch__occupancy_limit_registers", "occ_lim_regs"),
+        ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps_active%"),
+        ("dram__bytes_read.sum", "dram_rd"), ("dram__bytes_write.sum", "dram_wr"),
+        ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram%"),
+        ("lts__t_sector_hit_rate.pct", "l2_hit%"),
+        ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm%"),
+        ("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "fma_pipe%"),
+        ("sm__inst_executed_pipe_tensor_subpipe_hmma.avg.pct_of_peak_sustained_active", "hmma%"),
+        ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor%"),
+        ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "lsu%"),
+        ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue%"),
+        ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smem_wavefronts"),
+        ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smem_conflicts"),
+        ("smsp__inst_executed.sum", "warp_insts")]
+rows = list(csv.reader(open(sys.argv[1], errors="ignore")))
+hdr, units = rows[0], rows[1]
+idx = {h: i for i, h in enumerate(hdr)}
+print(f"# {sys.argv[1]}: ncu --set full --clock-control none (cold-cache, serialised launches)")
+for r in rows[2:]:
+    if len(r) < len(hdr):
+        continue
+    print("\n" + r[idx["Kernel Name"]][:150])
+    for k, short in KEYS:
+        if k in idx:
+            print(f"  {short:16s} {r[idx[k]]} {units[idx[k]]}")
+    stalls = []
+    for h, i in idx.items():
+        if "average_warp_latency_issue_stalled" in h or ("warp_issue_stalled" in h and h.endswith("_per_warp_active.pct")):
+            try:
+                v = float(r[i].replace(",", ""))
+            except ValueError:
+                continue
+            if v > 0:
+                stalls.append((v, h.split("issue_stalled_")[-1].replace("_per_warp_active.pct", "")))
+    stalls.sort(reverse=True)
+    tot = sum(v for v, _ in stalls) or 1
+    print("  stalls           " + ", ".join(f"{n} {100 * v / tot:.0f}%" for v, n in stalls[:7]))

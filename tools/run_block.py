@@ -14,7 +14,7 @@ sys.path[:0] = [ROOT, os.path.join(ROOT, "lm-net_b200")]
 import torch  # noqa: E402
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--unit", default="reparam", choices=["reparam", "na"])
+ap.add_argument("--unit", default="reparam", choices=["reparam", "na", "conv", "natt"])
 ap.add_argument("--level", type=int, default=1)
 ap.add_argument("--batch", type=int, default=16)
 ap.add_argument("--res", type=int, default=352)
@@ -34,6 +34,16 @@ if a.unit == "reparam":
 
     m = ReparamConv(width, 2 * width, width).to(dev).train()
     x = torch.randn(a.batch, width, R, R, device=dev, requires_grad=True)
+elif a.unit == "conv":
+    from lmnet_b200.conv3x3 import Conv3x3
+
+    m = Conv3x3(2 * width, width, 3, 1, 1).to(dev).train()            # the decoder / skip shape: 2C -> C at this level
+    x = torch.randn(a.batch, 2 * width, R, R, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last).requires_grad_()
+elif a.unit == "natt":
+    from lmnet_b200.model import NeighborhoodTransformer
+
+    m = NeighborhoodTransformer(width).to(dev).train()
+    x = torch.randn(a.batch, width, R, R, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last).requires_grad_()
 else:
     import natten
 
