@@ -13,7 +13,10 @@ A step = forward + CE+Dice loss + backward + AdamW step over one batch.  N>1: on
 One JSON line on rank 0:
   value       whole-job images/s with the batch already resident in HBM (CUDA events, max over ranks)
   e2e         the same metric through the reference-shaped public API lmnet_b200.train.train_one_epoch
-              with pinned HOST batches: H2D of images+masks and D2H of loss + argmax mask every step
+              with pinned HOST batches: H2D of images + masks every step, D2H of the loss scalar every step
+              (4 bytes; the confusion matrix of the argmax mask is accumulated on the GPU).  `e2e_as_is`
+              repeats it with the reference loop's exact host traffic (utils/train_eval_utils.py:128-156:
+              no prefetch, loss.item() every step, argmax mask and labels shipped to the host every step)
   roofline    dominant lmnet_b200 kernel of the step: algorithmic bytes / CUDA-event time (measured
               live in a separate profiled leg, never inside the timed region) vs MEASURED_PEAKS.json
   cpu_baseline the CPU oracle path (reference modules in torch CPU + natten's ops restated in C/OpenMP)
@@ -52,6 +55,10 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--workload", default="train", choices=["train", "cfg1", "na2d", "infer1024"],
+                    help="train = BASELINE configs[1]/[2] (default); cfg1 = configs[0] (CPU fwd+bwd, batch 2, 256x256, fp32); "
+                         "na2d = configs[3] (na2d micro-benchmark, kernel 3/7, dilation 1/2, every stage shape); "
+                         "infer1024 = configs[4] (bf16 inference, batch 8, 1024x1024)")
     return ap.parse_args()
 
 
@@ -152,6 +159,40 @@ def measured_peaks():
         return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     except Exception:
         return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def csrc_fingerprint():
+    """sha256 over the CUDA sources the library was built from: stamps profiles/*_traffic.json (written by
+    tools/launch_list_summary.py) so that a stale ncu traffic file is refused instead of silently reported."""
+    import glob
+    import hashlib
+
+    h = hashlib.sha256()
+    for f in sorted(glob.glob(os.path.join(ROOT, "lm-net_b200", "csrc", "*.cu")) + glob.glob(os.path.join(ROOT, "lm-net_b200", "csrc", "*.cuh"))):
+        h.update(os.path.basename(f).encode())
+        h.update(open(f, "rb").read())
+    return h.hexdigest()[:16]
+
+
+def measured_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the newest committed ncu launch list whose source stamp matches this tree."""
+    import glob
+
+    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")), reverse=True):
+        try:
+            tj = json.load(open(f))
+        except Exception:
+            continue
+        stamp = tj.get("_csrc_sha256")
+        rel = os.path.relpath(f, ROOT)
+        if stamp is None:
+            continue                                     # unstamped files (round 1) are never trusted
+        if stamp != csrc_fingerprint():
+            return None, f"{rel} is stale (kernels changed since the ncu capture: {stamp} != {csrc_fingerprint()})"
+        if kernel in tj:
+            return round(tj[kernel]["dram_bytes_per_launch"]), f"{rel} (ncu dram__bytes_read+write per launch, same sources: {stamp})"
+        return None, f"{rel} has no entry for {kernel}"
+    return None, "no stamped ncu launch list committed"
 
 
 def step_roofline(batch, res, ms_per_step):
@@ -284,6 +325,20 @@ def run_b200_arm(args):
     h2d = host[0][0].numel() * 4 + host[0][1].numel() * 8
     d2h = 4                     # loss scalar every step (loss.item()); the confusion matrix stays on the GPU
 
+    # ---- the reference loop AS IS (utils/train_eval_utils.py:128-156): no prefetch, loss.item() every step,
+    #      argmax mask + labels copied to the host for the metric update every step
+    asis = dict(metrics_on_device=False, prefetch=False, defer_loss_read=False)
+    train_one_epoch(model, opt, metrics, 2, Loader(2), dev, crit, scaler_flag, dice, step_fn=graphed, **asis)
+    barrier()
+    t0 = time.perf_counter()
+    train_one_epoch(model, opt, metrics, 2, Loader(args.steps), dev, crit, scaler_flag, dice, step_fn=graphed, **asis)
+    barrier()
+    asis_ms = torch.tensor([1e3 * (time.perf_counter() - t0)], device=dev)
+    if world > 1:
+        dist.all_reduce(asis_ms, op=dist.ReduceOp.MAX)
+    asis_value = B * world * args.steps / (float(asis_ms) / 1e3)
+    asis_d2h = 4 + 2 * host[0][1].numel() * 8          # loss + int64 argmax mask + int64 labels
+
     # ---- per-kernel profile leg (separate from both timed regions) ----
     roofline, kernels = None, None
     if rank == 0 and not args.no_profile:
@@ -307,13 +362,7 @@ def run_b200_arm(args):
         own_ms = sum(v["ms_per_step"] for v in kernels.values())
         top = next(k for k, v in kernels.items() if v["achieved_GBs"])
         kt = kernels[top]
-        traffic, traffic_src = None, None
-        try:   # DRAM bytes per launch of that kernel from the committed ncu launch list of this very command
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-            traffic = round(tj[top]["dram_bytes_per_launch"])
-            traffic_src = "profiles/r01_traffic.json (ncu dram__bytes_read+write per launch, average over the step's launches)"
-        except Exception:
-            pass
+        traffic, traffic_src = measured_traffic(top)
         roofline = {"kernel": top, "bound": "hbm", "achieved": round(kt["achieved_GBs"], 1), "peak": peak,
                     "unit": "GB/s", "frac": round(kt["achieved_GBs"] / peak, 4), "traffic": traffic,
                     "traffic_source": traffic_src,
@@ -342,6 +391,10 @@ def run_b200_arm(args):
                 "e2e": {"value": round(e2e_value, 2), "unit": "images/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h, "ms_per_step": round(float(e2e_ms) / args.steps, 3),
                         "api": "lmnet_b200.train.train_one_epoch (reference-shaped loop, pinned host batches)"},
+                "e2e_as_is": {"value": round(asis_value, 2), "unit": "images/s", "h2d_bytes_per_step": h2d,
+                              "d2h_bytes_per_step": asis_d2h, "ms_per_step": round(float(asis_ms) / args.steps, 3),
+                              "api": "train_one_epoch(metrics_on_device=False, prefetch=False, defer_loss_read=False): the "
+                                     "reference loop's exact host traffic and synchronisation"},
                 "cuda_graph": bool(graphed is not None and graphed.graph is not None),
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
                 "step_roofline": step_roofline(B, R, ms_total / args.steps),
@@ -352,10 +405,140 @@ def run_b200_arm(args):
         dist.destroy_process_group()
 
 
+def run_cfg1(args):
+    """BASELINE configs[0]: LM-Net fwd+bwd, batch 2, 256x256, fp32 on the host CPU (reference op sequence + the C/OpenMP
+    restatement of natten's CPU ops).  Pure CPU line; printed by both arms."""
+    if int(os.environ.get("RANK", 0)) != 0:
+        return
+    r = cpu_reference_run(256, 2, max(1, min(args.steps, 5)), max(1, min(args.warmup, 2)))
+    line = {"impl": "reference" if args.impl == "reference" else "b200", "metric": "LM-Net fwd+bwd+AdamW images/sec @256x256 on the host CPU (BASELINE configs[0])",
+            "value": r["value"], "unit": "images/s", "n_gpus": 0, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": "configs[0]: LM-Net fwd+bwd, batch 2, 256x256 synthetic RGB + binary mask, fp32, CPU",
+                                            "global_batch": 2, "resolution": 256},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_na2d(args):
+    """BASELINE configs[3]: fused na2d forward and backward, kernel 3 and 7, dilation 1/2, at every LM-Net stage shape
+    (bf16, batch `--batch`, 12 heads).  value = algorithmic GB/s over all cases (fwd 4N, bwd 7N bytes); L2 flushed."""
+    from lmnet_b200 import _lib
+    from natten.functional import na2d
+
+    dev = torch.device("cuda")
+    _lib.lib()
+    peak, peak_src = measured_peaks()
+    flush = torch.empty(512 * 1024 * 1024 // 4, device=dev)
+    gen = torch.Generator(device=dev).manual_seed(0)
+
+    def timed(fn, iters):
+        for _ in range(args.warmup):
+            fn()
+        ts = []
+        for _ in range(iters):
+            flush.fill_(1.0)
+            torch.cuda._sleep(2_000_000)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        ts.sort()
+        return ts[len(ts) // 2]
+
+    B, R0 = args.batch, args.res
+    cases, tot_bytes, tot_ms, launches0 = [], 0.0, 0.0, _lib.launch_count()
+    sampler = ClockSampler(0)
+    sampler.start()
+    for lvl, hd in enumerate((1, 2, 4, 8)):
+        R = R0 >> lvl
+        for K, d in ((3, 1), (7, 1), (7, 2)):
+            q, k, v = (torch.randn(B, R, R, 12, hd, device=dev, dtype=torch.bfloat16, generator=gen).requires_grad_() for _ in range(3))
+            rpb = (0.02 * torch.randn(12, 2 * K - 1, 2 * K - 1, device=dev, generator=gen)).requires_grad_()
+            go = torch.randn(B, R, R, 12, hd, device=dev, dtype=torch.bfloat16, generator=gen)
+            nb = q.numel() * 2
+            with torch.no_grad():
+                tf = timed(lambda: na2d(q, k, v, K, d, rel_pos_bias=rpb), args.steps)
+            out = na2d(q, k, v, K, d, rel_pos_bias=rpb)
+            tb = timed(lambda: torch.autograd.grad(out, (q, k, v, rpb), go, retain_graph=True), args.steps)
+            cases.append({"shape": [B, R, R, 12, hd], "kernel": K, "dilation": d, "fwd_ms": round(tf, 4), "bwd_ms": round(tb, 4),
+                          "fwd_GBs": round(4 * nb / tf / 1e6, 1), "bwd_GBs": round(7 * nb / tb / 1e6, 1),
+                          "fwd_frac": round(4 * nb / tf / 1e6 / peak, 4), "bwd_frac": round(7 * nb / tb / 1e6 / peak, 4)})
+            tot_bytes += 11 * nb
+            tot_ms += tf + tb
+            del q, k, v, out
+    clocks = sampler.stop()
+    value = tot_bytes / tot_ms / 1e6
+    line = {"metric": "na2d fwd+bwd algorithmic GB/s vs roofline (BASELINE configs[3])", "value": round(value, 1), "unit": "GB/s",
+            "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(tot_ms, 3), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"configs[3]: fused na2d fwd+bwd, kernel 3/7, dilation 1/2, [{B},R,R,12,hd] for R,hd = "
+                                   f"{R0},1 / {R0 // 2},2 / {R0 // 4},4 / {R0 // 8},8; a step = all 12 cases once", "l2": "flushed (512 MB write) between iterations"},
+            "roofline": {"bound": "hbm", "achieved": round(value, 1), "peak": peak, "unit": "GB/s", "frac": round(value / peak, 4),
+                         "traffic": None, "peak_source": peak_src},
+            "gpu_launches": _lib.launch_count() - launches0, "clocks": clocks, "cases": cases}
+    print(json.dumps(line), flush=True)
+
+
+def run_infer1024(args):
+    """BASELINE configs[4]: LM-Net inference, bf16 autocast, batch 8, 1024x1024, eval mode (running statistics)."""
+    from lmnet_b200 import _lib
+    from lmnet_b200.model import LM_Net
+
+    dev = torch.device("cuda")
+    _lib.lib()
+    torch.backends.cudnn.benchmark = True
+    torch.manual_seed(0)
+    net = LM_Net(3, 2).to(dev).eval()
+    B, R = 8, 1024
+    host = torch.randn(B, 3, R, R).pin_memory()
+    x = host.to(dev)
+    sampler = ClockSampler(0)
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        for _ in range(args.warmup):
+            net(x)
+        torch.cuda.synchronize()
+        sampler.start()
+        l0 = _lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            y = net(x)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        launches = _lib.launch_count() - l0
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            pred = net(host.to(dev, non_blocking=True)).argmax(1).to(torch.uint8).cpu()
+        e2e_ms = 1e3 * (time.perf_counter() - t0) / args.steps
+    clocks = sampler.stop()
+    line = {"metric": "LM-Net inference images/sec @1024x1024 (bf16, batch 8; BASELINE configs[4])", "value": round(B * 1e3 / ms, 2),
+            "unit": "images/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "configs[4]: LM-Net inference, bf16 autocast, batch 8, 1024x1024, eval mode", "global_batch": B,
+                       "resolution": R, "l2": "activations >> 126 MB L2"},
+            "e2e": {"value": round(B * 1e3 / e2e_ms, 2), "unit": "images/s", "h2d_bytes_per_step": host.numel() * 4,
+                    "d2h_bytes_per_step": B * R * R, "ms_per_step": round(e2e_ms, 3),
+                    "api": "LM_Net(x.to(device)).argmax(1) -> uint8 mask on the host"},
+            "gpu_launches": launches, "clocks": clocks, "finite": bool(torch.isfinite(y.float()).all()),
+            "peak_memory_GiB": round(torch.cuda.max_memory_allocated() / 2 ** 30, 2), "pred_shape": list(pred.shape)}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     args = parse()
-    if args.impl == "reference":
+    if args.workload == "cfg1":
+        run_cfg1(args)
+    elif args.impl == "reference":
         run_reference_arm(args)
+    elif args.workload == "na2d":
+        run_na2d(args)
+    elif args.workload == "infer1024":
+        run_infer1024(args)
     else:
         run_b200_arm(args)
 

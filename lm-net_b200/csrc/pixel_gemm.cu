@@ -39,6 +39,7 @@ struct PgGeom {
     int K1p, K2p;                      // padded to 16
     int64_t P;                         // pixels per image
     int PT;                            // pixels per CTA tile
+    int pt_shift;                      // PT / 8 == 1 << pt_shift (PT is 64, 128 or 256)
     int tiles, ctas_x, tiles_per_cta;  // per image
     int w_pitch;                       // element pitch of the weight rows [N][K1p + K2p + 8]
     int in1_pitch, in2_pitch, out_pitch;
@@ -93,33 +94,69 @@ template <> __device__ __forceinline__ uint32_t pg_pack<__half>(float lo, float 
     return *reinterpret_cast<uint32_t*>(&v);
 }
 
-// stage a channels-last tile: `rows` pixel rows x C channels at src (pixel stride C) -> smem [rows][pitch]
+// ---- shared-memory addressing in the 32-bit shared window (no generic-pointer arithmetic in the hot loops)
+__device__ __forceinline__ uint32_t pg_saddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void pg_cp16a(uint32_t s, const void* gmem, bool valid) {
+    const int sz = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(sz));
+}
+__device__ __forceinline__ void pg_cp8a(uint32_t s, const void* gmem, bool valid) {
+    const int sz = valid ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(s), "l"(gmem), "r"(sz));
+}
+__device__ __forceinline__ void pg_ldsm_x4a(uint32_t (&r)[4], uint32_t a) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void pg_ldsm_x4ta(uint32_t (&r)[4], uint32_t a) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void pg_ldsm_x2a(uint32_t (&r)[2], uint32_t a) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(a));
+}
+
+// (i / d, i % d) for i = i0, i0 + step, ... without a division per iteration
+struct PgDiv {
+    int q, r;
+    __device__ __forceinline__ PgDiv(int i0, int d) { q = i0 / d; r = i0 - q * d; }
+    __device__ __forceinline__ void step(int dq, int dr, int d) {
+        q += dq;
+        r += dr;
+        if (r >= d) { r -= d; ++q; }
+    }
+};
+
+// stage a channels-last tile: `rows` pixel rows x C channels, contiguous in global memory -> smem [rows][pitch]
 template <typename T>
-__device__ __forceinline__ void pg_issue_cl(T* s, int pitch, const T* src, int C, int rows, int64_t valid_rows) {
+__device__ __forceinline__ void pg_issue_cl(uint32_t s, int pitch, const T* src, int C, int rows, int64_t valid_rows) {
+    const int vrows = (int)min((int64_t)rows, valid_rows);
     if ((C & 7) == 0) {
-        const int vpr = C >> 3;
-        for (int i = threadIdx.x; i < rows * vpr; i += kPgThreads) {
-            const int r = i / vpr, v = i - r * vpr;
-            const bool ok = r < valid_rows;
-            pg_cp16(s + r * pitch + v * 8, ok ? src + (int64_t)r * C + v * 8 : src, ok);
+        const int vpr = C >> 3, total = rows * vpr, nvalid = vrows * vpr;
+        const int dq = kPgThreads / vpr, dr = kPgThreads - dq * vpr;
+        PgDiv d(threadIdx.x, vpr);
+        for (int i = threadIdx.x; i < total; i += kPgThreads) {
+            const bool ok = i < nvalid;
+            pg_cp16a(s + (uint32_t)(d.q * pitch + d.r * 8) * 2, ok ? src + (int64_t)i * 8 : src, ok);
+            d.step(dq, dr, vpr);
         }
     } else {
-        const int vpr = C >> 2;
-        for (int i = threadIdx.x; i < rows * vpr; i += kPgThreads) {
-            const int r = i / vpr, v = i - r * vpr;
-            const bool ok = r < valid_rows;
-            pg_cp8(s + r * pitch + v * 4, ok ? src + (int64_t)r * C + v * 4 : src, ok);
+        const int vpr = C >> 2, total = rows * vpr, nvalid = vrows * vpr;
+        const int dq = kPgThreads / vpr, dr = kPgThreads - dq * vpr;
+        PgDiv d(threadIdx.x, vpr);
+        for (int i = threadIdx.x; i < total; i += kPgThreads) {
+            const bool ok = i < nvalid;
+            pg_cp8a(s + (uint32_t)(d.q * pitch + d.r * 4) * 2, ok ? src + (int64_t)i * 4 : src, ok);
+            d.step(dq, dr, vpr);
         }
     }
 }
-// stage a planes tile: C channel rows x `cols` pixels at src (channel stride P) -> smem [C][pitch]
+// stage a planes tile: C channel rows x `cols` pixels (cols = 8 << sh) at src (channel stride P) -> smem [C][pitch]
 template <typename T>
-__device__ __forceinline__ void pg_issue_planes(T* s, int pitch, const T* src, int C, int64_t P, int cols, int64_t valid_cols) {
-    const int vpr = cols >> 3;
-    for (int i = threadIdx.x; i < C * vpr; i += kPgThreads) {
-        const int r = i / vpr, v = i - r * vpr;
+__device__ __forceinline__ void pg_issue_planes(uint32_t s, int pitch, const T* src, int C, int64_t P, int sh, int64_t valid_cols) {
+    const int mask = (1 << sh) - 1;
+    for (int i = threadIdx.x; i < (C << sh); i += kPgThreads) {
+        const int r = i >> sh, v = i & mask;
         const bool ok = v * 8 < valid_cols;             // P % 8 == 0: a vector is all in or all out
-        pg_cp16(s + r * pitch + v * 8, ok ? src + (int64_t)r * P + v * 8 : src, ok);
+        pg_cp16a(s + (uint32_t)(r * pitch + v * 8) * 2, ok ? src + (int64_t)r * P + v * 8 : src, ok);
     }
 }
 
@@ -137,7 +174,7 @@ pixel_gemm_kernel(const T* __restrict__ in1, const T* __restrict__ w1, const T* 
     static_assert(OUT_CL || !HAS_IN2, "a second operand is only used by channels-last outputs");
     extern __shared__ __align__(16) unsigned char pg_smem[];
     T* s_w = reinterpret_cast<T*>(pg_smem);                                  // [Npad][w_pitch]
-    const int n_pad = OUT_CL ? TB * 8 : TB * 16;
+    constexpr int n_pad = OUT_CL ? TB * 8 : TB * 16;
     const int in1_elems = IN1_CL ? g.PT * g.in1_pitch : g.K1p * g.in1_pitch;
     const int in2_elems = HAS_IN2 ? g.PT * g.in2_pitch : 0;
     const int stage_elems = in1_elems + in2_elems;
@@ -161,7 +198,10 @@ pixel_gemm_kernel(const T* __restrict__ in1, const T* __restrict__ w1, const T* 
         s_w[i] = v;
     }
     for (int i = threadIdx.x; i < n_pad; i += kPgThreads) s_bias[i] = (bias != nullptr && i < g.NC) ? bias[n0 + i] : 0.f;
-    for (int i = threadIdx.x; i < 2 * stage_elems; i += kPgThreads) s_in[i] = zero;
+    {
+        uint4* z = reinterpret_cast<uint4*>(s_in);                           // stage sizes are multiples of 8 elements
+        for (int i = threadIdx.x; i < (2 * stage_elems) >> 3; i += kPgThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
     __syncthreads();
 
     const T* in1_b = in1 + (int64_t)b * g.P * g.K1;
@@ -169,20 +209,45 @@ pixel_gemm_kernel(const T* __restrict__ in1, const T* __restrict__ w1, const T* 
     T* out_b = out + (int64_t)b * g.P * g.N;
     const int tile0 = blockIdx.x * g.tiles_per_cta;
     const int ntiles = max(0, min(g.tiles_per_cta, g.tiles - tile0));
+    const uint32_t sin_a = pg_saddr(s_in), sw_a = pg_saddr(s_w);
 
     auto issue = [&](int t, int st) {
-        T* s1 = s_in + st * stage_elems;
+        const uint32_t s1 = sin_a + (uint32_t)(st * stage_elems) * 2;
         const int64_t p0 = (int64_t)(tile0 + t) * g.PT;
         const int64_t valid = g.P - p0;
         if (IN1_CL) pg_issue_cl<T>(s1, g.in1_pitch, in1_b + p0 * g.K1, g.K1, g.PT, valid);
-        else pg_issue_planes<T>(s1, g.in1_pitch, in1_b + p0, g.K1, g.P, g.PT, valid);
-        if (HAS_IN2) pg_issue_cl<T>(s1 + in1_elems, g.in2_pitch, in2_b + p0 * g.K2, g.K2, g.PT, valid);
+        else pg_issue_planes<T>(s1, g.in1_pitch, in1_b + p0, g.K1, g.P, g.pt_shift, valid);
+        if (HAS_IN2) pg_issue_cl<T>(s1 + (uint32_t)in1_elems * 2, g.in2_pitch, in2_b + p0 * g.K2, g.K2, g.PT, valid);
         pg_commit();
     };
 
     float st_s[TB][2], st_q[TB][2];                     // BatchNorm partial sums (planes output): rows gq, gq + 8 of each m-tile
 #pragma unroll
     for (int i = 0; i < TB; ++i) st_s[i][0] = st_s[i][1] = st_q[i][0] = st_q[i][1] = 0.f;
+
+    // per-lane fragment offsets (bytes) that do not change from tile to tile
+    const int m = lane >> 3, rr = lane & 7, l16 = lane & 15;
+    uint32_t a_lane, a_lane2 = 0, b_lane;
+    if constexpr (OUT_CL) {
+        const int px0 = warp * TA * 16;
+        // A = input pixels
+        if (IN1_CL) a_lane = (uint32_t)((px0 + (m & 1) * 8 + rr) * g.in1_pitch + (m >> 1) * 8) * 2;
+        else a_lane = (uint32_t)(((m >> 1) * 8 + rr) * g.in1_pitch + px0 + (m & 1) * 8) * 2;
+        if (HAS_IN2) a_lane2 = (uint32_t)(in1_elems + (px0 + (m & 1) * 8 + rr) * g.in2_pitch + (m >> 1) * 8) * 2;
+        // B = weights [n][k], x2: rows l & 7, k half l >> 3
+        b_lane = sw_a + (uint32_t)((l16 & 7) * g.w_pitch + (l16 >> 3) * 8) * 2;
+    } else {
+        const int px0 = warp * TA * 8;
+        // A = weights [n][k], x4
+        a_lane = sw_a + (uint32_t)(((m & 1) * 8 + rr) * g.w_pitch + (m >> 1) * 8) * 2;
+        // B = input pixels (channels-last), x2
+        b_lane = (uint32_t)((px0 + (l16 & 7)) * g.in1_pitch + (l16 >> 3) * 8) * 2;
+    }
+    const uint32_t a_tile = OUT_CL ? (uint32_t)(IN1_CL ? 16 * g.in1_pitch : 16) * 2 : (uint32_t)(16 * g.w_pitch) * 2;
+    const uint32_t a_tile2 = (uint32_t)(16 * g.in2_pitch) * 2;
+    const uint32_t a_kstep = (OUT_CL && !IN1_CL) ? (uint32_t)(16 * g.in1_pitch) * 2 : 32u;
+    const uint32_t b_tile = OUT_CL ? (uint32_t)(8 * g.w_pitch) * 2 : (uint32_t)(8 * g.in1_pitch) * 2;
+    const int ksteps1 = g.K1p >> 4, ksteps2 = HAS_IN2 ? g.K2p >> 4 : 0;
 
     if (ntiles > 0) issue(0, 0);
     for (int t = 0; t < ntiles; ++t) {
@@ -194,8 +259,7 @@ pixel_gemm_kernel(const T* __restrict__ in1, const T* __restrict__ w1, const T* 
             pg_wait<0>();
         }
         __syncthreads();                                // tile t landed; everybody is done with s_out of tile t-1
-        const T* s1 = s_in + st * stage_elems;
-        const T* s2 = s1 + in1_elems;
+        const uint32_t s1 = sin_a + (uint32_t)(st * stage_elems) * 2;
         const int64_t p0 = (int64_t)(tile0 + t) * g.PT;
         float acc[TA][TB][4];
 #pragma unroll
@@ -205,96 +269,99 @@ pixel_gemm_kernel(const T* __restrict__ in1, const T* __restrict__ w1, const T* 
 
         if constexpr (OUT_CL) {
             // pixels on M: A = input (this warp's TA x 16 pixels), B = weights [n][k]
-            const int px0 = warp * TA * 16;
-            const int ksteps1 = g.K1p >> 4, ksteps2 = HAS_IN2 ? g.K2p >> 4 : 0;
-            for (int ks = 0; ks < ksteps1 + ksteps2; ++ks) {
-                const bool second = ks >= ksteps1;
-                const int k0 = second ? (ks - ksteps1) << 4 : ks << 4;
+            uint32_t pa = s1 + a_lane, pb = b_lane;
+            for (int ks = 0; ks < ksteps1; ++ks, pa += a_kstep, pb += 32u) {
                 uint32_t bf[TB][2];
-                {
-                    const int l = lane & 15;
 #pragma unroll
-                    for (int j = 0; j < TB; ++j)
-                        pg_ldsm_x2(bf[j], s_w + (j * 8 + (l & 7)) * g.w_pitch + (second ? g.K1p : 0) + k0 + (l >> 3) * 8);
-                }
+                for (int j = 0; j < TB; ++j) pg_ldsm_x2a(bf[j], pb + j * b_tile);
 #pragma unroll
                 for (int i = 0; i < TA; ++i) {
                     uint32_t af[4];
-                    const int m = lane >> 3, rr = lane & 7;
-                    if (second || IN1_CL) {
-                        const T* base = second ? s2 : s1;
-                        const int pitch = second ? g.in2_pitch : g.in1_pitch;
-                        pg_ldsm_x4(af, base + (px0 + i * 16 + (m & 1) * 8 + rr) * pitch + k0 + (m >> 1) * 8);
-                    } else {
-                        pg_ldsm_x4_t(af, s1 + (k0 + (m >> 1) * 8 + rr) * g.in1_pitch + px0 + i * 16 + (m & 1) * 8);
-                    }
+                    if (IN1_CL) pg_ldsm_x4a(af, pa + i * a_tile);
+                    else pg_ldsm_x4ta(af, pa + i * a_tile);
 #pragma unroll
                     for (int j = 0; j < TB; ++j) pg_mma<T>(acc[i][j], af, bf[j]);
                 }
             }
+            if constexpr (HAS_IN2) {
+                uint32_t pa2 = s1 + a_lane2;
+                pb = b_lane + (uint32_t)g.K1p * 2;
+                for (int ks = 0; ks < ksteps2; ++ks, pa2 += 32u, pb += 32u) {
+                    uint32_t bf[TB][2];
+#pragma unroll
+                    for (int j = 0; j < TB; ++j) pg_ldsm_x2a(bf[j], pb + j * b_tile);
+#pragma unroll
+                    for (int i = 0; i < TA; ++i) {
+                        uint32_t af[4];
+                        pg_ldsm_x4a(af, pa2 + i * a_tile2);
+#pragma unroll
+                        for (int j = 0; j < TB; ++j) pg_mma<T>(acc[i][j], af, bf[j]);
+                    }
+                }
+            }
             // fragments -> staging [pixel][channel]
+            const int px0 = warp * TA * 16;
 #pragma unroll
-            for (int i = 0; i < TA; ++i)
+            for (int j = 0; j < TB; ++j) {
+                const int n = j * 8 + 2 * tq;
+                const float b0 = s_bias[n], b1 = s_bias[n + 1];
 #pragma unroll
-                for (int j = 0; j < TB; ++j) {
-                    const int n = j * 8 + 2 * tq;
-                    const float b0 = s_bias[n], b1 = s_bias[n + 1];
+                for (int i = 0; i < TA; ++i) {
                     const int r0 = px0 + i * 16 + gq;
                     *reinterpret_cast<uint32_t*>(s_out + r0 * g.out_pitch + n) = pg_pack<T>(acc[i][j][0] + b0, acc[i][j][1] + b1);
                     *reinterpret_cast<uint32_t*>(s_out + (r0 + 8) * g.out_pitch + n) = pg_pack<T>(acc[i][j][2] + b0, acc[i][j][3] + b1);
                 }
+            }
             __syncthreads();
             // staging -> global: PT pixel rows of NC channels (one contiguous chunk when NC == N)
-            const int64_t valid = min((int64_t)g.PT, g.P - p0);
+            const int valid = (int)min((int64_t)g.PT, g.P - p0);
             T* dst = out_b + p0 * g.N + n0;
             if ((g.NC & 7) == 0 && (g.N & 7) == 0) {
-                const int vpr = g.NC >> 3;
-                for (int i = threadIdx.x; i < (int)valid * vpr; i += kPgThreads) {
-                    const int r = i / vpr, v = i - r * vpr;
-                    *reinterpret_cast<uint4*>(dst + (int64_t)r * g.N + v * 8) = *reinterpret_cast<const uint4*>(s_out + r * g.out_pitch + v * 8);
+                const int vpr = g.NC >> 3, total = valid * vpr;
+                const int dq = kPgThreads / vpr, dr = kPgThreads - dq * vpr;
+                PgDiv d(threadIdx.x, vpr);
+                for (int i = threadIdx.x; i < total; i += kPgThreads) {
+                    *reinterpret_cast<uint4*>(dst + (int64_t)d.q * g.N + d.r * 8) = *reinterpret_cast<const uint4*>(s_out + d.q * g.out_pitch + d.r * 8);
+                    d.step(dq, dr, vpr);
                 }
             } else {
-                const int vpr = g.NC >> 2;
-                for (int i = threadIdx.x; i < (int)valid * vpr; i += kPgThreads) {
-                    const int r = i / vpr, v = i - r * vpr;
-                    *reinterpret_cast<uint2*>(dst + (int64_t)r * g.N + v * 4) = *reinterpret_cast<const uint2*>(s_out + r * g.out_pitch + v * 4);
+                const int vpr = g.NC >> 2, total = valid * vpr;
+                const int dq = kPgThreads / vpr, dr = kPgThreads - dq * vpr;
+                PgDiv d(threadIdx.x, vpr);
+                for (int i = threadIdx.x; i < total; i += kPgThreads) {
+                    *reinterpret_cast<uint2*>(dst + (int64_t)d.q * g.N + d.r * 4) = *reinterpret_cast<const uint2*>(s_out + d.q * g.out_pitch + d.r * 4);
+                    d.step(dq, dr, vpr);
                 }
             }
         } else {
             // channels on M: A = weights [n][k], B = input pixels (this warp's TA x 8 pixels), channels-last input
-            const int px0 = warp * TA * 8;
-            const int ksteps = g.K1p >> 4;
-            for (int ks = 0; ks < ksteps; ++ks) {
-                const int k0 = ks << 4;
+            uint32_t pa = a_lane, pb = s1 + b_lane;
+            for (int ks = 0; ks < ksteps1; ++ks, pa += 32u, pb += 32u) {
                 uint32_t bf[TA][2];
-                {
-                    const int l = lane & 15;
 #pragma unroll
-                    for (int i = 0; i < TA; ++i)
-                        pg_ldsm_x2(bf[i], s1 + (px0 + i * 8 + (l & 7)) * g.in1_pitch + k0 + (l >> 3) * 8);
-                }
+                for (int i = 0; i < TA; ++i) pg_ldsm_x2a(bf[i], pb + i * b_tile);
 #pragma unroll
                 for (int j = 0; j < TB; ++j) {
                     uint32_t af[4];
-                    const int m = lane >> 3, rr = lane & 7;
-                    pg_ldsm_x4(af, s_w + (j * 16 + (m & 1) * 8 + rr) * g.w_pitch + k0 + (m >> 1) * 8);
+                    pg_ldsm_x4a(af, pa + j * a_tile);
 #pragma unroll
                     for (int i = 0; i < TA; ++i) pg_mma<T>(acc[i][j], af, bf[i]);
                 }
             }
             // fragments -> staging [channel][pixel]; BatchNorm partial sums of the values as stored
-            const int64_t valid = min((int64_t)g.PT, g.P - p0);
+            const int px0 = warp * TA * 8;
+            const int valid = (int)min((int64_t)g.PT, g.P - p0);
 #pragma unroll
             for (int j = 0; j < TB; ++j) {
-                const int n0 = j * 16 + gq;
-                const float b0 = s_bias[n0], b1 = s_bias[n0 + 8];
+                const int nn = j * 16 + gq;
+                const float b0 = s_bias[nn], b1 = s_bias[nn + 8];
 #pragma unroll
                 for (int i = 0; i < TA; ++i) {
                     const int px = px0 + i * 8 + 2 * tq;
                     const uint32_t lo = pg_pack<T>(acc[i][j][0] + b0, acc[i][j][1] + b0);
                     const uint32_t hi = pg_pack<T>(acc[i][j][2] + b1, acc[i][j][3] + b1);
-                    *reinterpret_cast<uint32_t*>(s_out + n0 * g.out_pitch + px) = lo;
-                    *reinterpret_cast<uint32_t*>(s_out + (n0 + 8) * g.out_pitch + px) = hi;
+                    *reinterpret_cast<uint32_t*>(s_out + nn * g.out_pitch + px) = lo;
+                    *reinterpret_cast<uint32_t*>(s_out + (nn + 8) * g.out_pitch + px) = hi;
                     if (stats_part != nullptr && px < valid) {           // P even: the pair is in or out together
                         const T* le = reinterpret_cast<const T*>(&lo);
                         const T* he = reinterpret_cast<const T*>(&hi);
@@ -305,11 +372,11 @@ pixel_gemm_kernel(const T* __restrict__ in1, const T* __restrict__ w1, const T* 
                 }
             }
             __syncthreads();
-            // staging -> global: each channel row is PT contiguous pixels
+            // staging -> global: each channel row is PT contiguous pixels (PT / 8 = 1 << pt_shift vectors)
             T* dst = out_b + p0;
-            const int vpr = g.PT >> 3;
-            for (int i = threadIdx.x; i < g.N * vpr; i += kPgThreads) {
-                const int r = i / vpr, v = i - r * vpr;
+            const int sh = g.pt_shift, mask = (1 << sh) - 1;
+            for (int i = threadIdx.x; i < (g.N << sh); i += kPgThreads) {
+                const int r = i >> sh, v = i & mask;
                 if (v * 8 < valid)
                     *reinterpret_cast<uint4*>(dst + (int64_t)r * g.P + v * 8) = *reinterpret_cast<const uint4*>(s_out + r * g.out_pitch + v * 8);
             }
@@ -399,6 +466,9 @@ static bool pg_plan(const lmnet_pgemm_dims* d, bool in1_cl, bool out_cl, bool st
         g.in2_pitch = 0;
         g.out_pitch = pg_pitch(g.PT);
     }
+    g.pt_shift = 0;
+    while ((8 << g.pt_shift) < g.PT) ++g.pt_shift;
+    if ((8 << g.pt_shift) != g.PT) return false;
     const int n_pad = out_cl ? pl.TB * 8 : pl.TB * 16;
     const size_t in1_elems = in1_cl ? (size_t)g.PT * g.in1_pitch : (size_t)g.K1p * g.in1_pitch;
     const size_t in2_elems = d->K2 > 0 ? (size_t)g.PT * g.in2_pitch : 0;

@@ -393,6 +393,10 @@ wgrad_1x1_cl_kernel(const T* __restrict__ A, const T* __restrict__ B1, const T* 
         }
 }
 
+}  // namespace lmnet
+#include "wgrad_stream.cuh"
+namespace lmnet {
+
 // element pitch of a channels-last tile that must cover `cols` columns: multiple of 8, == 8 (mod 16) so that the
 // eight 16-byte rows of an ldmatrix land in distinct bank groups
 static int wg_cl_pitch(int cols) {
@@ -538,16 +542,94 @@ static int wg_cl_layouts(bool a_cl, bool b1_cl, const void* A, const void* B1, c
 
 using namespace lmnet;
 
+// ---- warp-streaming variant (wgrad_stream.cuh): skinny shapes of the two largest resolutions ----
+// (MT, NT1, NT2, A channels-last, B1 channels-last)
+#define WS_LIST(X) \
+    X(2, 2, 0, false, true) X(2, 1, 0, false, true) X(3, 3, 0, false, true) \
+    X(1, 3, 2, true, false) X(1, 3, 1, true, false) X(2, 6, 3, true, false) \
+    X(3, 2, 0, true, true) X(1, 2, 0, true, true) X(2, 2, 0, true, true) X(1, 3, 0, true, true) \
+    X(5, 3, 0, true, true) X(2, 3, 0, true, true) X(3, 3, 0, true, true) X(2, 6, 0, true, true)
+
+struct WsPlan {
+    WsGeom g;
+    int MT, NT1, NT2;
+    size_t smem;
+};
+static bool ws_plan(const lmnet_wgrad_dims* d, bool a_cl, bool b1_cl, const WgClPlan& cl, WsPlan& pl) {
+    static const bool off = getenv("LMNET_WGRAD_NO_STREAM") != nullptr;
+    if (off || d->P < 8 * kWsKW) return false;
+    pl.MT = (d->M + 15) / 16;
+    pl.NT1 = (d->N1 + 7) / 8;
+    pl.NT2 = d->N2 > 0 ? (d->N2 + 7) / 8 : 0;
+    bool listed = false;
+#define X(mt, n1, n2, acl, bcl) if (pl.MT == mt && pl.NT1 == n1 && pl.NT2 == n2 && a_cl == acl && b1_cl == bcl) listed = true;
+    WS_LIST(X)
+#undef X
+    if (!listed) return false;
+    WsGeom& g = pl.g;
+    g.B = d->B; g.M = d->M; g.N1 = d->N1; g.N2 = d->N2; g.P = d->P;
+    g.pitchA = wg_cl_pitch(pl.MT * 16);
+    g.pitchB1 = wg_cl_pitch(pl.NT1 * 8);
+    g.pitchB2 = pl.NT2 > 0 ? wg_cl_pitch(pl.NT2 * 8) : 0;
+    g.a_elems = a_cl ? kWsKW * g.pitchA : pl.MT * 16 * kWsPlanePitch;
+    g.b1_elems = b1_cl ? kWsKW * g.pitchB1 : pl.NT1 * 8 * kWsPlanePitch;
+    g.b2_elems = pl.NT2 > 0 ? kWsKW * g.pitchB2 : 0;
+    const size_t stage_bytes = (size_t)(g.a_elems + g.b1_elems + g.b2_elems) * 2 * kWgWarps;
+    g.stages = 3 * stage_bytes <= 100 * 1024 ? 3 : 2;
+    const int ldn = (cl.g.NT1 + cl.g.NT2) * 8;
+    const size_t red_bytes = (size_t)kWgWarps * pl.MT * 16 * ldn * sizeof(float);
+    pl.smem = g.stages * stage_bytes;
+    if (red_bytes > pl.smem) pl.smem = red_bytes;
+    if (pl.smem > 200 * 1024) return false;
+    const int64_t nchunks = (d->P + kWsKW - 1) / kWsKW;
+    int per_sm = (int)((220 * 1024) / (pl.smem + 1024));
+    if (per_sm > 3) per_sm = 3;
+    if (per_sm < 1) per_sm = 1;
+    int64_t splits = (per_sm * 148 + d->B - 1) / d->B;
+    if (splits > nchunks / (2 * kWgWarps)) splits = nchunks / (2 * kWgWarps);       // >= 2 chunks per warp
+    if (splits < 1) splits = 1;
+    g.chunks_per_split = (int)((nchunks + splits - 1) / splits);
+    g.splits = (int)((nchunks + g.chunks_per_split - 1) / g.chunks_per_split);
+    return true;
+}
+
+template <typename T, int MT, int NT1, int NT2, bool ACL, bool B1CL>
+static int ws_launch(const void* A, const void* B1, const void* B2, float* part, const WsPlan& pl, int ldn, int n2_off, int ones_col,
+                     cudaStream_t st) {
+    auto kern = wgrad_stream_kernel<T, MT, NT1, NT2, ACL, B1CL>;
+    static std::atomic<size_t> granted[kMaxDevices];
+    if (!ensure_smem(kern, pl.smem, granted)) return LMNET_ERR_LAUNCH;
+    const WsGeom& g = pl.g;
+    const double bytes = (double)g.B * (g.M + g.N1 + g.N2) * g.P * sizeof(T);
+    dim3 grid(g.splits, g.B);
+    LMNET_LAUNCH(KID_WGRAD_1X1, st, bytes, (kern<<<grid, kWgThreads, pl.smem, st>>>((const T*)A, (const T*)B1, (const T*)B2, part, g,
+                                                                                   ldn, n2_off, ones_col)));
+    return LMNET_OK;
+}
+template <typename T>
+static int ws_dispatch(bool a_cl, bool b1_cl, const void* A, const void* B1, const void* B2, float* part, const WsPlan& pl, int ldn,
+                       int n2_off, int ones_col, cudaStream_t st) {
+#define X(mt, n1, n2, acl, bcl) \
+    if (pl.MT == mt && pl.NT1 == n1 && pl.NT2 == n2 && a_cl == acl && b1_cl == bcl) \
+        return ws_launch<T, mt, n1, n2, acl, bcl>(A, B1, B2, part, pl, ldn, n2_off, ones_col, st);
+    WS_LIST(X)
+#undef X
+    return LMNET_ERR_UNSUPPORTED;
+}
+
 extern "C" int lmnet_wgrad_1x1_cl_supported(const lmnet_wgrad_dims* d, int a_cl, int b1_cl, int dtype) {
     if (dtype != LMNET_BF16 && dtype != LMNET_F16) return 0;
     if (!a_cl && !b1_cl) return 0;
-    WgClPlan pl;
+    WgClPlan pl{};
     return wg_cl_plan(d, a_cl != 0, b1_cl != 0, pl) ? 1 : 0;
 }
 extern "C" size_t lmnet_wgrad_1x1_cl_workspace_bytes(const lmnet_wgrad_dims* d, int a_cl, int b1_cl) {
-    WgClPlan pl;
+    WgClPlan pl{};
     if (!wg_cl_plan(d, a_cl != 0, b1_cl != 0, pl)) return 0;
-    return (size_t)pl.g.B * pl.g.splits * pl.g.M * ((pl.g.NT1 + pl.g.NT2) * 8) * sizeof(float);
+    int splits = pl.g.splits;
+    WsPlan ws;
+    if (ws_plan(d, a_cl != 0, b1_cl != 0, pl, ws) && ws.g.splits > splits) splits = ws.g.splits;
+    return (size_t)pl.g.B * splits * pl.g.M * ((pl.g.NT1 + pl.g.NT2) * 8) * sizeof(float);
 }
 extern "C" int lmnet_wgrad_1x1_cl(const void* A, const void* B1, const void* B2, float* dW, float* drow,
                                   void* workspace, size_t workspace_bytes, const lmnet_wgrad_dims* d, int a_cl, int b1_cl,
@@ -556,18 +638,28 @@ extern "C" int lmnet_wgrad_1x1_cl(const void* A, const void* B1, const void* B2,
     if (!A || !B1 || (d->N2 > 0 && !B2) || !dW || !workspace) return LMNET_ERR_INVALID_ARG;
     if (workspace_bytes < lmnet_wgrad_1x1_cl_workspace_bytes(d, a_cl, b1_cl)) return LMNET_ERR_WORKSPACE;
     if ((uintptr_t)A % 16 || (uintptr_t)B1 % 16 || (uintptr_t)B2 % 16) return LMNET_ERR_UNSUPPORTED;
-    WgClPlan pl;
+    WgClPlan pl{};
     wg_cl_plan(d, a_cl != 0, b1_cl != 0, pl);
     cudaStream_t st = (cudaStream_t)stream;
     float* part = (float*)workspace;
-    int rc = dtype == LMNET_BF16 ? wg_cl_layouts<__nv_bfloat16>(a_cl != 0, b1_cl != 0, A, B1, d->N2 > 0 ? B2 : B1, part, pl, st)
-                                 : wg_cl_layouts<__half>(a_cl != 0, b1_cl != 0, A, B1, d->N2 > 0 ? B2 : B1, part, pl, st);
-    if (rc != LMNET_OK) return rc;
     const int Ntot = d->N1 + d->N2;
     const int64_t total = (int64_t)d->B * d->M * (Ntot + 1);
     const int ones_col = d->N2 > 0 ? pl.g.NT1 * 8 + d->N2 : d->N1;
+    const int ldn = (pl.g.NT1 + pl.g.NT2) * 8, n2_off = pl.g.NT1 * 8;
+    int splits = pl.g.splits;
+    WsPlan ws;
+    int rc;
+    if (ws_plan(d, a_cl != 0, b1_cl != 0, pl, ws)) {
+        splits = ws.g.splits;
+        rc = dtype == LMNET_BF16 ? ws_dispatch<__nv_bfloat16>(a_cl != 0, b1_cl != 0, A, B1, B2, part, ws, ldn, n2_off, ones_col, st)
+                                 : ws_dispatch<__half>(a_cl != 0, b1_cl != 0, A, B1, B2, part, ws, ldn, n2_off, ones_col, st);
+    } else {
+        rc = dtype == LMNET_BF16 ? wg_cl_layouts<__nv_bfloat16>(a_cl != 0, b1_cl != 0, A, B1, d->N2 > 0 ? B2 : B1, part, pl, st)
+                                 : wg_cl_layouts<__half>(a_cl != 0, b1_cl != 0, A, B1, d->N2 > 0 ? B2 : B1, part, pl, st);
+    }
+    if (rc != LMNET_OK) return rc;
     LMNET_LAUNCH(KID_WGRAD_REDUCE, st, 0, (wgrad_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
-        part, dW, drow, d->B, pl.g.splits, d->M, Ntot, (pl.g.NT1 + pl.g.NT2) * 8, d->N1, pl.g.NT1 * 8, ones_col)));
+        part, dW, drow, d->B, splits, d->M, Ntot, ldn, d->N1, n2_off, ones_col)));
     return LMNET_OK;
 }
 

@@ -35,12 +35,27 @@ for k, v in sorted(t.items(), key=lambda kv: -kv[1]["ms"])[:60]:
 open(out_txt, "w").write("\n".join(lines) + "\n")
 merged = collections.defaultdict(lambda: {"bytes": 0.0, "n": 0, "ms": 0.0})
 for k, v in own.items():
-    base = k.replace("lmnet::", "").split("<")[0].replace("_mma_kernel", "").replace("_kernel", "")
+    base = k.replace("lmnet::", "").split("<")[0]
+    for suffix in ("_tma_kernel", "_mma_kernel", "_fast_kernel", "_cl_kernel", "_kernel"):
+        if base.endswith(suffix):
+            base = base[:-len(suffix)]
+            break
+    if base.endswith("_cl"):
+        base = base[:-3]
+    base = {"conv3x3_fwd": "conv3x3", "upsample2x_cl_fwd": "upsample2x_fwd", "upsample2x_cl_bwd": "upsample2x_bwd"}.get(base, base)
     base = {"bnact_stats": "bn_stats", "bnact_apply": "bn_apply", "bnact_bwd_reduce": "bn_bwd_reduce", "bnact_bwd_apply": "bn_bwd_apply",
             "bnact_fin_fwd": "bn_fin_fwd", "bnact_fin_bwd": "bn_fin_bwd", "drpb_reduce": "na2d_drpb_reduce"}.get(base, base)
     merged[base]["bytes"] += v["rd"] + v["wr"]
     merged[base]["n"] += v["n"]
     merged[base]["ms"] += v["ms"]
-json.dump({k: {"dram_bytes_per_launch": v["bytes"] / v["n"], "launches_per_step": v["n"], "ncu_ms_per_step": v["ms"],
-               "share_of_step": v["ms"] / total} for k, v in sorted(merged.items())}, open(out_json, "w"), indent=1)
+import hashlib, glob, os
+_root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_h = hashlib.sha256()
+for _f in sorted(glob.glob(os.path.join(_root, "lm-net_b200", "csrc", "*.cu")) + glob.glob(os.path.join(_root, "lm-net_b200", "csrc", "*.cuh"))):
+    _h.update(os.path.basename(_f).encode())
+    _h.update(open(_f, "rb").read())
+_out = {"_csrc_sha256": _h.hexdigest()[:16]}       # bench.py refuses this file once the kernels change
+_out.update({k: {"dram_bytes_per_launch": v["bytes"] / v["n"], "launches_per_step": v["n"], "ncu_ms_per_step": v["ms"],
+               "share_of_step": v["ms"] / total} for k, v in sorted(merged.items())})
+json.dump(_out, open(out_json, "w"), indent=1)
 print("\n".join(lines[:34]))
