@@ -337,3 +337,29 @@ def test_oracle_against_flex_attention_with_dilation(H, W, K, d):
         got = flex_attention(q, k, v, score_mod=lambda s, b, h, qi, ki: s + rpb[h, by[qi, ki], bx[qi, ki]], block_mask=bm)
     ref = R.c_oracle().fused_fwd(nhwc(q), nhwc(k), nhwc(v), rpb, K, d)
     assert (nhwc(got) - ref).abs().max() < 1e-10
+
+
+@pytest.mark.parametrize("K", [3, 5, 7])
+def test_oracle_against_the_stock_torch_gather_formulation_of_the_baseline_tool(K):
+    """tools/stock_baselines.py times a plain-torch neighbourhood attention (advanced-indexing gather of the clamped
+    window + softmax + einsum) as the same-device stock baseline; it is a third, independently written formulation
+    and must agree with the C oracle (forward and, through autograd, all four gradients)."""
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    from stock_baselines import stock_na
+
+    from oracle.na2d_ref import c_oracle
+
+    torch.manual_seed(K)
+    q, k, v, go = (torch.randn(2, 2 * K + 1, 2 * K + 3, 3, 2, dtype=torch.float64) for _ in range(4))
+    rpb = torch.randn(3, 2 * K - 1, 2 * K - 1, dtype=torch.float64)
+    o = c_oracle()
+    ref = o.fused_fwd(q, k, v, rpb, K, 1, scale=0.7)
+    rg = o.fused_bwd(q, k, v, rpb, go, K, 1, scale=0.7)
+    qs, ks, vs, rs = (t.clone().requires_grad_() for t in (q, k, v, rpb))
+    got = stock_na(qs, ks, vs, rs, K, 0.7)
+    assert float((got - ref).abs().max()) < 1e-12
+    for g_, w_ in zip(torch.autograd.grad(got, (qs, ks, vs, rs), go), rg):
+        assert float((g_ - w_).abs().max()) < 1e-11
