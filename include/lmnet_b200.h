@@ -239,14 +239,18 @@ size_t lmnet_wgrad_1x1_cl_workspace_bytes(const lmnet_wgrad_dims* dims, int a_ch
 int lmnet_wgrad_1x1_cl(const void* A, const void* B1, const void* B2, float* dW, float* drow,
                        void* workspace, size_t workspace_bytes, const lmnet_wgrad_dims* dims,
                        int a_channels_last, int b1_channels_last, int dtype, void* stream);
+/* same, summed over the batch in the fixed-order reduction: dW [M][N1+N2], drow [M] (layers whose weights are shared
+ * by all images need no per-image result) */
+int lmnet_wgrad_1x1_cl_sum(const void* A, const void* B1, const void* B2, float* dW, float* drow,
+                           void* workspace, size_t workspace_bytes, const lmnet_wgrad_dims* dims,
+                           int a_channels_last, int b1_channels_last, int dtype, void* stream);
 
 /* ---- 1x1 convolutions as small-K GEMMs over pixels (widening step f1: forward + input gradients) -----------
  * out[b] = W1[b or shared] . in1[b]  (+ W2 . in2[b])  (+ bias)   for every batch image b and pixel.
  * Replaces expand_conv[0], pointwise_conv[0](gate * z) + shortcut[0](x) and their input gradients
  * (/root/reference/core/modules.py:537, 576-584, 587, 598-599).  Operand layouts: "planes" = [B, C, P] (NCHW),
  * "channels-last" = [B, P, C].  in2 (K2 > 0) is always channels-last and requires a channels-last output; a planes
- * output requires a channels-last in1.  Weights are [N, K] row-major in `dtype` (w1: [B, N, K1] when
- * w1_per_batch); bias fp32 [N] or NULL.  stats_part (planes output only, or NULL): per-CTA partial sums
+ * output requires a channels-last in1.  bias fp32 [N] or NULL.  stats_part (planes output only, or NULL): per-CTA partial sums
  * [N][ctas][2] (sum, sum of squares of the stored output) in the layout of lmnet_bn_act_fwd_stats;
  * ctas = lmnet_pixel_gemm_stats_ctas().  16-bit dtypes, P % 8 == 0, channel counts % 4 == 0. */
 typedef struct lmnet_pgemm_dims {
@@ -254,11 +258,23 @@ typedef struct lmnet_pgemm_dims {
     int64_t P;
     int32_t N, K1, K2;
 } lmnet_pgemm_dims;
+/* Weights are the layer's fp32 parameters, read in place with element strides (a transposed view costs nothing) and
+ * rounded to `dtype` while they are staged in shared memory — no cast / permute / gate-multiply kernels around the call.
+ * W1[n][k] = w1[n * w1_sn + k * w1_sk] * (gate ? gate[b][gate_on_n ? n : k] : 1)   (gate: fp32 [B][K1] or [B][N], the
+ * squeeze-excite gate folded into the pointwise weights per image);  W2[n][k] = w2[n * w2_sn + k * w2_sk]. */
+typedef struct lmnet_pgemm_weights {
+    const float* w1;
+    int64_t w1_sn, w1_sk;
+    const float* gate;
+    int32_t gate_on_n;
+    const float* w2;
+    int64_t w2_sn, w2_sk;
+} lmnet_pgemm_weights;
 int lmnet_pixel_gemm_supported(const lmnet_pgemm_dims* dims, int in1_channels_last, int out_channels_last,
                                int want_stats, int dtype);
 int lmnet_pixel_gemm_stats_ctas(const lmnet_pgemm_dims* dims, int in1_channels_last, int out_channels_last);
-int lmnet_pixel_gemm(const void* in1, int in1_channels_last, const void* w1, int w1_per_batch, const void* in2,
-                     const void* w2, const float* bias, void* out, int out_channels_last, float* stats_part,
+int lmnet_pixel_gemm(const void* in1, int in1_channels_last, const void* in2, const lmnet_pgemm_weights* weights,
+                     const float* bias, void* out, int out_channels_last, float* stats_part,
                      const lmnet_pgemm_dims* dims, int dtype, void* stream);
 /* BatchNorm + activation forward (training, NCHW planes) whose statistics pass already happened elsewhere:
  * stats_part = [C][nchunks][2] partial (sum, sum of squares) over all B*HW elements of each channel. */
@@ -273,16 +289,18 @@ int lmnet_bn_act_fwd_stats(const void* y, const float* stats_part, int nchunks, 
  * OverlapPatchEmbed of the neighbourhood transformers (/root/reference/core/modules.py:30-39), where the channel counts
  * fit the resident-weights kernel (lmnet_conv3x3_*_supported); cuDNN keeps the wide, low-resolution layers.
  * x: [B, H, W, Cin], y / dy: [B, Ho, Wo, Cout] with Ho = (H - 1) / stride + 1; 16-bit dtypes; Cin, Cout % 4 == 0.
- * w_packed: [9][Cout][Cin] in `dtype` (tap = ky * 3 + kx, i.e. weight.permute(2, 3, 0, 1)); bias fp32 [Cout] or NULL.
- * The stride-1 input gradient is the same call on dy with w_packed[tap][ci][co] = weight[co][ci][2 - ky][2 - kx].
+ * weight: the layer's fp32 parameter in torch layout, read in place and rounded to `dtype` while it is staged in shared
+ * memory: w_transposed = 0: [Cout][Cin][3][3];  w_transposed = 1 (the stride-1 input gradient: x := dy, Cin := the
+ * layer's Cout, Cout := the layer's Cin): the layer's own [Cin][Cout][3][3] tensor, used flipped and transposed.
+ * bias fp32 [Cout] or NULL.
  * wgrad: dW fp32 in torch layout [Cout][Cin][3][3], dbias fp32 [Cout] (or NULL); deterministic (per-CTA partials in the
  * workspace + fixed-order reduction). */
 typedef struct lmnet_conv3x3_dims {
     int32_t B, H, W, Cin, Cout, stride;
 } lmnet_conv3x3_dims;
 int lmnet_conv3x3_fwd_supported(const lmnet_conv3x3_dims* dims, int dtype);
-int lmnet_conv3x3_fwd(const void* x, const void* w_packed, const float* bias, void* y, const lmnet_conv3x3_dims* dims,
-                      int dtype, void* stream);
+int lmnet_conv3x3_fwd(const void* x, const float* weight, int w_transposed, const float* bias, void* y,
+                      const lmnet_conv3x3_dims* dims, int dtype, void* stream);
 int lmnet_conv3x3_wgrad_supported(const lmnet_conv3x3_dims* dims, int dtype);
 size_t lmnet_conv3x3_wgrad_workspace_bytes(const lmnet_conv3x3_dims* dims);
 int lmnet_conv3x3_wgrad(const void* x, const void* dy, float* dW, float* dbias, void* workspace, size_t workspace_bytes,

@@ -33,8 +33,8 @@ namespace lmnet {
 // ---------------------------------------------------------------------------------------------------
 template <typename T, int S, int MW, int NT>
 __global__ void __launch_bounds__(kCvThreads)
-conv3x3_fwd_kernel(const T* __restrict__ x, const T* __restrict__ wp /* [9][Cout][Cin] */, const float* __restrict__ bias,
-                   T* __restrict__ y, CvGeom g) {
+conv3x3_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w /* fp32 parameter, see cv_weight */, int w_t,
+                   const float* __restrict__ bias, T* __restrict__ y, CvGeom g) {
     extern __shared__ __align__(16) unsigned char cv_smem[];
     constexpr int n_pad = NT * 8;
     T* s_w = reinterpret_cast<T*>(cv_smem);                       // [9][n_pad][pitch_w]
@@ -46,11 +46,9 @@ conv3x3_fwd_kernel(const T* __restrict__ x, const T* __restrict__ wp /* [9][Cout
     const int gq = lane >> 2, tq = lane & 3;
     const T zero = from_f<T>(0.f);
 
-    for (int i = threadIdx.x; i < 9 * n_pad * g.pitch_w; i += kCvThreads) {
-        const int row = i / g.pitch_w, k = i - row * g.pitch_w;
-        const int tap = row / n_pad, n = row - tap * n_pad;
-        s_w[i] = (n < g.Cout && k < g.Cin) ? wp[((int64_t)tap * g.Cout + n) * g.Cin + k] : zero;
-    }
+    for (int i = threadIdx.x; i < 9 * n_pad * g.pitch_w; i += kCvThreads) s_w[i] = zero;
+    __syncthreads();
+    cv_stage_weights<T, kCvThreads>(s_w, w, w_t, g.Cin, g.Cout, n_pad, g.pitch_w);
     for (int i = threadIdx.x; i < n_pad; i += kCvThreads) s_bias[i] = (bias != nullptr && i < g.Cout) ? bias[i] : 0.f;
     for (int i = threadIdx.x; i < 2 * x_elems; i += kCvThreads) s_x[i] = zero;       // channel padding stays zero
     __syncthreads();
@@ -371,20 +369,20 @@ static bool cv_wg_plan(const lmnet_conv3x3_dims* d, CvWgPlan& pl) {
 }
 
 template <typename T, int S, int MW, int NT>
-static int cv_fwd_launch(const void* x, const void* wp, const float* bias, void* y, const CvFwdPlan& pl, cudaStream_t st) {
+static int cv_fwd_launch(const void* x, const float* w, int w_t, const float* bias, void* y, const CvFwdPlan& pl, cudaStream_t st) {
     auto kern = conv3x3_fwd_kernel<T, S, MW, NT>;
     static std::atomic<size_t> granted[kMaxDevices];
     if (!ensure_smem(kern, pl.smem, granted)) return LMNET_ERR_LAUNCH;
     const CvGeom& g = pl.g;
     const double bytes = ((double)g.B * g.H * g.W * g.Cin + (double)g.B * g.Ho * g.Wo * g.Cout) * sizeof(T);
-    LMNET_LAUNCH(KID_CONV3X3, st, bytes, (kern<<<pl.grid, kCvThreads, pl.smem, st>>>((const T*)x, (const T*)wp, bias, (T*)y, g)));
+    LMNET_LAUNCH(KID_CONV3X3, st, bytes, (kern<<<pl.grid, kCvThreads, pl.smem, st>>>((const T*)x, w, w_t, bias, (T*)y, g)));
     return LMNET_OK;
 }
 
 template <typename T>
-static int cv_fwd_dispatch(const void* x, const void* wp, const float* bias, void* y, const CvFwdPlan& pl, cudaStream_t st) {
+static int cv_fwd_dispatch(const void* x, const float* w, int w_t, const float* bias, void* y, const CvFwdPlan& pl, cudaStream_t st) {
 #define CV_CASE(SS, MWW, NTT) \
-    if (pl.g.S == SS && pl.MW == MWW && pl.NT == NTT) return cv_fwd_launch<T, SS, MWW, NTT>(x, wp, bias, y, pl, st);
+    if (pl.g.S == SS && pl.MW == MWW && pl.NT == NTT) return cv_fwd_launch<T, SS, MWW, NTT>(x, w, w_t, bias, y, pl, st);
     CV_CASE(1, 2, 2) CV_CASE(1, 2, 3) CV_CASE(1, 2, 6) CV_CASE(1, 1, 9) CV_CASE(1, 1, 12)
     CV_CASE(2, 1, 2) CV_CASE(2, 1, 3) CV_CASE(2, 1, 6) CV_CASE(2, 1, 9) CV_CASE(2, 1, 12)
 #undef CV_CASE
@@ -423,17 +421,18 @@ extern "C" int lmnet_conv3x3_fwd_supported(const lmnet_conv3x3_dims* d, int dtyp
     return cv_fwd_plan(d, pl) ? 1 : 0;
 }
 
-extern "C" int lmnet_conv3x3_fwd(const void* x, const void* w_packed, const float* bias, void* y, const lmnet_conv3x3_dims* d,
-                                 int dtype, void* stream) {
+extern "C" int lmnet_conv3x3_fwd(const void* x, const float* weight, int w_transposed, const float* bias, void* y,
+                                 const lmnet_conv3x3_dims* d, int dtype, void* stream) {
     if (!lmnet_conv3x3_fwd_supported(d, dtype)) return LMNET_ERR_UNSUPPORTED;
-    if (!x || !w_packed || !y) return LMNET_ERR_INVALID_ARG;
-    if ((uintptr_t)x % 16 != 0 || (uintptr_t)y % 16 != 0 || (uintptr_t)w_packed % 8 != 0) return LMNET_ERR_UNSUPPORTED;
+    if (!x || !weight || !y) return LMNET_ERR_INVALID_ARG;
+    if ((uintptr_t)x % 16 != 0 || (uintptr_t)y % 16 != 0) return LMNET_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
-    if (cv_fast_fwd_has(d->stride, d->Cin, d->Cout)) return cv_fast_fwd(x, w_packed, bias, y, d, dtype, st);
+    const int w_t = w_transposed ? 1 : 0;
+    if (cv_fast_fwd_has(d->stride, d->Cin, d->Cout)) return cv_fast_fwd(x, weight, w_t, bias, y, d, dtype, st);
     CvFwdPlan pl{};
     cv_fwd_plan(d, pl);
-    return dtype == LMNET_BF16 ? cv_fwd_dispatch<__nv_bfloat16>(x, w_packed, bias, y, pl, st)
-                               : cv_fwd_dispatch<__half>(x, w_packed, bias, y, pl, st);
+    return dtype == LMNET_BF16 ? cv_fwd_dispatch<__nv_bfloat16>(x, weight, w_t, bias, y, pl, st)
+                               : cv_fwd_dispatch<__half>(x, weight, w_t, bias, y, pl, st);
 }
 
 extern "C" int lmnet_conv3x3_wgrad_supported(const lmnet_conv3x3_dims* d, int dtype) {

@@ -117,10 +117,33 @@ __host__ __device__ constexpr int cv_pitch_c(int cols) {     // multiple of 8 el
     return p;
 }
 
+// W[tap][n][k] of the contraction out of the layer's fp32 parameter (torch layout [Co][Ci][3][3]):
+//   forward (w_t = 0):            n = co, k = ci:  w[co][ci][tap]
+//   stride-1 input gradient (1):  n = ci, k = co:  w[co][ci][8 - tap]   (flipped taps, transposed channels)
+__device__ __forceinline__ float cv_weight(const float* __restrict__ w, int w_t, int tap, int n, int k, int Cin, int Cout) {
+    return w_t ? __ldg(w + ((int64_t)k * Cout + n) * 9 + (8 - tap)) : __ldg(w + ((int64_t)n * Cin + k) * 9 + tap);
+}
+
+// stage the whole fp32 parameter [Co][Ci][3][3] into shared memory as W[tap][n][k] (pitch PW, n_pad rows per tap), read
+// in memory order (coalesced) and rounded to T here; the padding must have been zeroed before
+template <typename T, int NTHREADS>
+__device__ __forceinline__ void cv_stage_weights(T* s_w, const float* __restrict__ w, int w_t, int Cin, int Cout, int n_pad, int PW) {
+    // forward: the tensor is [Cout][Cin][9]; transposed: the layer's own tensor is [Cin_op = its Cout ... ] = [K][N][9]
+    const int outer = w_t ? Cin : Cout, inner = w_t ? Cout : Cin;           // memory: [outer][inner][9]
+    const int total = outer * inner * 9;
+    for (int i = threadIdx.x; i < total; i += NTHREADS) {
+        const int o = i / (inner * 9), rem = i - o * inner * 9;
+        const int in = rem / 9, tap = rem - in * 9;
+        const float v = __ldg(w + i);
+        if (w_t) s_w[((8 - tap) * n_pad + in) * PW + o] = from_f<T>(v);      // n = ci (inner), k = co (outer), flipped tap
+        else s_w[(tap * n_pad + o) * PW + in] = from_f<T>(v);                // n = co (outer), k = ci (inner)
+    }
+}
+
 // channel-specialised kernels (conv3x3_fast.cu): LMNET_ERR_UNSUPPORTED when (stride, Cin, Cout) is not in their list
 bool cv_fast_fwd_has(int S, int Cin, int Cout);
 bool cv_fast_wgrad_has(int S, int Cin, int Cout);
-int cv_fast_fwd(const void* x, const void* wp, const float* bias, void* y, const lmnet_conv3x3_dims* d, int dtype, cudaStream_t st);
+int cv_fast_fwd(const void* x, const float* w, int w_t, const float* bias, void* y, const lmnet_conv3x3_dims* d, int dtype, cudaStream_t st);
 int cv_fast_wgrad_grid(const lmnet_conv3x3_dims* d, int* mp, int* ldn);     // CTAs (= partials), padded Cout, padded Cin
 int cv_fast_wgrad(const void* x, const void* dy, float* part, float* part_b, const lmnet_conv3x3_dims* d, int dtype, cudaStream_t st);
 

@@ -68,8 +68,8 @@ __device__ __forceinline__ void cvf_issue_x(uint32_t s, const T* __restrict__ x,
 
 template <typename T, int S, int CIN, int COUT>
 __global__ void __launch_bounds__(kCvThreads)
-conv3x3_fwd_fast_kernel(const T* __restrict__ x, const T* __restrict__ wp /* [9][COUT][CIN] */, const float* __restrict__ bias,
-                        T* __restrict__ y, CvGeom g) {
+conv3x3_fwd_fast_kernel(const T* __restrict__ x, const float* __restrict__ w /* fp32 parameter, see cv_weight */, int w_t,
+                        const float* __restrict__ bias, T* __restrict__ y, CvGeom g) {
     using C = CvCfg<S, CIN, COUT>;
     constexpr int KS = C::KS, NT = C::NT, MW = C::MW, PX = C::PX, PW = C::PW, PO = C::PO, IW = C::IW, n_pad = NT * 8;
     extern __shared__ __align__(16) unsigned char cv_smem[];
@@ -80,15 +80,11 @@ conv3x3_fwd_fast_kernel(const T* __restrict__ x, const T* __restrict__ wp /* [9]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gq = lane >> 2, tq = lane & 3;
 
-    {   // weights [9][n_pad][PW]: 8-byte vectors, zero padding beyond COUT rows / CIN columns
-        constexpr int VR = PW / 4;
-        for (int i = threadIdx.x; i < 9 * n_pad * VR; i += kCvThreads) {
-            const int row = i / VR, v = i - row * VR;
-            const int tap = row / n_pad, n = row - tap * n_pad;
-            uint2 val = make_uint2(0u, 0u);
-            if (n < COUT && v * 4 < CIN) val = __ldg(reinterpret_cast<const uint2*>(wp + ((int64_t)tap * COUT + n) * CIN + v * 4));
-            *reinterpret_cast<uint2*>(s_w + row * PW + v * 4) = val;
-        }
+    {   // weights [9][n_pad][PW] from the fp32 parameter (coalesced reads, rounded here), zero padding
+        uint4* zw = reinterpret_cast<uint4*>(s_w);
+        for (int i = threadIdx.x; i < C::W_ELEMS / 8; i += kCvThreads) zw[i] = make_uint4(0u, 0u, 0u, 0u);
+        __syncthreads();
+        cv_stage_weights<T, kCvThreads>(s_w, w, w_t, CIN, COUT, n_pad, PW);
         for (int i = threadIdx.x; i < n_pad; i += kCvThreads) s_bias[i] = (bias != nullptr && i < COUT) ? bias[i] : 0.f;
         uint4* z = reinterpret_cast<uint4*>(s_x);
         for (int i = threadIdx.x; i < 2 * C::X_ELEMS / 8; i += kCvThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -334,7 +330,7 @@ static int cvf_grid(int tiles, size_t smem, int cap) {
 }
 
 template <typename T, int S, int CIN, int COUT>
-static int cvf_fwd_launch(const void* x, const void* wp, const float* bias, void* y, const lmnet_conv3x3_dims* d, cudaStream_t st) {
+static int cvf_fwd_launch(const void* x, const float* w, int w_t, const float* bias, void* y, const lmnet_conv3x3_dims* d, cudaStream_t st) {
     using C = CvCfg<S, CIN, COUT>;
     auto kern = conv3x3_fwd_fast_kernel<T, S, CIN, COUT>;
     static std::atomic<size_t> granted[kMaxDevices];
@@ -343,15 +339,15 @@ static int cvf_fwd_launch(const void* x, const void* wp, const float* bias, void
     cvf_geom(d, C::TH, g);
     g.ncta = cvf_grid(g.tiles, C::SMEM, 4);
     const double bytes = ((double)g.B * g.H * g.W * g.Cin + (double)g.B * g.Ho * g.Wo * g.Cout) * sizeof(T);
-    LMNET_LAUNCH(KID_CONV3X3, st, bytes, (kern<<<g.ncta, kCvThreads, C::SMEM, st>>>((const T*)x, (const T*)wp, bias, (T*)y, g)));
+    LMNET_LAUNCH(KID_CONV3X3, st, bytes, (kern<<<g.ncta, kCvThreads, C::SMEM, st>>>((const T*)x, w, w_t, bias, (T*)y, g)));
     return LMNET_OK;
 }
 
-int cv_fast_fwd(const void* x, const void* wp, const float* bias, void* y, const lmnet_conv3x3_dims* d, int dtype, cudaStream_t st) {
+int cv_fast_fwd(const void* x, const float* w, int w_t, const float* bias, void* y, const lmnet_conv3x3_dims* d, int dtype, cudaStream_t st) {
 #define X(SS, CI, CO)                                                                                              \
     if (d->stride == SS && d->Cin == CI && d->Cout == CO)                                                          \
-        return dtype == LMNET_BF16 ? cvf_fwd_launch<__nv_bfloat16, SS, CI, CO>(x, wp, bias, y, d, st)              \
-                                   : cvf_fwd_launch<__half, SS, CI, CO>(x, wp, bias, y, d, st);
+        return dtype == LMNET_BF16 ? cvf_fwd_launch<__nv_bfloat16, SS, CI, CO>(x, w, w_t, bias, y, d, st)         \
+                                   : cvf_fwd_launch<__half, SS, CI, CO>(x, w, w_t, bias, y, d, st);
     CV_FAST_FWD_LIST(X)
 #undef X
     return LMNET_ERR_UNSUPPORTED;

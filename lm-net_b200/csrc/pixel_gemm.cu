@@ -43,7 +43,6 @@ struct PgGeom {
     int tiles, ctas_x, tiles_per_cta;  // per image
     int w_pitch;                       // element pitch of the weight rows [N][K1p + K2p + 8]
     int in1_pitch, in2_pitch, out_pitch;
-    int w1_per_batch;
 };
 
 __device__ __forceinline__ void pg_cp16(void* smem, const void* gmem, bool valid) {
@@ -167,7 +166,7 @@ __device__ __forceinline__ void pg_issue_planes(uint32_t s, int pitch, const T* 
 // ---------------------------------------------------------------------------------------------------
 template <typename T, bool OUT_CL, bool IN1_CL, bool HAS_IN2, int TA, int TB>
 __global__ void __launch_bounds__(kPgThreads)
-pixel_gemm_kernel(const T* __restrict__ in1, const T* __restrict__ w1, const T* __restrict__ in2, const T* __restrict__ w2,
+pixel_gemm_kernel(const T* __restrict__ in1, const T* __restrict__ in2, const lmnet_pgemm_weights w,
                   const float* __restrict__ bias, T* __restrict__ out, float* __restrict__ stats_part, PgGeom g) {
     static_assert(TA * TB <= kPgMaxAcc, "accumulator budget");
     static_assert(OUT_CL || IN1_CL, "planes -> planes is not needed by the block");
@@ -188,14 +187,35 @@ pixel_gemm_kernel(const T* __restrict__ in1, const T* __restrict__ w1, const T* 
     const T zero = from_f<T>(0.f);
 
     // ---- one-time: weights (zero padded), bias, zero the padding of the input stages
-    for (int i = threadIdx.x; i < n_pad * g.w_pitch; i += kPgThreads) {
-        const int n = i / g.w_pitch, k = i - n * g.w_pitch;
-        T v = zero;
-        if (n < g.NC) {
-            if (k < g.K1) v = w1[((int64_t)(g.w1_per_batch ? b : 0) * g.N + n0 + n) * g.K1 + k];
-            else if (HAS_IN2 && k >= g.K1p && k - g.K1p < g.K2) v = w2[(int64_t)(n0 + n) * g.K2 + (k - g.K1p)];
+    {
+        uint4* z = reinterpret_cast<uint4*>(s_w);                            // w_pitch is a multiple of 8 elements
+        for (int i = threadIdx.x; i < (n_pad * g.w_pitch) >> 3; i += kPgThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    __syncthreads();
+    {   // fp32 parameters, read in memory order (coalesced whichever way the view is transposed), rounded here (RN, as a
+        // host-side cast would) and scattered to [n][k]
+        const bool k_fast = w.w1_sk <= w.w1_sn;
+        const int inner = k_fast ? g.K1 : g.NC;
+        PgDiv d(threadIdx.x, inner);
+        const int dq = kPgThreads / inner, dr = kPgThreads - dq * inner;
+        for (int i = threadIdx.x; i < g.NC * g.K1; i += kPgThreads) {
+            const int n = k_fast ? d.q : d.r, k = k_fast ? d.r : d.q;
+            float f = __ldg(w.w1 + (int64_t)(n0 + n) * w.w1_sn + (int64_t)k * w.w1_sk);
+            if (w.gate != nullptr) f *= __ldg(w.gate + (w.gate_on_n ? (int64_t)b * g.N + n0 + n : (int64_t)b * g.K1 + k));
+            s_w[n * g.w_pitch + k] = from_f<T>(f);
+            d.step(dq, dr, inner);
         }
-        s_w[i] = v;
+        if constexpr (HAS_IN2) {
+            const bool k_fast2 = w.w2_sk <= w.w2_sn;
+            const int inner2 = k_fast2 ? g.K2 : g.NC;
+            PgDiv d2(threadIdx.x, inner2);
+            const int dq2 = kPgThreads / inner2, dr2 = kPgThreads - dq2 * inner2;
+            for (int i = threadIdx.x; i < g.NC * g.K2; i += kPgThreads) {
+                const int n = k_fast2 ? d2.q : d2.r, k = k_fast2 ? d2.r : d2.q;
+                s_w[n * g.w_pitch + g.K1p + k] = from_f<T>(__ldg(w.w2 + (int64_t)(n0 + n) * w.w2_sn + (int64_t)k * w.w2_sk));
+                d2.step(dq2, dr2, inner2);
+            }
+        }
     }
     for (int i = threadIdx.x; i < n_pad; i += kPgThreads) s_bias[i] = (bias != nullptr && i < g.NC) ? bias[n0 + i] : 0.f;
     {
@@ -439,7 +459,6 @@ static bool pg_plan(const lmnet_pgemm_dims* d, bool in1_cl, bool out_cl, bool st
     g.K1p = (d->K1 + 15) / 16 * 16;
     g.K2p = d->K2 > 0 ? (d->K2 + 15) / 16 * 16 : 0;
     g.w_pitch = pg_pitch(g.K1p + g.K2p);
-    g.w1_per_batch = 0;
     g.NC = d->N;
     int nchunks = 1;
     if (out_cl) {
@@ -487,7 +506,7 @@ static bool pg_plan(const lmnet_pgemm_dims* d, bool in1_cl, bool out_cl, bool st
 }
 
 template <typename T, bool OUT_CL, bool IN1_CL, bool HAS_IN2, int TA, int TB>
-static int pg_launch(const void* in1, const void* w1, const void* in2, const void* w2, const float* bias, void* out,
+static int pg_launch(const void* in1, const void* in2, const lmnet_pgemm_weights& w, const float* bias, void* out,
                      float* stats_part, const PgPlan& pl, cudaStream_t st) {
     auto kern = pixel_gemm_kernel<T, OUT_CL, IN1_CL, HAS_IN2, TA, TB>;
     static std::atomic<size_t> granted[kMaxDevices];
@@ -495,15 +514,15 @@ static int pg_launch(const void* in1, const void* w1, const void* in2, const voi
     const PgGeom& g = pl.g;
     const double bytes = (double)g.B * g.P * (g.K1 + g.K2 + g.N) * sizeof(T);
     LMNET_LAUNCH(KID_PIXEL_GEMM, st, bytes, (kern<<<pl.grid, kPgThreads, pl.smem, st>>>(
-        (const T*)in1, (const T*)w1, (const T*)in2, (const T*)w2, bias, (T*)out, stats_part, g)));
+        (const T*)in1, (const T*)in2, w, bias, (T*)out, stats_part, g)));
     return LMNET_OK;
 }
 
 template <typename T, bool OUT_CL, bool IN1_CL, bool HAS_IN2>
-static int pg_dispatch_tiles(const void* in1, const void* w1, const void* in2, const void* w2, const float* bias, void* out,
+static int pg_dispatch_tiles(const void* in1, const void* in2, const lmnet_pgemm_weights& w, const float* bias, void* out,
                              float* stats_part, const PgPlan& pl, cudaStream_t st) {
 #define PG_CASE(A, B) \
-    if (pl.TA == A && pl.TB == B) return pg_launch<T, OUT_CL, IN1_CL, HAS_IN2, A, B>(in1, w1, in2, w2, bias, out, stats_part, pl, st);
+    if (pl.TA == A && pl.TB == B) return pg_launch<T, OUT_CL, IN1_CL, HAS_IN2, A, B>(in1, in2, w, bias, out, stats_part, pl, st);
     PG_CASE(4, 1) PG_CASE(4, 2) PG_CASE(4, 3) PG_CASE(2, 4) PG_CASE(2, 5) PG_CASE(2, 6) PG_CASE(1, 7) PG_CASE(1, 8)
     PG_CASE(1, 9) PG_CASE(1, 10) PG_CASE(1, 11) PG_CASE(1, 12)
 #undef PG_CASE
@@ -511,17 +530,17 @@ static int pg_dispatch_tiles(const void* in1, const void* w1, const void* in2, c
 }
 
 template <typename T>
-static int pg_dispatch(bool in1_cl, bool out_cl, bool has_in2, const void* in1, const void* w1, const void* in2, const void* w2,
+static int pg_dispatch(bool in1_cl, bool out_cl, bool has_in2, const void* in1, const void* in2, const lmnet_pgemm_weights& w,
                        const float* bias, void* out, float* stats_part, const PgPlan& pl, cudaStream_t st) {
     if (out_cl) {
         if (in1_cl) {
             if (has_in2) return LMNET_ERR_UNSUPPORTED;
-            return pg_dispatch_tiles<T, true, true, false>(in1, w1, in2, w2, bias, out, stats_part, pl, st);
+            return pg_dispatch_tiles<T, true, true, false>(in1, in2, w, bias, out, stats_part, pl, st);
         }
-        if (has_in2) return pg_dispatch_tiles<T, true, false, true>(in1, w1, in2, w2, bias, out, stats_part, pl, st);
-        return pg_dispatch_tiles<T, true, false, false>(in1, w1, in2, w2, bias, out, stats_part, pl, st);
+        if (has_in2) return pg_dispatch_tiles<T, true, false, true>(in1, in2, w, bias, out, stats_part, pl, st);
+        return pg_dispatch_tiles<T, true, false, false>(in1, in2, w, bias, out, stats_part, pl, st);
     }
-    return pg_dispatch_tiles<T, false, true, false>(in1, w1, in2, w2, bias, out, stats_part, pl, st);
+    return pg_dispatch_tiles<T, false, true, false>(in1, in2, w, bias, out, stats_part, pl, st);
 }
 
 }  // namespace lmnet
@@ -540,18 +559,16 @@ extern "C" int lmnet_pixel_gemm_stats_ctas(const lmnet_pgemm_dims* d, int in1_cl
     return (int)(pl.grid.x * pl.grid.y);
 }
 
-extern "C" int lmnet_pixel_gemm(const void* in1, int in1_cl, const void* w1, int w1_per_batch, const void* in2,
-                                const void* w2, const float* bias, void* out, int out_cl, float* stats_part,
-                                const lmnet_pgemm_dims* d, int dtype, void* stream) {
+extern "C" int lmnet_pixel_gemm(const void* in1, int in1_cl, const void* in2, const lmnet_pgemm_weights* w, const float* bias,
+                                void* out, int out_cl, float* stats_part, const lmnet_pgemm_dims* d, int dtype, void* stream) {
     if (!lmnet_pixel_gemm_supported(d, in1_cl, out_cl, stats_part != nullptr, dtype)) return LMNET_ERR_UNSUPPORTED;
-    if (!in1 || !w1 || !out || (d->K2 > 0 && (!in2 || !w2))) return LMNET_ERR_INVALID_ARG;
+    if (!in1 || !w || !w->w1 || !out || (d->K2 > 0 && (!in2 || !w->w2))) return LMNET_ERR_INVALID_ARG;
     for (const void* q : {in1, in2, (const void*)out})
         if ((uintptr_t)q % 16 != 0) return LMNET_ERR_UNSUPPORTED;
     PgPlan pl;
     pg_plan(d, in1_cl != 0, out_cl != 0, stats_part != nullptr, pl);
-    pl.g.w1_per_batch = w1_per_batch ? 1 : 0;
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == LMNET_BF16)
-        return pg_dispatch<__nv_bfloat16>(in1_cl != 0, out_cl != 0, d->K2 > 0, in1, w1, in2, w2, bias, out, stats_part, pl, st);
-    return pg_dispatch<__half>(in1_cl != 0, out_cl != 0, d->K2 > 0, in1, w1, in2, w2, bias, out, stats_part, pl, st);
+        return pg_dispatch<__nv_bfloat16>(in1_cl != 0, out_cl != 0, d->K2 > 0, in1, in2, *w, bias, out, stats_part, pl, st);
+    return pg_dispatch<__half>(in1_cl != 0, out_cl != 0, d->K2 > 0, in1, in2, *w, bias, out, stats_part, pl, st);
 }

@@ -197,6 +197,28 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part, float* __res
     else if (drow != nullptr) drow[(int64_t)b * M + m] = a;
 }
 
+// the same reduction, additionally summed over the batch: dW[m][n], drow[m]
+__global__ void __launch_bounds__(256)
+wgrad_reduce_bsum_kernel(const float* __restrict__ part, float* __restrict__ dW, float* __restrict__ drow,
+                         int B, int splits, int M, int Ntot, int ldn, int N1, int n2_off, int ones_col) {
+    // one warp per output element: lanes stride over the B * splits partials, then a fixed-order butterfly
+    const int idx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (idx >= M * (Ntot + 1)) return;
+    const int n = idx % (Ntot + 1), m = idx / (Ntot + 1);
+    const int col = n < N1 ? n : n < Ntot ? n2_off + (n - N1) : ones_col;
+    const int total = B * splits;
+    const float* p = part + (int64_t)m * ldn + col;
+    const int64_t stride = (int64_t)M * ldn;
+    float a = 0.f;
+    for (int s = lane; s < total; s += 32) a += p[s * stride];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) {
+        if (n < Ntot) dW[(int64_t)m * Ntot + n] = a;
+        else if (drow != nullptr) drow[m] = a;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Mixed-layout variant: operands may be channels-last ([B, P, C], C contiguous — the layout of the block's
 // input / output tensors) instead of NCHW planes ([B, C, P]).  A channels-last tile is staged as [64 pixels][C]
@@ -631,9 +653,9 @@ extern "C" size_t lmnet_wgrad_1x1_cl_workspace_bytes(const lmnet_wgrad_dims* d, 
     if (ws_plan(d, a_cl != 0, b1_cl != 0, pl, ws) && ws.g.splits > splits) splits = ws.g.splits;
     return (size_t)pl.g.B * splits * pl.g.M * ((pl.g.NT1 + pl.g.NT2) * 8) * sizeof(float);
 }
-extern "C" int lmnet_wgrad_1x1_cl(const void* A, const void* B1, const void* B2, float* dW, float* drow,
-                                  void* workspace, size_t workspace_bytes, const lmnet_wgrad_dims* d, int a_cl, int b1_cl,
-                                  int dtype, void* stream) {
+static int wgrad_1x1_cl_impl(const void* A, const void* B1, const void* B2, float* dW, float* drow,
+                             void* workspace, size_t workspace_bytes, const lmnet_wgrad_dims* d, int a_cl, int b1_cl,
+                             int dtype, void* stream, bool batch_sum) {
     if (!lmnet_wgrad_1x1_cl_supported(d, a_cl, b1_cl, dtype)) return LMNET_ERR_UNSUPPORTED;
     if (!A || !B1 || (d->N2 > 0 && !B2) || !dW || !workspace) return LMNET_ERR_INVALID_ARG;
     if (workspace_bytes < lmnet_wgrad_1x1_cl_workspace_bytes(d, a_cl, b1_cl)) return LMNET_ERR_WORKSPACE;
@@ -658,9 +680,26 @@ extern "C" int lmnet_wgrad_1x1_cl(const void* A, const void* B1, const void* B2,
                                  : wg_cl_layouts<__half>(a_cl != 0, b1_cl != 0, A, B1, d->N2 > 0 ? B2 : B1, part, pl, st);
     }
     if (rc != LMNET_OK) return rc;
+    if (batch_sum) {
+        const int n_out = d->M * (Ntot + 1);
+        LMNET_LAUNCH(KID_WGRAD_REDUCE, st, 0, (wgrad_reduce_bsum_kernel<<<(n_out + 7) / 8, 256, 0, st>>>(
+            part, dW, drow, d->B, splits, d->M, Ntot, ldn, d->N1, n2_off, ones_col)));
+        return LMNET_OK;
+    }
     LMNET_LAUNCH(KID_WGRAD_REDUCE, st, 0, (wgrad_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
         part, dW, drow, d->B, splits, d->M, Ntot, ldn, d->N1, n2_off, ones_col)));
     return LMNET_OK;
+}
+
+extern "C" int lmnet_wgrad_1x1_cl(const void* A, const void* B1, const void* B2, float* dW, float* drow,
+                                  void* workspace, size_t workspace_bytes, const lmnet_wgrad_dims* d, int a_cl, int b1_cl,
+                                  int dtype, void* stream) {
+    return wgrad_1x1_cl_impl(A, B1, B2, dW, drow, workspace, workspace_bytes, d, a_cl, b1_cl, dtype, stream, false);
+}
+extern "C" int lmnet_wgrad_1x1_cl_sum(const void* A, const void* B1, const void* B2, float* dW, float* drow,
+                                      void* workspace, size_t workspace_bytes, const lmnet_wgrad_dims* d, int a_cl, int b1_cl,
+                                      int dtype, void* stream) {
+    return wgrad_1x1_cl_impl(A, B1, B2, dW, drow, workspace, workspace_bytes, d, a_cl, b1_cl, dtype, stream, true);
 }
 
 extern "C" int lmnet_wgrad_1x1_supported(const lmnet_wgrad_dims* d, int dtype) {

@@ -66,6 +66,11 @@ class PgemmDims(Structure):
     _fields_ = [("B", c_int32), ("P", c_int64), ("N", c_int32), ("K1", c_int32), ("K2", c_int32)]
 
 
+class PgemmWeights(Structure):
+    _fields_ = [("w1", c_void_p), ("w1_sn", c_int64), ("w1_sk", c_int64), ("gate", c_void_p), ("gate_on_n", c_int32),
+                ("w2", c_void_p), ("w2_sn", c_int64), ("w2_sk", c_int64)]
+
+
 class Conv3x3Dims(Structure):
     _fields_ = [("B", c_int32), ("H", c_int32), ("W", c_int32), ("Cin", c_int32), ("Cout", c_int32), ("stride", c_int32)]
 
@@ -122,6 +127,7 @@ def lib():
     L.lmnet_wgrad_1x1_cl_workspace_bytes.restype = c_size_t
     L.lmnet_wgrad_1x1_cl_workspace_bytes.argtypes = [POINTER(WgradDims), c_int, c_int]
     L.lmnet_wgrad_1x1_cl.argtypes = [c_void_p] * 5 + [c_void_p, c_size_t, POINTER(WgradDims), c_int, c_int, c_int, c_void_p]
+    L.lmnet_wgrad_1x1_cl_sum.argtypes = L.lmnet_wgrad_1x1_cl.argtypes
     L.lmnet_layer_norm_supported.argtypes = [c_int]
     L.lmnet_layer_norm_workspace_bytes.restype = c_size_t
     L.lmnet_layer_norm_workspace_bytes.argtypes = [c_int64, c_int]
@@ -135,13 +141,13 @@ def lib():
     ppg = POINTER(PgemmDims)
     L.lmnet_pixel_gemm_supported.argtypes = [ppg, c_int, c_int, c_int, c_int]
     L.lmnet_pixel_gemm_stats_ctas.argtypes = [ppg, c_int, c_int]
-    L.lmnet_pixel_gemm.argtypes = [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+    L.lmnet_pixel_gemm.argtypes = [c_void_p, c_int, c_void_p, POINTER(PgemmWeights), c_void_p, c_void_p, c_int,
                                    c_void_p, ppg, c_int, c_void_p]
     L.lmnet_bn_act_fwd_stats.argtypes = [c_void_p, c_void_p, c_int] + [c_void_p] * 8 + [c_float, c_float, c_int, c_void_p,
                                                                                       c_size_t, pbd, c_int, c_void_p]
     pcv = POINTER(Conv3x3Dims)
     L.lmnet_conv3x3_fwd_supported.argtypes = [pcv, c_int]
-    L.lmnet_conv3x3_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, pcv, c_int, c_void_p]
+    L.lmnet_conv3x3_fwd.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p, pcv, c_int, c_void_p]
     L.lmnet_conv3x3_wgrad_supported.argtypes = [pcv, c_int]
     L.lmnet_conv3x3_wgrad_workspace_bytes.restype = c_size_t
     L.lmnet_conv3x3_wgrad_workspace_bytes.argtypes = [pcv]
@@ -260,4 +266,4 @@ def dw_grads(dw, dgamma, dbeta) -> DwGrads:
 
 
 __all__ = ["lib", "check", "dtype_code", "require_cuda", "stream_ptr", "ptr", "view5", "na_dims", "dw_params",
-           "dw_grads", "View5", "NADims", "DwParams", "DwGrads", "DwDims", "BnDims", "ACT_CODES", "WgradDims", "PgemmDims", "Conv3x3Dims", "UpsampleDims", "UpsampleClDims", "byref", "launch_count", "LIB_PATH"]
+           "dw_grads", "View5", "NADims", "DwParams", "DwGrads", "DwDims", "BnDims", "ACT_CODES", "WgradDims", "PgemmDims", "PgemmWeights", "Conv3x3Dims", "UpsampleDims", "UpsampleClDims", "byref", "launch_count", "LIB_PATH"]

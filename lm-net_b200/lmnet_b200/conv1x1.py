@@ -111,19 +111,22 @@ class _PointwiseShortcut(torch.autograd.Function):
         return dz, dgate, dx, dwpw, dwsc, dbias
 
 
-def _wgrad_cl(A, B1, B2, a_cl, b1_cl):
+def _wgrad_cl(A, B1, B2, a_cl, b1_cl, batch_sum=False):
     """Mixed-layout weight gradient.  A: planes [B,M,P] or channels-last [B,P,M]; B1 likewise with N1; B2 (or None) is
-    channels-last [B,P,N2].  Returns (dW [B,M,N1+N2] fp32, drow [B,M] fp32)."""
+    channels-last [B,P,N2].  Returns (dW [B,M,N1+N2] fp32, drow [B,M] fp32), or with batch_sum the sums over the batch
+    ([M,N1+N2], [M]) straight out of the fixed-order reduction kernel."""
     Bn = A.shape[0]
     M, P = (A.shape[2], A.shape[1]) if a_cl else (A.shape[1], A.shape[2])
     N1 = B1.shape[2] if b1_cl else B1.shape[1]
     N2 = 0 if B2 is None else B2.shape[2]
     dims = L.WgradDims(Bn, M, N1, N2, P)
-    dW = torch.empty(Bn, M, N1 + N2, dtype=torch.float32, device=A.device)
-    drow = torch.empty(Bn, M, dtype=torch.float32, device=A.device)
+    lead = () if batch_sum else (Bn,)
+    dW = torch.empty(*lead, M, N1 + N2, dtype=torch.float32, device=A.device)
+    drow = torch.empty(*lead, M, dtype=torch.float32, device=A.device)
     n = L.lib().lmnet_wgrad_1x1_cl_workspace_bytes(L.byref(dims), int(a_cl), int(b1_cl))
     ws = torch.empty(max(int(n), 16), dtype=torch.uint8, device=A.device)
-    rc = L.lib().lmnet_wgrad_1x1_cl(L.ptr(A), L.ptr(B1), L.ptr(B2), L.ptr(dW), L.ptr(drow), L.ptr(ws), ws.numel(),
+    fn = L.lib().lmnet_wgrad_1x1_cl_sum if batch_sum else L.lib().lmnet_wgrad_1x1_cl
+    rc = fn(L.ptr(A), L.ptr(B1), L.ptr(B2), L.ptr(dW), L.ptr(drow), L.ptr(ws), ws.numel(),
                                     L.byref(dims), int(a_cl), int(b1_cl), L.dtype_code(A), L.stream_ptr())
     L.check(rc, "wgrad_1x1_cl")
     return dW, drow
@@ -147,29 +150,38 @@ def pgemm_supported(B, P, N, K1, K2, in1_cl, out_cl, stats, dtype) -> bool:
                                                    int(stats), L._DTYPES[dtype]))
 
 
-def pixel_gemm(in1, in1_cl, w1, in2=None, w2=None, bias=None, out_cl=True, stats=False):
+def _f32_param(w):
+    w = w.detach()
+    return w if w.dtype == torch.float32 else w.float()
+
+
+def pixel_gemm(in1, in1_cl, w1, in2=None, w2=None, bias=None, out_cl=True, stats=False, gate=None, gate_on_n=False):
     """out[b] = W1 . in1[b] (+ W2 . in2[b]) (+ bias) over the pixels of every image (csrc/pixel_gemm.cu).
 
-    in1: [B,P,K1] (in1_cl) or [B,K1,P] planes; w1: [N,K1] or per-image [B,N,K1]; in2: [B,P,K2] channels-last with
-    w2 [N,K2]; bias fp32 [N].  Returns out ([B,P,N] if out_cl else [B,N,P]) and, with stats=True, the per-CTA
-    (sum, sum of squares) partials [N, ctas, 2] of the stored output for lmnet_bn_act_fwd_stats."""
+    in1: [B,P,K1] (in1_cl) or [B,K1,P] planes; w1: fp32 [N,K1] with ANY strides (a `.t()` view is read in place); in2:
+    [B,P,K2] channels-last with w2 fp32 [N,K2]; bias fp32 [N]; gate: fp32 [B,K1] (or [B,N] with gate_on_n) multiplied into
+    W1 per image while the kernel stages it.  The kernel rounds the weights to the activation dtype itself, so no cast,
+    transpose or gate-multiply kernel runs around the call.  Returns out ([B,P,N] if out_cl else [B,N,P]) and, with
+    stats=True, the per-CTA (sum, sum of squares) partials [N, ctas, 2] of the stored output for lmnet_bn_act_fwd_stats."""
     B = in1.shape[0]
     P, K1 = (in1.shape[1], in1.shape[2]) if in1_cl else (in1.shape[2], in1.shape[1])
-    N = w1.shape[-2]
+    N = w1.shape[0]
     K2 = 0 if in2 is None else in2.shape[2]
     dt = in1.dtype
     dims = _pgemm_dims(B, P, N, K1, K2)
-    w1 = w1.to(dt).contiguous()
-    w2 = None if w2 is None else w2.to(dt).contiguous()
+    w1 = _f32_param(w1)
+    w2 = None if w2 is None else _f32_param(w2)
+    gate = None if gate is None else gate.detach().float().contiguous()
+    wts = L.PgemmWeights(w1.data_ptr(), w1.stride(0), w1.stride(1), None if gate is None else gate.data_ptr(), int(gate_on_n),
+                         None if w2 is None else w2.data_ptr(), 0 if w2 is None else w2.stride(0), 0 if w2 is None else w2.stride(1))
     bias = None if bias is None else bias.detach().float().contiguous()
     out = torch.empty((B, P, N) if out_cl else (B, N, P), dtype=dt, device=in1.device)
     part = None
     if stats:
         ctas = L.lib().lmnet_pixel_gemm_stats_ctas(L.byref(dims), int(in1_cl), int(out_cl))
         part = torch.empty(N, ctas, 2, dtype=torch.float32, device=in1.device)
-    rc = L.lib().lmnet_pixel_gemm(L.ptr(in1), int(in1_cl), L.ptr(w1), int(w1.dim() == 3), L.ptr(in2), L.ptr(w2),
-                                  L.ptr(bias), L.ptr(out), int(out_cl), L.ptr(part), L.byref(dims), L.dtype_code(in1),
-                                  L.stream_ptr())
+    rc = L.lib().lmnet_pixel_gemm(L.ptr(in1), int(in1_cl), L.ptr(in2), L.byref(wts), L.ptr(bias), L.ptr(out), int(out_cl),
+                                  L.ptr(part), L.byref(dims), L.dtype_code(in1), L.stream_ptr())
     L.check(rc, "pixel_gemm")
     return out, part
 
@@ -230,9 +242,9 @@ class _Expand1x1Cl(torch.autograd.Function):
                 dx = _as_cl(pixel_gemm(dyf, False, w.t(), out_cl=True)[0], H, Wd)
             else:
                 dx = _as_cl(torch.bmm(dyf.transpose(1, 2), w.to(x.dtype).unsqueeze(0).expand(B, M, K)), H, Wd)
-        dW, drow = _wgrad_cl(dyf, _pixels(x), None, False, True)
-        dw = dW.sum(0).to(w.dtype)
-        db = drow.sum(0).to(ctx.bias_dtype) if ctx.has_bias else None
+        dW, drow = _wgrad_cl(dyf, _pixels(x), None, False, True, batch_sum=True)
+        dw = dW.to(w.dtype)
+        db = drow.to(ctx.bias_dtype) if ctx.has_bias else None
         return dx, dw, db, None
 
 
@@ -246,29 +258,30 @@ class _PointwiseShortcutCl(torch.autograd.Function):
         Cin, Cout = x.shape[1], wpw.shape[0]
         P = H * Wd
         dt = z.dtype
-        wg = (wpw.float().unsqueeze(0) * gate.float().unsqueeze(1)).to(dt)            # [B, Cout, E]
         xp = _pixels(x)                                                                # [B, P, Cin]
         if pgemm_supported(B, P, Cout, E, Cin, False, True, False, dt):
-            out = pixel_gemm(z.view(B, E, P), False, wg, xp, wsc, bias, out_cl=True)[0]
+            out = pixel_gemm(z.view(B, E, P), False, wpw, xp, wsc, bias, out_cl=True, gate=gate)[0]   # W_b = Wpw * gate_b in-kernel
         else:
+            wg = (wpw.float().unsqueeze(0) * gate.float().unsqueeze(1)).to(dt)        # [B, Cout, E]
             out = torch.baddbmm(bias.to(dt).view(1, 1, Cout), xp, wsc.to(dt).t().unsqueeze(0).expand(B, Cin, Cout))
             out = torch.baddbmm(out, z.view(B, E, P).transpose(1, 2), wg.transpose(1, 2))  # [B, P, Cout]
-        ctx.save_for_backward(z, gate, x, wpw, wsc, wg)
+        ctx.save_for_backward(z, gate, x, wpw, wsc)
         ctx.bias_dtype = bias.dtype
         return _as_cl(out, H, Wd)
 
     @staticmethod
     @custom_bwd(device_type="cuda")
     def backward(ctx, dout):
-        z, gate, x, wpw, wsc, wg = ctx.saved_tensors
+        z, gate, x, wpw, wsc = ctx.saved_tensors
         B, E, H, Wd = z.shape
         Cin, Cout = x.shape[1], wpw.shape[0]
         P = H * Wd
         dt = z.dtype
         do = _pixels(dout.to(dt).contiguous(memory_format=torch.channels_last))        # [B, P, Cout]
         if pgemm_supported(B, P, E, Cout, 0, True, False, False, dt):
-            dz = pixel_gemm(do, True, wg.transpose(1, 2), out_cl=False)[0].view(B, E, H, Wd)
+            dz = pixel_gemm(do, True, wpw.t(), out_cl=False, gate=gate, gate_on_n=True)[0].view(B, E, H, Wd)
         else:
+            wg = (wpw.float().unsqueeze(0) * gate.float().unsqueeze(1)).to(dt)
             dz = torch.bmm(wg.transpose(1, 2), do.transpose(1, 2)).view(B, E, H, Wd)   # planes
         dx = None
         if ctx.needs_input_grad[2]:

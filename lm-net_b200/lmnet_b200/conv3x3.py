@@ -38,13 +38,15 @@ def wgrad_supported(B, H, W, Cin, Cout, stride, dtype) -> bool:
     return bool(L.lib().lmnet_conv3x3_wgrad_supported(L.byref(_dims(B, H, W, Cin, Cout, stride)), L._DTYPES[dtype]))
 
 
-def _launch_fwd(x, wp, bias, Cout, stride):
-    """x: logical [B,Cin,H,W] in channels-last memory; wp [9,Cout,Cin]; returns logical [B,Cout,Ho,Wo] channels-last."""
+def _launch_fwd(x, w, transposed, bias, Cout, stride):
+    """x: logical [B,Cin,H,W] in channels-last memory; w: the layer's fp32 weight, read in place by the kernel (transposed:
+    the stride-1 input gradient uses it flipped and transposed); returns logical [B,Cout,Ho,Wo] channels-last."""
     B, Cin, H, W = x.shape
     Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
     y = torch.empty((B, Cout, Ho, Wo), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
     dims = _dims(B, H, W, Cin, Cout, stride)
-    rc = L.lib().lmnet_conv3x3_fwd(L.ptr(x), L.ptr(wp), L.ptr(bias), L.ptr(y), L.byref(dims), L.dtype_code(x), L.stream_ptr())
+    rc = L.lib().lmnet_conv3x3_fwd(L.ptr(x), L.ptr(w), int(transposed), L.ptr(bias), L.ptr(y), L.byref(dims), L.dtype_code(x),
+                                   L.stream_ptr())
     L.check(rc, "conv3x3_fwd")
     return y
 
@@ -53,14 +55,18 @@ def _cl(t):
     return t.contiguous(memory_format=torch.channels_last)
 
 
+def _w32(w):
+    w = w.detach()
+    return w if (w.dtype == torch.float32 and w.is_contiguous()) else w.float().contiguous()
+
+
 class _Conv3x3(torch.autograd.Function):
     @staticmethod
     @custom_fwd(device_type="cuda")
     def forward(ctx, x, w, bias, stride):
         Cout, Cin = w.shape[0], w.shape[1]
-        wp = w.detach().permute(2, 3, 0, 1).reshape(9, Cout, Cin).to(x.dtype).contiguous()
         b32 = None if bias is None else bias.detach().float().contiguous()
-        y = _launch_fwd(x, wp, b32, Cout, stride)
+        y = _launch_fwd(x, _w32(w), False, b32, Cout, stride)
         ctx.save_for_backward(x, w)
         ctx.stride = stride
         ctx.bias_dtype = None if bias is None else bias.dtype
@@ -85,8 +91,7 @@ class _Conv3x3(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             Ho, Wo = dy.shape[2], dy.shape[3]
             if s == 1 and fwd_supported(B, Ho, Wo, Cout, Cin, 1, dt):
-                wpt = w.detach().flip(2, 3).permute(2, 3, 1, 0).reshape(9, Cin, Cout).to(dt).contiguous()
-                dx = _launch_fwd(dy, wpt, None, Cin, 1)
+                dx = _launch_fwd(dy, _w32(w), True, None, Cin, 1)
             else:
                 dx = aten_bwd([True, False, False])[0]
         if ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2]):

@@ -56,9 +56,9 @@ class _LinearPx(torch.autograd.Function):
             else:
                 dx = (do @ w.to(x.dtype)).view(x.shape)
         if wgrad_cl_supported(B, N, K, 0, P, True, True, x.dtype):
-            dW, drow = _wgrad_cl(do, xp, None, True, True)
-            dw = dW.sum(0).to(w.dtype)
-            db = drow.sum(0).to(ctx.bias_dtype) if ctx.has_bias else None
+            dW, drow = _wgrad_cl(do, xp, None, True, True, batch_sum=True)
+            dw = dW.to(w.dtype)
+            db = drow.to(ctx.bias_dtype) if ctx.has_bias else None
         else:
             dw = (do.reshape(-1, N).t() @ xp.reshape(-1, K)).to(w.dtype)
             db = do.reshape(-1, N).sum(0).to(ctx.bias_dtype) if ctx.has_bias else None

@@ -96,6 +96,10 @@ def test_raw_mixed_layout_wgrad_kernel_vs_einsum(shape):
     dW, drow = _wgrad_cl(dy.cuda(), x.cuda(), None, False, True)
     assert rel_err(dW.cpu(), torch.einsum("bmp,bpn->bmn", dy.double(), x.double())) < 1e-5
     assert rel_err(drow.cpu(), dy.double().sum(-1)) < 1e-5
+    dWs, drows = _wgrad_cl(dy.cuda(), x.cuda(), None, False, True, batch_sum=True)       # summed over the batch in the reduction
+    assert dWs.shape == (E, Cin) and drows.shape == (E,)
+    assert rel_err(dWs.cpu(), torch.einsum("bmp,bpn->mn", dy.double(), x.double())) < 1e-5
+    assert rel_err(drows.cpu(), dy.double().sum((0, 2))) < 1e-5
     # pointwise + shortcut: A channels-last, B1 planes, B2 channels-last
     assert wgrad_cl_supported(B, Cout, E, Cin, P, True, False, torch.bfloat16)
     dW, drow = _wgrad_cl(do.cuda(), z.cuda(), x.cuda(), True, False)
@@ -165,34 +169,38 @@ def test_raw_pixel_gemm_all_roles_vs_einsum(case):
         assert rel_err(got.float().cpu(), want) < 6e-3      # one bf16 rounding of the output (2^-9) + accumulation order
 
     x_cl, dy_pl, z_pl, do_cl = rnd(B, P, C), rnd(B, E, P), rnd(B, E, P), rnd(B, P, C)
-    w_ex, w_pw, w_sc = rnd(E, C), rnd(B, C, E), rnd(C, C)
+    # weights are fp32 parameters (read in place, rounded to bf16 by the kernel); the gate multiplies W_pw per image
+    w_ex, w_pw, w_sc = (torch.randn(*sh, generator=g) for sh in ((E, C), (C, E), (C, C)))
+    gate = torch.rand(B, E, generator=g)
     bias_e, bias_c = torch.randn(E, generator=g), torch.randn(C, generator=g)
+    w_ex_r, w_sc_r = w_ex.to(bf).double(), w_sc.to(bf).double()                       # what the kernel contracts with
+    w_pw_r = (w_pw.unsqueeze(0) * gate.unsqueeze(1)).to(bf).double()                  # [B, C, E]
     # expand forward: channels-last -> planes, with BatchNorm partial sums
     assert pgemm_supported(B, P, E, C, 0, True, False, True, bf)
     y, part = pixel_gemm(x_cl.cuda(), True, w_ex.cuda(), bias=bias_e.cuda(), out_cl=False, stats=True)
-    want = torch.einsum("nk,bpk->bnp", w_ex.double(), x_cl.double()) + bias_e.double().view(1, E, 1)
+    want = torch.einsum("nk,bpk->bnp", w_ex_r, x_cl.double()) + bias_e.double().view(1, E, 1)
     close(y, want)
     yd = y.double().cpu()
     tot = part.double().sum(1).cpu()
     assert rel_err(tot[:, 0], yd.sum((0, 2))) < 1e-5 and rel_err(tot[:, 1], (yd * yd).sum((0, 2))) < 1e-5
-    # expand input gradient: planes -> channels-last
+    # expand input gradient: planes -> channels-last (the weight is read through a transposed view)
     if pgemm_supported(B, P, C, E, 0, False, True, False, bf):
-        dx, _ = pixel_gemm(dy_pl.cuda(), False, w_ex.t().cuda(), out_cl=True)
-        close(dx, torch.einsum("nk,bnp->bpk", w_ex.double(), dy_pl.double()))
-    # pointwise (per-image weights, planes) + shortcut (channels-last) -> channels-last
+        dx, _ = pixel_gemm(dy_pl.cuda(), False, w_ex.cuda().t(), out_cl=True)
+        close(dx, torch.einsum("nk,bnp->bpk", w_ex_r, dy_pl.double()))
+    # pointwise (gated weights, planes) + shortcut (channels-last) -> channels-last
     if pgemm_supported(B, P, C, E, C, False, True, False, bf):
-        o, _ = pixel_gemm(z_pl.cuda(), False, w_pw.cuda(), x_cl.cuda(), w_sc.cuda(), bias_c.cuda(), out_cl=True)
-        want = (torch.einsum("bne,bep->bpn", w_pw.double(), z_pl.double()) +
-                torch.einsum("nk,bpk->bpn", w_sc.double(), x_cl.double()) + bias_c.double().view(1, 1, C))
+        o, _ = pixel_gemm(z_pl.cuda(), False, w_pw.cuda(), x_cl.cuda(), w_sc.cuda(), bias_c.cuda(), out_cl=True, gate=gate.cuda())
+        want = (torch.einsum("bne,bep->bpn", w_pw_r, z_pl.double()) +
+                torch.einsum("nk,bpk->bpn", w_sc_r, x_cl.double()) + bias_c.double().view(1, 1, C))
         close(o, want)
-    # pointwise input gradient: channels-last, per-image weights -> planes
+    # pointwise input gradient: channels-last, gated weights (gate indexed by the OUTPUT channel) -> planes
     assert pgemm_supported(B, P, E, C, 0, True, False, False, bf)
-    dz, _ = pixel_gemm(do_cl.cuda(), True, w_pw.transpose(1, 2).cuda(), out_cl=False)
-    close(dz, torch.einsum("bne,bpn->bep", w_pw.double(), do_cl.double()))
+    dz, _ = pixel_gemm(do_cl.cuda(), True, w_pw.cuda().t(), out_cl=False, gate=gate.cuda(), gate_on_n=True)
+    close(dz, torch.einsum("bne,bpn->bep", w_pw_r, do_cl.double()))
     # shortcut input gradient: channels-last -> channels-last
     assert pgemm_supported(B, P, C, C, 0, True, True, False, bf)
-    dxs, _ = pixel_gemm(do_cl.cuda(), True, w_sc.t().cuda(), out_cl=True)
-    close(dxs, torch.einsum("nk,bpn->bpk", w_sc.double(), do_cl.double()))
+    dxs, _ = pixel_gemm(do_cl.cuda(), True, w_sc.cuda().t(), out_cl=True)
+    close(dxs, torch.einsum("nk,bpn->bpk", w_sc_r, do_cl.double()))
 
 
 def test_expand_bn_hardswish_with_epilogue_statistics_matches_separate_statistics_pass():
