@@ -283,6 +283,27 @@ int lmnet_bn_act_fwd_stats(const void* y, const float* stats_part, int nchunks, 
                            float* save_mean, float* save_rstd, float eps, float momentum, int act,
                            void* workspace, size_t workspace_bytes, const lmnet_bn_dims* dims, int dtype, void* stream);
 
+/* ---- squeeze-excite gate (row a7) -------------------------------------------------------------------------
+ * Replaces scale_activation(fc2(activation(fc1(pooled)))) of SE.forward (/root/reference/core/modules.py:1030-1036):
+ * gate[b][e] = hardsigmoid(b2[e] + sum_r W2[e][r] * relu(b1[r] + sum_e' W1[r][e'] * pool[b][e'])), everything fp32.
+ * W1 [R][E], W2 [E][R] are the 1x1 convolution weights; h1 [B][R] / pre2 [B][E] (pre-activations) are saved for the
+ * backward (NULL at inference).  bwd: dpool [B][E], dW1, db1, dW2, db2 from dgate [B][E]; fixed-order sums. */
+int lmnet_se_gate_supported(int B, int E, int R);
+int lmnet_se_gate_fwd(const float* pool, const float* W1, const float* b1, const float* W2, const float* b2, float* gate,
+                      float* h1, float* pre2, int B, int E, int R, void* stream);
+int lmnet_se_gate_bwd(const float* dgate, const float* pool, const float* h1, const float* pre2, const float* W1,
+                      const float* W2, float* dpool, float* dW1, float* db1, float* dW2, float* db2, int B, int E, int R,
+                      void* stream);
+
+/* ---- average pooling by an integer factor, channels-last (widening step f3) --------------------------------
+ * Replaces the nn.AdaptiveAvgPool2d calls of PyramidPool (/root/reference/core/modules.py:454-498) when the input size is
+ * an exact multiple of the output size.  x / dx: [B, Ho*factor, Wo*factor, C], y / dy: [B, Ho, Wo, C]; 16-bit; C % 4 == 0. */
+typedef struct lmnet_pool_dims {
+    int32_t B, Ho, Wo, C, factor;
+} lmnet_pool_dims;
+int lmnet_avgpool_cl_fwd(const void* x, void* y, const lmnet_pool_dims* dims, int dtype, void* stream);
+int lmnet_avgpool_cl_bwd(const void* dy, void* dx, const lmnet_pool_dims* dims, int dtype, void* stream);
+
 /* ---- dense 3x3 convolution, padding 1, stride 1 or 2, channels-last (widening step f3) ---------------------
  * Replaces the nn.Conv2d(.., 3, stride, 1) layers of LM-Net outside ReparamConv: down1-4 / up1-4
  * (/root/reference/core/LM_Net.py:14-39, 58-74), M2Skip / M3Skip (/root/reference/core/modules.py:83-143) and the

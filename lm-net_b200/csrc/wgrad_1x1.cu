@@ -499,8 +499,11 @@ static bool wg_cl_plan(const lmnet_wgrad_dims* d, bool a_cl, bool b1_cl, WgClPla
     g.NT1 = (d->N1 + (d->N2 > 0 ? 0 : 1) + 7) / 8;
     g.NT2 = d->N2 > 0 ? (d->N2 + 1 + 7) / 8 : 0;
     pl.MT = (d->M + 15) / 16;
+    if (pl.MT == 4 || pl.MT == 5) pl.MT = 6;                           // instantiated: 1, 2, 3, 6, 12 (padding rows are zero)
+    if (pl.MT > 6 && pl.MT < 12) pl.MT = 12;
     const int NT = g.NT1 + g.NT2;
     pl.NTW = (NT + kWgWarps - 1) / kWgWarps;
+    if (pl.NTW == 4) pl.NTW = 5;
     const bool mt_ok = pl.MT == 1 || pl.MT == 2 || pl.MT == 3 || pl.MT == 6 || pl.MT == 12;
     const bool nt_ok = pl.NTW == 1 || pl.NTW == 2 || pl.NTW == 3 || pl.NTW == 5;
     if (!mt_ok || !nt_ok || pl.MT * pl.NTW > 30) return false;

@@ -71,6 +71,10 @@ class PgemmWeights(Structure):
                 ("w2", c_void_p), ("w2_sn", c_int64), ("w2_sk", c_int64)]
 
 
+class PoolDims(Structure):
+    _fields_ = [("B", c_int32), ("Ho", c_int32), ("Wo", c_int32), ("C", c_int32), ("factor", c_int32)]
+
+
 class Conv3x3Dims(Structure):
     _fields_ = [("B", c_int32), ("H", c_int32), ("W", c_int32), ("Cin", c_int32), ("Cout", c_int32), ("stride", c_int32)]
 
@@ -152,6 +156,11 @@ def lib():
     L.lmnet_conv3x3_wgrad_workspace_bytes.restype = c_size_t
     L.lmnet_conv3x3_wgrad_workspace_bytes.argtypes = [pcv]
     L.lmnet_conv3x3_wgrad.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, pcv, c_int, c_void_p]
+    L.lmnet_avgpool_cl_fwd.argtypes = [c_void_p, c_void_p, POINTER(PoolDims), c_int, c_void_p]
+    L.lmnet_avgpool_cl_bwd.argtypes = [c_void_p, c_void_p, POINTER(PoolDims), c_int, c_void_p]
+    L.lmnet_se_gate_supported.argtypes = [c_int, c_int, c_int]
+    L.lmnet_se_gate_fwd.argtypes = [c_void_p] * 8 + [c_int, c_int, c_int, c_void_p]
+    L.lmnet_se_gate_bwd.argtypes = [c_void_p] * 11 + [c_int, c_int, c_int, c_void_p]
     pud = POINTER(UpsampleDims)
     L.lmnet_upsample2x_fwd.argtypes = [c_void_p, c_void_p, pud, c_int, c_void_p]
     L.lmnet_upsample2x_bwd.argtypes = [c_void_p, c_void_p, pud, c_int, c_void_p]
@@ -266,4 +275,4 @@ def dw_grads(dw, dgamma, dbeta) -> DwGrads:
 
 
 __all__ = ["lib", "check", "dtype_code", "require_cuda", "stream_ptr", "ptr", "view5", "na_dims", "dw_params",
-           "dw_grads", "View5", "NADims", "DwParams", "DwGrads", "DwDims", "BnDims", "ACT_CODES", "WgradDims", "PgemmDims", "PgemmWeights", "Conv3x3Dims", "UpsampleDims", "UpsampleClDims", "byref", "launch_count", "LIB_PATH"]
+           "dw_grads", "View5", "NADims", "DwParams", "DwGrads", "DwDims", "BnDims", "ACT_CODES", "WgradDims", "PgemmDims", "PgemmWeights", "PoolDims", "Conv3x3Dims", "UpsampleDims", "UpsampleClDims", "byref", "launch_count", "LIB_PATH"]

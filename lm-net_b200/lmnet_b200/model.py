@@ -25,7 +25,7 @@ from torch import nn
 from natten import NeighborhoodAttention2D
 
 from .conv3x3 import Conv3x3
-from .patch import _cl, _m2skip_forward, _m3skip_forward, _natt_forward
+from .patch import _cl, _m2skip_forward, _m3skip_forward, _natt_forward, _pyramidpool_forward
 from .reparam import reparam_forward
 from .upsample import Upsample2x
 
@@ -234,9 +234,7 @@ class GFT(nn.Module):
 class PyramidPool(nn.Module):
     """Average-pools x1..x4 to the resolution of x5 and stacks everything (reference: core/modules.py:454-498)."""
 
-    def forward(self, x1, x2, x3, x4, x5):
-        size = x5.shape[-2:]
-        return torch.cat([F.adaptive_avg_pool2d(t, size) for t in (x1, x2, x3, x4)] + [x5], dim=1)
+    forward = _pyramidpool_forward
 
 
 class LM_Net(nn.Module):

@@ -10,6 +10,7 @@ What is swapped (constructors, sub-module names and therefore checkpoints stay u
   ReparamConv.forward            core/modules.py:586-600   -> lmnet_b200.reparam.reparam_forward
   NeighborhoodTransformer.forward core/modules.py:514-521  -> fused LayerNorm + channels-last patch embedding
   M3Skip.forward / M2Skip.forward core/modules.py:101-107, 138-143 -> fused BatchNorm+GELU, channels-last 3x3 convs
+  PyramidPool.forward            core/modules.py:481-498   -> integer-factor channels-last average pooling kernel
   nn.Upsample(scale_factor=2, bilinear, align_corners=True) instances -> lmnet_b200.upsample.Upsample2x
   nn.Conv2d(.., 3, stride 1|2, padding 1) instances -> lmnet_b200.conv3x3.Conv3x3 (same parameters / state_dict keys)
 NeighborhoodAttention2D itself comes from the drop-in `natten` package.
@@ -22,6 +23,7 @@ from .bnact import conv_bn_act
 from .conv3x3 import convert_conv3x3
 from .layernorm import layer_norm
 from .linear import linear
+from .pool import adaptive_avg_pool
 from .reparam import patch_reparam_conv
 from .upsample import Upsample2x
 
@@ -55,11 +57,20 @@ def _m2skip_forward(self, xl, xs):
     return conv_bn_act(self.fuse_conv, torch.cat([self.convl(_cl(xl)), xs], dim=1))
 
 
+def _pyramidpool_forward(self, x1, x2, x3, x4, x5):
+    """PyramidPool.forward (core/modules.py:481-498): pool the four encoder outputs to x5's size and stack."""
+    size = x5.shape[-2:]
+    return torch.cat([adaptive_avg_pool(t, size) for t in (x1, x2, x3, x4)] + [x5], dim=1)
+
+
 def patch_reference_modules(mods) -> dict:
     """`mods` is the reference's imported `core.modules`.  Returns the original forwards (to undo)."""
     originals = {"ReparamConv": patch_reparam_conv(mods.ReparamConv)}
-    for name, fwd in (("NeighborhoodTransformer", _natt_forward), ("M3Skip", _m3skip_forward), ("M2Skip", _m2skip_forward)):
-        cls = getattr(mods, name)
+    for name, fwd in (("NeighborhoodTransformer", _natt_forward), ("M3Skip", _m3skip_forward), ("M2Skip", _m2skip_forward),
+                      ("PyramidPool", _pyramidpool_forward)):
+        cls = getattr(mods, name, None)
+        if cls is None:
+            continue
         originals[name] = cls.forward
         cls.forward = fwd
     return originals

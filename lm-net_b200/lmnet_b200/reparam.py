@@ -23,6 +23,7 @@ from torch.amp import custom_bwd, custom_fwd
 from . import _lib as L
 from .bnact import bn_act, conv_bn_act
 from .conv1x1 import _compute_dtype, expand_1x1, is_channels_last, pointwise_shortcut, to_channels_last
+from .se import se_gate
 
 
 def _dims(x):
@@ -229,12 +230,12 @@ def reparam_forward(self, x):
         z, pool = fused_dw_bn_gelu(self, x1)
     se = self.se
     B, E = pool.shape
-    gate = se.scale_activation(se.fc2(se.activation(se.fc1(pool.to(z.dtype).view(B, E, 1, 1)))))
+    gate = se_gate(se, pool) if pool.is_cuda else se.scale_activation(se.fc2(se.activation(se.fc1(pool.to(z.dtype).view(B, E, 1, 1)))))
     if len(self.pointwise_conv) == 1 and len(self.shortcut) == 1 and _is_1x1(self.pointwise_conv[0]) \
             and _is_1x1(self.shortcut[0]):
         # pointwise(gate * z) + shortcut(x): two accumulating plane-wise GEMMs, the SE multiply rides in the weights
         return pointwise_shortcut(self.pointwise_conv[0], self.shortcut[0], z, gate, x)
-    return self.pointwise_conv(gate * z) + self.shortcut(x)
+    return self.pointwise_conv(gate.reshape(B, E, 1, 1).to(z.dtype) * z) + self.shortcut(x)
 
 
 def patch_reparam_conv(cls):
