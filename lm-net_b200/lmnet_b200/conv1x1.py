@@ -344,7 +344,7 @@ def expand_1x1(conv: torch.nn.Conv2d, x: torch.Tensor, want_stats: bool = False)
 
 
 def pointwise_shortcut(pw: torch.nn.Conv2d, sc: torch.nn.Conv2d, z, gate, x):
-    """pw(gate * z) + sc(x) with gate [B,E,1,1] on CUDA tensors (module calls for uncovered shapes)."""
+    """pw(gate * z) + sc(x) with gate [B,E] or [B,E,1,1] on CUDA tensors (module calls for uncovered shapes)."""
     L.require_cuda(z, x)
     dt = _compute_dtype(z)
     B, E, H, W = z.shape
@@ -361,4 +361,4 @@ def pointwise_shortcut(pw: torch.nn.Conv2d, sc: torch.nn.Conv2d, z, gate, x):
         bias = pw.bias + sc.bias
         return _PointwiseShortcut.apply(z.to(dt).contiguous(), gate.reshape(B, E), x.to(dt).contiguous(),
                                         pw.weight.view(Cout, E), sc.weight.view(Cout, Cin), bias)
-    return pw(gate * z) + sc(x)
+    return pw(gate.reshape(B, E, 1, 1).to(z.dtype) * z) + sc(x)
