@@ -246,28 +246,38 @@ conv3x3_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ dy, float* _
     }
 }
 
-// dW[co][ci][ky][kx] = sum_cta part[cta][tap][co][ci] (fixed order); db[co] = sum_cta part_b[cta][co]
-__global__ void conv3x3_wgrad_reduce_kernel(const float* __restrict__ part, const float* __restrict__ part_b, float* __restrict__ dW,
-                                            float* __restrict__ db, int ncta, int Cout, int Cin, int Mp, int ldn) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+// dW[co][ci][ky][kx] = sum_cta part[cta][tap][co][ci];  db[co] = sum_cta part_b[cta][co].  64 outputs per block, four
+// threads per output each summing every fourth partial, combined in a fixed order (deterministic)
+__global__ void __launch_bounds__(256)
+conv3x3_wgrad_reduce_kernel(const float* __restrict__ part, const float* __restrict__ part_b, float* __restrict__ dW,
+                            float* __restrict__ db, int ncta, int Cout, int Cin, int Mp, int ldn) {
+    __shared__ float s_red[4][64];
+    const int o = threadIdx.x & 63, lane = threadIdx.x >> 6;
+    const int i = blockIdx.x * 64 + o;
     const int nW = 9 * Cout * Cin;
+    float s = 0.f;
+    int tap = 0, co = 0, ci = 0;
     if (i < nW) {
-        const int tap = i / (Cout * Cin), rem = i - tap * Cout * Cin;
-        const int co = rem / Cin, ci = rem - co * Cin;
+        tap = i / (Cout * Cin);
+        const int rem = i - tap * Cout * Cin;
+        co = rem / Cin;
+        ci = rem - co * Cin;
         const float* p = part + ((int64_t)tap * Mp + co) * ldn + ci;
         const int64_t stride = (int64_t)9 * Mp * ldn;
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-        int c = 0;
-        for (; c + 4 <= ncta; c += 4) {
-            s0 += p[(c + 0) * stride]; s1 += p[(c + 1) * stride]; s2 += p[(c + 2) * stride]; s3 += p[(c + 3) * stride];
-        }
-        for (; c < ncta; ++c) s0 += p[c * stride];
-        dW[((int64_t)co * Cin + ci) * 9 + tap] = (s0 + s1) + (s2 + s3);
+        float s0 = 0.f, s1 = 0.f;
+        int c = lane;
+        for (; c + 4 < ncta; c += 8) { s0 += p[c * stride]; s1 += p[(c + 4) * stride]; }
+        if (c < ncta) s0 += p[c * stride];
+        s = s0 + s1;
     } else if (i < nW + Cout && db != nullptr) {
-        const int co = i - nW;
-        float s = 0.f;
-        for (int c = 0; c < ncta; ++c) s += part_b[(int64_t)c * Mp + co];
-        db[co] = s;
+        for (int c = lane; c < ncta; c += 4) s += part_b[(int64_t)c * Mp + (i - nW)];
+    }
+    s_red[lane][o] = s;
+    __syncthreads();
+    if (lane == 0) {
+        const float t = (s_red[0][o] + s_red[1][o]) + (s_red[2][o] + s_red[3][o]);
+        if (i < nW) dW[((int64_t)co * Cin + ci) * 9 + tap] = t;
+        else if (i < nW + Cout && db != nullptr) db[i - nW] = t;
     }
 }
 
@@ -468,7 +478,7 @@ extern "C" int lmnet_conv3x3_wgrad(const void* x, const void* dy, float* dW, flo
         float* fpart_b = fpart + (size_t)grid * 9 * mp * ldn;
         const int frc = cv_fast_wgrad(x, dy, fpart, fpart_b, d, dtype, st);
         if (frc != LMNET_OK) return frc;
-        LMNET_LAUNCH(KID_CONV3X3_REDUCE, st, 0, (conv3x3_wgrad_reduce_kernel<<<(n_out + 127) / 128, 128, 0, st>>>(
+        LMNET_LAUNCH(KID_CONV3X3_REDUCE, st, 0, (conv3x3_wgrad_reduce_kernel<<<(n_out + 63) / 64, 256, 0, st>>>(
             fpart, fpart_b, dW, dbias, grid, d->Cout, d->Cin, mp, ldn)));
         return LMNET_OK;
     }
@@ -480,7 +490,7 @@ extern "C" int lmnet_conv3x3_wgrad(const void* x, const void* dy, float* dW, flo
                                  : cv_wg_dispatch<__half>(x, dy, part, part_b, pl, st);
     if (rc != LMNET_OK) return rc;
     const int n = 9 * d->Cout * d->Cin + d->Cout;
-    LMNET_LAUNCH(KID_CONV3X3_REDUCE, st, 0, (conv3x3_wgrad_reduce_kernel<<<(n + 127) / 128, 128, 0, st>>>(
+    LMNET_LAUNCH(KID_CONV3X3_REDUCE, st, 0, (conv3x3_wgrad_reduce_kernel<<<(n + 63) / 64, 256, 0, st>>>(
         part, part_b, dW, dbias, pl.grid, d->Cout, d->Cin, pl.MT * 16, pl.NTC * 8)));
     return LMNET_OK;
 }

@@ -44,8 +44,11 @@ se_gate_fwd_kernel(const float* __restrict__ pool, const float* __restrict__ W1,
     }
 }
 
-// one CTA: dpool, dW1, db1, dW2, db2 from dgate (B <= 64 images)
-__global__ void __launch_bounds__(1024)
+// dpool, dW1, db1, dW2, db2 from dgate (B <= 64 images).  kSeBwdCtas CTAs: each recomputes the two small intermediate
+// tables (d pre2, d h1 — B x E and B x R numbers) in shared memory and then owns a slice of every output; all sums run in
+// a fixed order.
+constexpr int kSeBwdCtas = 16;
+__global__ void __launch_bounds__(kSeThreads)
 se_gate_bwd_kernel(const float* __restrict__ dgate, const float* __restrict__ pool, const float* __restrict__ h1,
                    const float* __restrict__ pre2, const float* __restrict__ W1, const float* __restrict__ W2,
                    float* __restrict__ dpool, float* __restrict__ dW1, float* __restrict__ db1, float* __restrict__ dW2,
@@ -55,7 +58,9 @@ se_gate_bwd_kernel(const float* __restrict__ dgate, const float* __restrict__ po
     float* s_a = s_d2 + B * E;        // [B][R] relu(h1)
     float* s_dh = s_a + B * R;        // [B][R] d h1
     float* s_pool = s_dh + B * R;     // [B][E]
-    const int tid = threadIdx.x, nthr = blockDim.x;
+    float* s_w2 = s_pool + B * E;     // [E][R] (coalesced copy: the d h1 loop walks W2 with stride R)
+    const int tid = threadIdx.x, nthr = blockDim.x, cta = blockIdx.x, ncta = gridDim.x;
+    for (int i = tid; i < E * R; i += nthr) s_w2[i] = __ldg(W2 + i);
     for (int i = tid; i < B * E; i += nthr) {
         const float p = pre2[i];
         s_d2[i] = (p > -3.f && p < 3.f) ? dgate[i] * (1.f / 6.f) : 0.f;
@@ -63,43 +68,53 @@ se_gate_bwd_kernel(const float* __restrict__ dgate, const float* __restrict__ po
     }
     for (int i = tid; i < B * R; i += nthr) s_a[i] = fmaxf(h1[i], 0.f);
     __syncthreads();
-    // d h1[b][r] = (h1 > 0) * sum_e d2[b][e] W2[e][r]
+    // d h1[b][r] = (h1 > 0) * sum_e d2[b][e] W2[e][r]   (every CTA needs the whole table)
     for (int i = tid; i < B * R; i += nthr) {
         const int b = i / R, r = i - b * R;
         float a = 0.f;
-        for (int e = 0; e < E; ++e) a = fmaf(s_d2[b * E + e], __ldg(W2 + (int64_t)e * R + r), a);
+        for (int e = 0; e < E; ++e) a = fmaf(s_d2[b * E + e], s_w2[e * R + r], a);
         s_dh[i] = h1[i] > 0.f ? a : 0.f;
     }
-    // dW2[e][r] = sum_b d2[b][e] relu(h1[b][r]);  db2[e] = sum_b d2[b][e]
-    for (int i = tid; i < E * R; i += nthr) {
+    __syncthreads();
+    // this CTA's slice of the outputs (element index i with i % ncta == cta would scatter; use contiguous chunks)
+    auto chunk = [&](int n, int& lo, int& hi) {
+        const int per = (n + ncta - 1) / ncta;
+        lo = min(n, cta * per);
+        hi = min(n, lo + per);
+    };
+    int lo, hi;
+    chunk(E * R, lo, hi);             // dW2[e][r] = sum_b d2[b][e] relu(h1[b][r])
+    for (int i = lo + tid; i < hi; i += nthr) {
         const int e = i / R, r = i - e * R;
         float a = 0.f;
         for (int b = 0; b < B; ++b) a = fmaf(s_d2[b * E + e], s_a[b * R + r], a);
         dW2[i] = a;
     }
-    for (int e = tid; e < E; e += nthr) {
-        float a = 0.f;
-        for (int b = 0; b < B; ++b) a += s_d2[b * E + e];
-        if (db2 != nullptr) db2[e] = a;
-    }
-    __syncthreads();
-    // dW1[r][e] = sum_b dh[b][r] pool[b][e];  db1[r] = sum_b dh[b][r];  dpool[b][e] = sum_r dh[b][r] W1[r][e]
-    for (int i = tid; i < R * E; i += nthr) {
+    chunk(R * E, lo, hi);             // dW1[r][e] = sum_b dh[b][r] pool[b][e]
+    for (int i = lo + tid; i < hi; i += nthr) {
         const int r = i / E, e = i - r * E;
         float a = 0.f;
         for (int b = 0; b < B; ++b) a = fmaf(s_dh[b * R + r], s_pool[b * E + e], a);
         dW1[i] = a;
     }
-    for (int r = tid; r < R; r += nthr) {
-        float a = 0.f;
-        for (int b = 0; b < B; ++b) a += s_dh[b * R + r];
-        if (db1 != nullptr) db1[r] = a;
-    }
-    for (int i = tid; i < B * E; i += nthr) {
+    chunk(B * E, lo, hi);             // dpool[b][e] = sum_r dh[b][r] W1[r][e]
+    for (int i = lo + tid; i < hi; i += nthr) {
         const int b = i / E, e = i - b * E;
         float a = 0.f;
         for (int r = 0; r < R; ++r) a = fmaf(s_dh[b * R + r], __ldg(W1 + (int64_t)r * E + e), a);
         dpool[i] = a;
+    }
+    chunk(E, lo, hi);                 // db2[e] = sum_b d2[b][e]
+    for (int e = lo + tid; e < hi; e += nthr) {
+        float a = 0.f;
+        for (int b = 0; b < B; ++b) a += s_d2[b * E + e];
+        if (db2 != nullptr) db2[e] = a;
+    }
+    chunk(R, lo, hi);                 // db1[r] = sum_b dh[b][r]
+    for (int r = lo + tid; r < hi; r += nthr) {
+        float a = 0.f;
+        for (int b = 0; b < B; ++b) a += s_dh[b * R + r];
+        if (db1 != nullptr) db1[r] = a;
     }
 }
 
@@ -111,7 +126,7 @@ static bool se_ok(int B, int E, int R) { return B > 0 && E > 0 && R > 0 && B <= 
 
 extern "C" int lmnet_se_gate_supported(int B, int E, int R) {
     if (!se_ok(B, E, R)) return 0;
-    return (size_t)(2 * B * E + 2 * B * R) * sizeof(float) <= 200 * 1024 ? 1 : 0;
+    return (size_t)(2 * B * E + 2 * B * R + E * R) * sizeof(float) <= 200 * 1024 ? 1 : 0;
 }
 
 extern "C" int lmnet_se_gate_fwd(const float* pool, const float* W1, const float* b1, const float* W2, const float* b2,
@@ -130,10 +145,10 @@ extern "C" int lmnet_se_gate_bwd(const float* dgate, const float* pool, const fl
     if (!lmnet_se_gate_supported(B, E, R)) return LMNET_ERR_UNSUPPORTED;
     if (!dgate || !pool || !h1 || !pre2 || !W1 || !W2 || !dpool || !dW1 || !dW2) return LMNET_ERR_INVALID_ARG;
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t smem = (size_t)(2 * B * E + 2 * B * R) * sizeof(float);
+    const size_t smem = (size_t)(2 * B * E + 2 * B * R + E * R) * sizeof(float);
     static std::atomic<size_t> granted[kMaxDevices];
     if (!ensure_smem(se_gate_bwd_kernel, smem, granted)) return LMNET_ERR_LAUNCH;
-    LMNET_LAUNCH(KID_SE_GATE_BWD, st, 0, (se_gate_bwd_kernel<<<1, 1024, smem, st>>>(dgate, pool, h1, pre2, W1, W2, dpool, dW1, db1, dW2,
+    LMNET_LAUNCH(KID_SE_GATE_BWD, st, 0, (se_gate_bwd_kernel<<<kSeBwdCtas, kSeThreads, smem, st>>>(dgate, pool, h1, pre2, W1, W2, dpool, dW1, db1, dW2,
                                                                                   db2, B, E, R)));
     return LMNET_OK;
 }

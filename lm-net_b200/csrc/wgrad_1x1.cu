@@ -201,19 +201,27 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part, float* __res
 __global__ void __launch_bounds__(256)
 wgrad_reduce_bsum_kernel(const float* __restrict__ part, float* __restrict__ dW, float* __restrict__ drow,
                          int B, int splits, int M, int Ntot, int ldn, int N1, int n2_off, int ones_col) {
-    // one warp per output element: lanes stride over the B * splits partials, then a fixed-order butterfly
-    const int idx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (idx >= M * (Ntot + 1)) return;
-    const int n = idx % (Ntot + 1), m = idx / (Ntot + 1);
-    const int col = n < N1 ? n : n < Ntot ? n2_off + (n - N1) : ones_col;
+    // one block per output row m; threads = (column of the partial, partial lane): adjacent threads read adjacent columns
+    // (coalesced), every lane sums its share of the B * splits partials, lanes are combined in a fixed order
+    extern __shared__ float s_red[];                      // [G][ldn]
+    const int m = blockIdx.x;
+    const int G = blockDim.x / ldn;
+    const int col = threadIdx.x % ldn, g = threadIdx.x / ldn;
     const int total = B * splits;
-    const float* p = part + (int64_t)m * ldn + col;
-    const int64_t stride = (int64_t)M * ldn;
-    float a = 0.f;
-    for (int s = lane; s < total; s += 32) a += p[s * stride];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-    if (lane == 0) {
+    if (g < G) {
+        const float* p = part + (int64_t)m * ldn + col;
+        const int64_t stride = (int64_t)M * ldn;
+        float a0 = 0.f, a1 = 0.f;
+        int s = g;
+        for (; s + G < total; s += 2 * G) { a0 += p[s * stride]; a1 += p[(s + G) * stride]; }
+        if (s < total) a0 += p[s * stride];
+        s_red[g * ldn + col] = a0 + a1;
+    }
+    __syncthreads();
+    for (int n = threadIdx.x; n <= Ntot; n += blockDim.x) {
+        const int c = n < N1 ? n : n < Ntot ? n2_off + (n - N1) : ones_col;
+        float a = 0.f;
+        for (int k = 0; k < G; ++k) a += s_red[k * ldn + c];
         if (n < Ntot) dW[(int64_t)m * Ntot + n] = a;
         else if (drow != nullptr) drow[m] = a;
     }
@@ -685,7 +693,10 @@ static int wgrad_1x1_cl_impl(const void* A, const void* B1, const void* B2, floa
     if (rc != LMNET_OK) return rc;
     if (batch_sum) {
         const int n_out = d->M * (Ntot + 1);
-        LMNET_LAUNCH(KID_WGRAD_REDUCE, st, 0, (wgrad_reduce_bsum_kernel<<<(n_out + 7) / 8, 256, 0, st>>>(
+        const int threads = ldn <= 256 ? 256 : ((ldn + 31) / 32) * 32;
+        const size_t red_smem = (size_t)(threads / ldn) * ldn * sizeof(float);
+        (void)n_out;
+        LMNET_LAUNCH(KID_WGRAD_REDUCE, st, 0, (wgrad_reduce_bsum_kernel<<<d->M, threads, red_smem, st>>>(
             part, dW, drow, d->B, splits, d->M, Ntot, ldn, d->N1, n2_off, ones_col)));
         return LMNET_OK;
     }

@@ -1,18 +1,25 @@
 #!/bin/bash
-# Round-end evidence run (one gpurun call): bench (own arm + reference arm), ncu launch list of the bench step,
-# ncu --set full of the NA streaming kernels, na2d micro-benchmark + high-res inference, torch-profiler step profile.
+# Round-end evidence run (one gpurun call, one GPU): bench (own arm + reference arm + the other BASELINE configs), ncu launch
+# list of exactly the timed bench step (-> profiles/rNN_launches_bench.txt + source-stamped rNN_traffic.json), ncu --set full
+# of the hot kernels exported to CSV ON THE BOX (the .ncu-rep files are ~9 MB per kernel and never travel), step profile.
+R=${1:-r02}
 mkdir -p gpurun_out
-timeout 500 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err
-python tools/summarize_bench.py gpurun_out/bench_final.json
-timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
-head -c 400 gpurun_out/bench_ref.json; echo
-LMNET_NCU_RANGE=1 timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum \
-  --clock-control none --csv --log-file gpurun_out/launches_final.csv \
-  python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-profile --no-graph > gpurun_out/launches_final.log 2>&1
-wc -l gpurun_out/launches_final.csv
-for lvl in 1 4; do
-  timeout 200 ncu --set full --import-source on --clock-control none -k regex:na2d_stream -c 2 -o gpurun_out/ncu_na_stream_final_l$lvl \
-    python tools/run_block.py --unit na --level $lvl --iters 1 > gpurun_out/ncu_na_final_l$lvl.log 2>&1
+timeout 500 python bench.py --steps 20 --warmup 5 > gpurun_out/${R}_bench_final.json 2> gpurun_out/${R}_bench_final.err
+python tools/summarize_bench.py gpurun_out/${R}_bench_final.json | head -30
+timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${R}_bench_ref.json 2> gpurun_out/${R}_bench_ref.err
+head -c 300 gpurun_out/${R}_bench_ref.json; echo
+timeout 300 python bench.py --workload cfg1 --steps 3 --warmup 1 > gpurun_out/${R}_bench_cfg1.json 2> /dev/null
+timeout 300 python bench.py --workload na2d --steps 10 --warmup 3 > gpurun_out/${R}_bench_na2d.json 2> /dev/null
+timeout 300 python bench.py --workload infer1024 --steps 10 --warmup 3 > gpurun_out/${R}_bench_infer1024.json 2> /dev/null
+LMNET_NCU_RANGE=1 timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum \
+  --clock-control none --csv --log-file /tmp/launches.csv \
+  python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-profile --no-graph > gpurun_out/${R}_launches.log 2>&1
+python tools/launch_list_summary.py /tmp/launches.csv gpurun_out/${R}_launches_bench.txt gpurun_out/${R}_traffic.json | head -5
+for spec in "reparam 1 dw_|pixel_gemm|wgrad|bnact|se_gate 26" "reparam 3 dw_bwd_dx|dw_apply 4" "conv 1 conv3x3 4" "natt 1 na2d_stream|ln_|pixel_gemm 12"; do
+  set -- $spec
+  timeout 600 ncu --set full --clock-control none -k regex:"$3" -c $4 -o /tmp/ncu_$1_l$2 python tools/run_block.py --unit $1 --level $2 --iters 1 > gpurun_out/${R}_ncu_$1_l$2.log 2>&1
+  ncu -i /tmp/ncu_$1_l$2.ncu-rep --page raw --csv > gpurun_out/${R}_ncu_$1_l$2_raw.csv 2>/dev/null
+  rm -f /tmp/ncu_$1_l$2.ncu-rep
 done
-timeout 300 python tools/bench_na2d.py --out gpurun_out/na2d_microbench_final.txt | tail -16
-timeout 300 python tools/profile_step.py --out gpurun_out/step_profile_final.txt | head -30
+timeout 300 python tools/profile_step.py --rows 120 --out gpurun_out/${R}_step_profile_final.txt | head -4 | cut -c1-200
+ls -la gpurun_out | head -40
