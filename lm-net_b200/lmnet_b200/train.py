@@ -316,38 +316,61 @@ class ConfusionMetrics:
 
 
 class _Prefetcher:
-    """Copies the next host batch to the device on a side stream while the current step computes."""
+    """Copies the next host batch to the device on a side stream while the current step computes.
+
+    Two persistent device staging buffers (no per-step allocation: fresh tensors + record_stream made the caching
+    allocator grow for several steps and cost 1-3 ms/step on slower hosts, tools/e2e_probe.py).  Ordering: the copy of
+    batch k+2 into a buffer waits for an event recorded on the consumer's stream after step k (which read that buffer) was
+    enqueued; the consumer waits for the copy's event before it touches the buffer."""
 
     def __init__(self, loader, device):
         self.it, self.device = iter(loader), torch.device(device)
+        if self.device.type == "cuda" and self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.stream = torch.cuda.Stream(self.device) if self.device.type == "cuda" else None
-        self.next = None
+        self.bufs, self.free_ev, self.slot = [None, None], [None, None], 0
+        self.next, self.ready, self.in_use = None, None, None
         self._load()
 
     def _load(self):
         try:
-            images, labels = next(self.it)
+            batch = next(self.it)
         except StopIteration:
             self.next = None
             return
-        if self.stream is None:
-            self.next = (images.to(self.device), labels.to(self.device))
+        if self.stream is None or all(t.device == self.device for t in batch):     # nothing to stage
+            self.next = (tuple(t.to(self.device) for t in batch), None)
             return
+        i = self.slot
+        self.slot ^= 1
         with torch.cuda.stream(self.stream):
-            self.next = (images.to(self.device, non_blocking=True), labels.to(self.device, non_blocking=True))
+            if self.free_ev[i] is not None:
+                self.stream.wait_event(self.free_ev[i])
+            buf = self.bufs[i]
+            if buf is None or any(b.shape != t.shape or b.dtype != t.dtype for b, t in zip(buf, batch)):
+                buf = self.bufs[i] = tuple(torch.empty(t.shape, dtype=t.dtype, device=self.device) for t in batch)
+            for b, t in zip(buf, batch):
+                b.copy_(t, non_blocking=True)
+            self.ready = torch.cuda.Event()
+            self.ready.record(self.stream)
+        self.next = (buf, i)
 
     def __iter__(self):
         return self
 
     def __next__(self):
+        cur = torch.cuda.current_stream(self.device) if self.stream is not None else None
+        if self.in_use is not None:               # everything that read the previous batch is enqueued by now
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            self.free_ev[self.in_use] = ev
+            self.in_use = None
         if self.next is None:
             raise StopIteration
-        if self.stream is not None:
-            torch.cuda.current_stream(self.device).wait_stream(self.stream)
-        batch = self.next
-        for t in batch:
-            if t.is_cuda:
-                t.record_stream(torch.cuda.current_stream(self.device))
+        batch, i = self.next
+        if i is not None:
+            cur.wait_event(self.ready)
+            self.in_use = i
         self._load()
         return batch
 
