@@ -32,13 +32,12 @@ for r in rows[2:]:
             print(f"  {short:16s} {r[idx[k]]} {units[idx[k]]}")
     stalls = []
     for h, i in idx.items():
-        if "average_warp_latency_issue_stalled" in h or ("warp_issue_stalled" in h and h.endswith("_per_warp_active.pct")):
+        if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio"):
             try:
                 v = float(r[i].replace(",", ""))
             except ValueError:
                 continue
             if v > 0:
-                stalls.append((v, h.split("issue_stalled_")[-1].replace("_per_warp_active.pct", "")))
+                stalls.append((v, h[len("smsp__average_warps_issue_stalled_"):-len("_per_issue_active.ratio")]))
     stalls.sort(reverse=True)
-    tot = sum(v for v, _ in stalls) or 1
-    print("  stalls           " + ", ".join(f"{n} {100 * v / tot:.0f}%" for v, n in stalls[:7]))
+    print("  stalls/issue     " + ", ".join(f"{n} {v:.2f}" for v, n in stalls[:7]))
