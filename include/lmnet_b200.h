@@ -239,6 +239,11 @@ size_t lmnet_wgrad_1x1_cl_workspace_bytes(const lmnet_wgrad_dims* dims, int a_ch
 int lmnet_wgrad_1x1_cl(const void* A, const void* B1, const void* B2, float* dW, float* drow,
                        void* workspace, size_t workspace_bytes, const lmnet_wgrad_dims* dims,
                        int a_channels_last, int b1_channels_last, int dtype, void* stream);
+/* Parameter gradients of pointwise(gate * z) + shortcut(x) out of the per-image weight gradient dW [B][M][E + Cin] and
+ * drow [B][M] of lmnet_wgrad_1x1_cl (the effective pointwise weight of image b is Wpw * gate_b):
+ * dWpw [M][E], dgate [B][E], dWsc [M][Cin], dbias [M]; wpw is read in place with element strides.  fp32. */
+int lmnet_pointwise_grads(const float* dW, const float* drow, const float* gate, const float* wpw, int64_t wpw_sm, int64_t wpw_se,
+                          float* dwpw, float* dgate, float* dwsc, float* dbias, int B, int M, int E, int Cin, void* stream);
 /* same, summed over the batch in the fixed-order reduction: dW [M][N1+N2], drow [M] (layers whose weights are shared
  * by all images need no per-image result) */
 int lmnet_wgrad_1x1_cl_sum(const void* A, const void* B1, const void* B2, float* dW, float* drow,

@@ -716,6 +716,62 @@ extern "C" int lmnet_wgrad_1x1_cl_sum(const void* A, const void* B1, const void*
     return wgrad_1x1_cl_impl(A, B1, B2, dW, drow, workspace, workspace_bytes, d, a_cl, b1_cl, dtype, stream, true);
 }
 
+// Parameter gradients of the SE-gated pointwise + shortcut pair out of the per-image weight gradient dW [B][M][E + Cin]
+// (W_b = Wpw * gate_b): dWpw[m][e] = sum_b dW[b][m][e] * gate[b][e];  dgate[b][e] = sum_m dW[b][m][e] * Wpw[m][e];
+// dWsc[m][c] = sum_b dW[b][m][E + c];  dbias[m] = sum_b drow[b][m].  One launch instead of six ATen kernels per block.
+namespace lmnet {
+__global__ void __launch_bounds__(256)
+pointwise_grads_kernel(const float* __restrict__ dW, const float* __restrict__ drow, const float* __restrict__ gate,
+                       const float* __restrict__ wpw, int64_t wpw_sm, int64_t wpw_se, float* __restrict__ dwpw,
+                       float* __restrict__ dgate, float* __restrict__ dwsc, float* __restrict__ dbias, int B, int M, int E, int Cin) {
+    const int N = E + Cin;
+    const int n_wpw = M * E, n_gate = B * E, n_wsc = M * Cin;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_wpw) {
+        const int m = i / E, e = i - m * E;
+        float a = 0.f;
+        for (int b = 0; b < B; ++b) a = fmaf(dW[((int64_t)b * M + m) * N + e], gate[(int64_t)b * E + e], a);
+        dwpw[i] = a;
+        return;
+    }
+    i -= n_wpw;
+    if (i < n_gate) {
+        const int b = i / E, e = i - b * E;
+        float a = 0.f;
+        for (int m = 0; m < M; ++m) a = fmaf(dW[((int64_t)b * M + m) * N + e], __ldg(wpw + m * wpw_sm + e * wpw_se), a);
+        dgate[i] = a;
+        return;
+    }
+    i -= n_gate;
+    if (i < n_wsc) {
+        const int m = i / Cin, c = i - m * Cin;
+        float a = 0.f;
+        for (int b = 0; b < B; ++b) a += dW[((int64_t)b * M + m) * N + E + c];
+        dwsc[i] = a;
+        return;
+    }
+    i -= n_wsc;
+    if (i < M) {
+        float a = 0.f;
+        for (int b = 0; b < B; ++b) a += drow[(int64_t)b * M + i];
+        dbias[i] = a;
+    }
+}
+}  // namespace lmnet
+
+extern "C" int lmnet_pointwise_grads(const float* dW, const float* drow, const float* gate, const float* wpw, int64_t wpw_sm,
+                                     int64_t wpw_se, float* dwpw, float* dgate, float* dwsc, float* dbias, int B, int M, int E,
+                                     int Cin, void* stream) {
+    if (!dW || !drow || !gate || !wpw || !dwpw || !dgate || !dwsc || !dbias) return LMNET_ERR_INVALID_ARG;
+    if (B <= 0 || M <= 0 || E <= 0 || Cin <= 0) return LMNET_ERR_INVALID_ARG;
+    const int64_t n = (int64_t)M * E + (int64_t)B * E + (int64_t)M * Cin + M;
+    if (n >= ((int64_t)1 << 30)) return LMNET_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    LMNET_LAUNCH(KID_WGRAD_REDUCE, st, 0, (pointwise_grads_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
+        dW, drow, gate, wpw, wpw_sm, wpw_se, dwpw, dgate, dwsc, dbias, B, M, E, Cin)));
+    return LMNET_OK;
+}
+
 extern "C" int lmnet_wgrad_1x1_supported(const lmnet_wgrad_dims* d, int dtype) {
     if (d == nullptr || d->B <= 0 || d->M <= 0 || d->N1 <= 0 || d->N2 < 0 || d->P <= 0) return 0;
     if (dtype != LMNET_BF16 && dtype != LMNET_F16) return 0;

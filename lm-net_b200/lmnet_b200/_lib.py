@@ -132,6 +132,7 @@ def lib():
     L.lmnet_wgrad_1x1_cl_workspace_bytes.argtypes = [POINTER(WgradDims), c_int, c_int]
     L.lmnet_wgrad_1x1_cl.argtypes = [c_void_p] * 5 + [c_void_p, c_size_t, POINTER(WgradDims), c_int, c_int, c_int, c_void_p]
     L.lmnet_wgrad_1x1_cl_sum.argtypes = L.lmnet_wgrad_1x1_cl.argtypes
+    L.lmnet_pointwise_grads.argtypes = [c_void_p] * 4 + [c_int64, c_int64] + [c_void_p] * 4 + [c_int, c_int, c_int, c_int, c_void_p]
     L.lmnet_layer_norm_supported.argtypes = [c_int]
     L.lmnet_layer_norm_workspace_bytes.restype = c_size_t
     L.lmnet_layer_norm_workspace_bytes.argtypes = [c_int64, c_int]

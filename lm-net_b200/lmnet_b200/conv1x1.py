@@ -290,12 +290,17 @@ class _PointwiseShortcutCl(torch.autograd.Function):
             else:
                 dx = _as_cl(torch.bmm(do, wsc.to(dt).unsqueeze(0).expand(B, Cout, Cin)), H, Wd)
         dW, drow = _wgrad_cl(do, z.view(B, E, P), _pixels(x), True, False)             # [B, Cout, E + Cin]
-        dWg = dW[:, :, :E]
-        dwpw = (dWg * gate.float().unsqueeze(1)).sum(0).to(wpw.dtype)
-        dgate = (dWg * wpw.float().unsqueeze(0)).sum(1).to(gate.dtype)                # [B, E]
-        dwsc = dW[:, :, E:].sum(0).to(wsc.dtype)
-        dbias = drow.sum(0).to(ctx.bias_dtype)
-        return dz, dgate, dx, dwpw, dwsc, dbias
+        dev = z.device
+        w32, g32 = _f32_param(wpw), gate.detach().float().contiguous()
+        dwpw = torch.empty(Cout, E, dtype=torch.float32, device=dev)
+        dgate = torch.empty(B, E, dtype=torch.float32, device=dev)
+        dwsc = torch.empty(Cout, Cin, dtype=torch.float32, device=dev)
+        dbias = torch.empty(Cout, dtype=torch.float32, device=dev)
+        rc = L.lib().lmnet_pointwise_grads(L.ptr(dW), L.ptr(drow), L.ptr(g32), L.ptr(w32), w32.stride(0), w32.stride(1),
+                                           L.ptr(dwpw), L.ptr(dgate), L.ptr(dwsc), L.ptr(dbias), B, Cout, E, Cin,
+                                           L.stream_ptr())
+        L.check(rc, "pointwise_grads")
+        return dz, dgate.to(gate.dtype), dx, dwpw.to(wpw.dtype), dwsc.to(wsc.dtype), dbias.to(ctx.bias_dtype)
 
 
 def _pad_channels(x, w, mult=4):
