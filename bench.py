@@ -275,7 +275,7 @@ def run_b200_arm(args):
         step_resident(i)
     sampler = ClockSampler(local)
     barrier()
-    if rank == 0:
+    if rank == 0 and os.environ.get("LMNET_NO_CLOCK_SAMPLER") != "1":
         sampler.start()
     launches0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -309,8 +309,11 @@ def run_b200_arm(args):
 
         def __iter__(self):
             for i in range(self.n):
+                if trace is not None:
+                    trace.append(time.perf_counter())
                 yield host[i % len(host)]
 
+    trace = [] if os.environ.get("LMNET_E2E_TRACE") == "1" else None      # diagnosis: host timestamps of the loader calls
     metrics = ConfusionMetrics(2)
     scaler_flag = object()   # non-None => autocast branch, as in the reference loop
     train_one_epoch(model, opt, metrics, 2, Loader(max(1, min(3, args.warmup))), dev, crit, scaler_flag, dice,
@@ -321,6 +324,9 @@ def run_b200_arm(args):
     train_one_epoch(model, opt, metrics, 2, Loader(args.steps), dev, crit, scaler_flag, dice, step_fn=graphed)
     e1.record()
     barrier()
+    if trace is not None and rank == 0:
+        print(f"[bench] e2e trace: events {e0.elapsed_time(e1):.1f} ms, wall {1e3 * (time.perf_counter() - t0):.1f} ms; loader calls at "
+              + " ".join(f"{1e3 * (s - t0):.1f}" for s in trace[-args.steps:]), file=sys.stderr)
     e2e_ms = torch.tensor([max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0))], device=dev)
     if world > 1:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)

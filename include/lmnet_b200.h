@@ -157,6 +157,27 @@ int lmnet_reparam_dw_train_bwd(const void* x, const void* u, const void* dz, con
                                void* workspace, size_t workspace_bytes,
                                const lmnet_dw_dims* dims, int dtype, void* stream);
 
+/* Training forward / backward with the forward's Gram by-product (same reference lines as above,
+ * /root/reference/core/modules.py:592-597; what autograd keeps between the two passes of the four
+ * conv + BatchNorm2d branches).  save_gram: fp32 [E][lmnet_reparam_dw_gram_floats()] lag sums of the
+ * branch outputs and of x taken by the statistics pass; with them the backward is ONE composite
+ * stencil pass (5x5 on du, 9x9 on x) plus a 2-pixel frame patch and needs no recomputation of
+ * the branch outputs.  *gram_saved (host int) is set to 1 when the buffer was filled (16-bit storage,
+ * W % 8 == 0, 16-byte aligned tensors), else 0 — pass save_gram to the backward only in the first
+ * case, NULL otherwise (the backward then is lmnet_reparam_dw_train_bwd).  save_gram and gram_saved
+ * are both NULL or both non-NULL. */
+int lmnet_reparam_dw_gram_floats(void);
+int lmnet_reparam_dw_train_fwd_gram(const void* x, const lmnet_dw_params* p, void* u, void* z, float* pool,
+                                    float* save_mean, float* save_rstd, float eps, float momentum,
+                                    int64_t* const* num_batches_tracked, float* save_gram, int* gram_saved,
+                                    void* workspace, size_t workspace_bytes,
+                                    const lmnet_dw_dims* dims, int dtype, void* stream);
+int lmnet_reparam_dw_train_bwd_gram(const void* x, const void* u, const void* dz, const float* dpool,
+                                    const lmnet_dw_params* p, const float* save_mean, const float* save_rstd,
+                                    const float* save_gram, void* dx, const lmnet_dw_grads* g,
+                                    void* workspace, size_t workspace_bytes,
+                                    const lmnet_dw_dims* dims, int dtype, void* stream);
+
 /* Inference forward with running statistics folded in (the algebra of
  * ReparamConv.get_equivalent_kernel_bias, /root/reference/core/modules.py:622-642):
  * one 5x5 depthwise conv + bias + GELU (+ pool).  If p->gamma[0] is NULL the weights in

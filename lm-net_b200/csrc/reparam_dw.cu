@@ -370,16 +370,22 @@ dw_stats_kernel(const T* __restrict__ x, lmnet_dw_params p, float* __restrict__ 
 
 // per-channel finalize of the forward statistics: mean / rstd, running-stat update, merged 5x5 kernel
 // coef[e][0..24] = merged taps, coef[e][25] = bias
-__global__ void dw_fin_fwd_kernel(const float* __restrict__ part, int ncta, lmnet_dw_params p, float* __restrict__ save_mean,
-                                  float* __restrict__ save_rstd, float* __restrict__ coef, float eps, float momentum,
+__global__ void dw_fin_fwd_kernel(const float* __restrict__ part, int ncta, int part_stride, lmnet_dw_params p,
+                                  float* __restrict__ save_mean, float* __restrict__ save_rstd, float* __restrict__ coef,
+                                  float* __restrict__ gram /* [E][40] or null */, float eps, float momentum,
                                   int64_t* nbt0, int64_t* nbt1, int64_t* nbt2, int64_t* nbt3, DwGeom g) {
-    // one warp per channel: lanes 0..7 each reduce one of the 8 partial sums over the CTAs, lane 0 finishes
+    // warp 0: lanes 0..7 each reduce one of the 8 partial sums over the CTAs, lane 0 finishes; with `gram` (launched
+    // with 64 threads) threads 8..47 reduce the 40 lag sums of the statistics + Gram pass (reparam_dw_tma2.cuh)
     const int e = blockIdx.x;
     __shared__ double s_tot[8];
     if (threadIdx.x < 8) {
         double a = 0;
-        for (int c = 0; c < ncta; ++c) a += part[((int64_t)e * ncta + c) * 8 + threadIdx.x];
+        for (int c = 0; c < ncta; ++c) a += part[((int64_t)e * ncta + c) * part_stride + threadIdx.x];
         s_tot[threadIdx.x] = a;
+    } else if (gram != nullptr && threadIdx.x < 48) {
+        double a = 0;
+        for (int c = 0; c < ncta; ++c) a += part[((int64_t)e * ncta + c) * part_stride + threadIdx.x];
+        gram[e * 40 + (threadIdx.x - 8)] = (float)a;
     }
     __syncwarp();
     if (threadIdx.x != 0) return;
@@ -816,6 +822,7 @@ __global__ void dw_fin_dw_kernel(const float* __restrict__ part, int ncta, const
 }  // namespace lmnet
 #include "reparam_dw_mma.cuh"
 #include "reparam_dw_tma.cuh"
+#include "reparam_dw_tma2.cuh"
 namespace lmnet {
 
 // =================================================================================================
@@ -846,22 +853,24 @@ static DwGeom dw_geom(const lmnet_dw_dims* d, int th, int tw, int ctas_per_sm = 
 }
 
 struct DwWs {
-    size_t part, coef, pool_part, pfin, cb, du, total;
+    size_t part, coef, pool_part, pfin, cb, coef2, wrec, du, total;
 };
 // CTAs per SM the TMA kernels are built for (__launch_bounds__ / shared memory): their grids are ONE wave
-constexpr int kStatsOcc = 4, kApplyOcc = 4, kReduceOcc = 3, kDxOcc = LMNET_DX_OCC;
+constexpr int kStatsOcc = 4, kApplyOcc = 4, kReduceOcc = 3, kDxOcc = LMNET_DX_OCC, kStatsGramOcc = 3, kDx2Occ = 4;
 static DwWs dw_ws_layout(const lmnet_dw_dims* d, size_t esize) {
     size_t ncta = 0;
-    const DwGeom gs[5] = {dw_geom(d, kFwdTH, kFwdTW), dw_geom(d, kMmaTH, kMmaTW, kStatsOcc, kFwdShift), dw_geom(d, kMmaTH, kMmaTW, kReduceOcc, kFwdShift),
-                          dw_geom(d, kDxTH, kDxTW), dw_geom(d, kDxTH, kDxTW, kDxOcc, kDxShift)};
+    const DwGeom gs[6] = {dw_geom(d, kFwdTH, kFwdTW), dw_geom(d, kMmaTH, kMmaTW, kStatsOcc, kFwdShift), dw_geom(d, kMmaTH, kMmaTW, kReduceOcc, kFwdShift),
+                          dw_geom(d, kDxTH, kDxTW), dw_geom(d, kDxTH, kDxTW, kDxOcc, kDxShift), dw_geom(d, kMmaTH, kMmaTW, kDx2Occ, kDx2Shift)};
     for (const DwGeom& gg : gs) ncta = std::max(ncta, (size_t)gg.stripes * gg.bands);
     DwWs w;
     size_t off = 0;
-    w.part = off; off = dw_align(off + (size_t)d->E * ncta * 40 * sizeof(float));
+    w.part = off; off = dw_align(off + (size_t)d->E * ncta * kReducePartS * sizeof(float));
     w.coef = off; off = dw_align(off + (size_t)d->E * 26 * sizeof(float));
     w.pool_part = off; off = dw_align(off + (size_t)d->B * d->E * ncta * kDwWarps * sizeof(float));
     w.pfin = off; off = dw_align(off + (size_t)d->E * 26 * sizeof(float));
     w.cb = off; off = dw_align(off + (size_t)d->E * 12 * sizeof(float));
+    w.coef2 = off; off = dw_align(off + (size_t)d->E * kCoef2Stride * sizeof(float));
+    w.wrec = off; off = dw_align(off + (size_t)d->E * 27 * sizeof(float4));
     w.du = off; off = dw_align(off + (size_t)d->B * d->E * d->H * d->W * esize);
     w.total = off;
     return w;
@@ -905,7 +914,8 @@ static int with_vec(int vec_bytes, F&& f) {
 template <typename T>
 static int dw_train_fwd(const void* x, const lmnet_dw_params* p, void* u, void* z, float* pool, float* save_mean,
                         float* save_rstd, float eps, float momentum, int64_t* const* nbt, char* ws,
-                        const lmnet_dw_dims* d, cudaStream_t st) {
+                        const lmnet_dw_dims* d, cudaStream_t st, float* save_gram = nullptr, int* gram_saved = nullptr) {
+    if (gram_saved != nullptr) *gram_saved = 0;
     DwGeom g = dw_geom(d, kFwdTH, kFwdTW);
     DwWs L = dw_ws_layout(d, sizeof(T));
     const double t_bytes = (double)d->B * d->E * d->H * d->W * sizeof(T);  // one [B,E,H,W] tensor
@@ -929,10 +939,24 @@ static int dw_train_fwd(const void* x, const lmnet_dw_params* p, void* u, void* 
             const DwGeom gs = dw_geom(d, kMmaTH, kMmaTW, kStatsOcc, kFwdShift);
             const int ncta_s = gs.stripes * gs.bands;
             const dim3 grid_s(gs.stripes, gs.bands, gs.E);
-            LMNET_LAUNCH(KID_DW_STATS, st, 1 * t_bytes, (dw_stats_tma_kernel<T><<<grid_s, kTmaThreads, kStatsSmem, st>>>(tm_x, *p, part, gs)));
-            LMNET_LAUNCH(KID_DW_FIN_FWD, st, 0, (dw_fin_fwd_kernel<<<g.E, 32, 0, st>>>(part, ncta_s, *p, save_mean, save_rstd, coef, eps, momentum,
-                                                             nbt ? nbt[0] : nullptr, nbt ? nbt[1] : nullptr,
-                                                             nbt ? nbt[2] : nullptr, nbt ? nbt[3] : nullptr, g)));
+            const bool kNoGram = getenv("LMNET_DW_NO_GRAM") != nullptr;     // A/B switch (tests)
+            if (save_gram != nullptr && gram_saved != nullptr && !kNoGram) {
+                // statistics + Gram pass: the lag sums Q_br, S that turn the backward into one composite stencil
+                static std::atomic<size_t> granted_g[kMaxDevices];
+                if (!dw_tma_smem(dw_stats_gram_tma_kernel<T>, kStatsGramSmem, granted_g)) return LMNET_ERR_LAUNCH;
+                const DwGeom gg = dw_geom(d, kMmaTH, kMmaTW, kStatsGramOcc, kFwdShift);
+                const dim3 grid_g(gg.stripes, gg.bands, gg.E);
+                LMNET_LAUNCH(KID_DW_STATS, st, 1 * t_bytes, (dw_stats_gram_tma_kernel<T><<<grid_g, kTmaThreads, kStatsGramSmem, st>>>(tm_x, *p, part, gg)));
+                LMNET_LAUNCH(KID_DW_FIN_FWD, st, 0, (dw_fin_fwd_kernel<<<g.E, 64, 0, st>>>(part, gg.stripes * gg.bands, kGramPartStride, *p, save_mean, save_rstd, coef, save_gram, eps, momentum,
+                                                                 nbt ? nbt[0] : nullptr, nbt ? nbt[1] : nullptr,
+                                                                 nbt ? nbt[2] : nullptr, nbt ? nbt[3] : nullptr, g)));
+                *gram_saved = 1;
+            } else {
+                LMNET_LAUNCH(KID_DW_STATS, st, 1 * t_bytes, (dw_stats_tma_kernel<T><<<grid_s, kTmaThreads, kStatsSmem, st>>>(tm_x, *p, part, gs)));
+                LMNET_LAUNCH(KID_DW_FIN_FWD, st, 0, (dw_fin_fwd_kernel<<<g.E, 32, 0, st>>>(part, ncta_s, 8, *p, save_mean, save_rstd, coef, nullptr, eps, momentum,
+                                                                 nbt ? nbt[0] : nullptr, nbt ? nbt[1] : nullptr,
+                                                                 nbt ? nbt[2] : nullptr, nbt ? nbt[3] : nullptr, g)));
+            }
             CUtensorMap tm_u, tm_z;
             if (!tma_make_planes_map(&tm_u, u ? u : z, (int64_t)d->B * d->E, d->H, d->W, kStageRows, kStageCols) ||
                 !tma_make_planes_map(&tm_z, z, (int64_t)d->B * d->E, d->H, d->W, kStageRows, kStageCols))
@@ -952,7 +976,7 @@ static int dw_train_fwd(const void* x, const lmnet_dw_params* p, void* u, void* 
         return LMNET_OK;
     });
     if (rc != LMNET_OK) return rc;
-    LMNET_LAUNCH(KID_DW_FIN_FWD, st, 0, (dw_fin_fwd_kernel<<<g.E, 32, 0, st>>>(part, ncta, *p, save_mean, save_rstd, coef, eps, momentum,
+    LMNET_LAUNCH(KID_DW_FIN_FWD, st, 0, (dw_fin_fwd_kernel<<<g.E, 32, 0, st>>>(part, ncta, 8, *p, save_mean, save_rstd, coef, nullptr, eps, momentum,
                                                      nbt ? nbt[0] : nullptr, nbt ? nbt[1] : nullptr,
                                                      nbt ? nbt[2] : nullptr, nbt ? nbt[3] : nullptr, g)));
     if constexpr (sizeof(T) == 2) {
@@ -1025,7 +1049,7 @@ constexpr size_t kA1SmemBytes = (size_t)(kA1XRows * kPitch + 4 * kA1RegRows * kD
 template <typename T>
 static int dw_train_bwd(const void* x, const void* u, const void* dz, const float* dpool, const lmnet_dw_params* p,
                         const float* save_mean, const float* save_rstd, void* dx, const lmnet_dw_grads* gr, char* ws,
-                        const lmnet_dw_dims* d, cudaStream_t st) {
+                        const lmnet_dw_dims* d, cudaStream_t st, const float* gram = nullptr) {
     DwGeom g = dw_geom(d, kFwdTH, kFwdTW);
     DwWs L = dw_ws_layout(d, sizeof(T));
     const double t_bytes = (double)d->B * d->E * d->H * d->W * sizeof(T);  // one [B,E,H,W] tensor
@@ -1049,12 +1073,34 @@ static int dw_train_bwd(const void* x, const void* u, const void* dz, const floa
                 !tma_make_planes_map(&tm_dz, dz, planes, d->H, d->W, kMmaTH, kMmaPitch) ||
                 !tma_make_planes_map(&tm_du, du, planes, d->H, d->W, kMmaTH, kMmaPitch))
                 return LMNET_ERR_LAUNCH;
-            static std::atomic<size_t> granted_r[kMaxDevices], granted_x[kMaxDevices];
-            if (!dw_tma_smem(dw_bwd_reduce_tma_kernel<T>, kReduceSmem, granted_r) || !dw_tma_smem(dw_bwd_dx_tma_kernel<T>, kDxTmaSmem, granted_x))
+            static std::atomic<size_t> granted_r[kMaxDevices], granted_r2[kMaxDevices], granted_x[kMaxDevices];
+            if (!dw_tma_smem(dw_bwd_reduce_tma_kernel<T, false>, kReduceSmem, granted_r) || !dw_tma_smem(dw_bwd_reduce_tma_kernel<T, true>, kReduceSmem, granted_r2) || !dw_tma_smem(dw_bwd_dx_tma_kernel<T>, kDxTmaSmem, granted_x))
                 return LMNET_ERR_LAUNCH;
             const DwGeom gr_ = dw_geom(d, kMmaTH, kMmaTW, kReduceOcc, kFwdShift);
             const dim3 grid_r(gr_.stripes, gr_.bands, gr_.E);
-            LMNET_LAUNCH(KID_DW_BWD_REDUCE, st, 2 * t_bytes, (dw_bwd_reduce_tma_kernel<T><<<grid_r, kTmaThreads, kReduceSmem, st>>>(tm_x, tm_u, tm_dz, dpool, du, part, gr_)));
+            if (gram == nullptr) LMNET_LAUNCH(KID_DW_BWD_REDUCE, st, 2 * t_bytes, (dw_bwd_reduce_tma_kernel<T, false><<<grid_r, kTmaThreads, kReduceSmem, st>>>(tm_x, tm_u, tm_dz, dpool, du, part, gr_)));
+            if (gram != nullptr) {
+                LMNET_LAUNCH(KID_DW_BWD_REDUCE, st, 2 * t_bytes, (dw_bwd_reduce_tma_kernel<T, true><<<grid_r, kTmaThreads, kReduceSmem, st>>>(tm_x, tm_u, tm_dz, dpool, du, part, gr_)));
+                // composite-stencil backward (reparam_dw_tma2.cuh): finalize (coefficients + all parameter gradients),
+                // one tile kernel, frame patch
+                CUtensorMap tm_x2, tm_dx;
+                if (!tma_make_planes_map(&tm_x2, x, planes, d->H, d->W, kDx2XRows, kMmaPitch) ||
+                    !tma_make_planes_map(&tm_du, du, planes, d->H, d->W, kMmaTileRows, kMmaPitch) ||
+                    !tma_make_planes_map(&tm_dx, dx, planes, d->H, d->W, kStageRows, kStageCols))
+                    return LMNET_ERR_LAUNCH;
+                static std::atomic<size_t> granted_x2[kMaxDevices];
+                if (!dw_tma_smem(dw_bwd_dx2_tma_kernel<T>, kDx2Smem, granted_x2)) return LMNET_ERR_LAUNCH;
+                float* coef2 = (float*)(ws + L.coef2);
+                float4* wrec = (float4*)(ws + L.wrec);
+                LMNET_LAUNCH(KID_DW_FIN_BWD, st, 0, (dw_fin_bwd2_kernel<<<g.E, 128, 0, st>>>(part, gr_.stripes * gr_.bands, *p, save_mean, save_rstd, gram, *gr, cb, coef2, wrec, g)));
+                const DwGeom gx = dw_geom(d, kMmaTH, kMmaTW, kDx2Occ, kDx2Shift);
+                const dim3 grid_x(gx.stripes, gx.bands, gx.E);
+                LMNET_LAUNCH(KID_DW_BWD_DX, st, 3 * t_bytes, (dw_bwd_dx2_tma_kernel<T><<<grid_x, kTmaThreads, kDx2Smem, st>>>(tm_x2, tm_du, tm_dx, coef2, (T*)dx, gx)));
+                const int nseg = (std::max(d->H, d->W) + kFrameSeg - 1) / kFrameSeg;
+                const dim3 grid_f((unsigned)planes, (unsigned)(4 * nseg));
+                LMNET_LAUNCH(KID_DW_BWD_FRAME, st, 0, (dw_bwd_frame_kernel<T><<<grid_f, kFrameThreads, 0, st>>>((const T*)x, (T*)dx, wrec, g)));
+                return LMNET_OK;
+            }
             LMNET_LAUNCH(KID_DW_FIN_BWD, st, 0, (dw_fin_bwd_kernel<<<g.E, 32, 0, st>>>(part, gr_.stripes * gr_.bands, *p, save_mean, save_rstd, *gr, pfin, cb, g)));
             const DwGeom gx = dw_geom(d, kDxTH, kDxTW, kDxOcc, kDxShift);
             const dim3 grid_x(gx.stripes, gx.bands, gx.E);
@@ -1130,6 +1176,48 @@ extern "C" int lmnet_reparam_dw_train_fwd(const void* x, const lmnet_dw_params* 
         case LMNET_F32: return dw_train_fwd<float>(x, p, u, z, pool, save_mean, save_rstd, eps, momentum, num_batches_tracked, (char*)workspace, dims, st);
         case LMNET_BF16: return dw_train_fwd<__nv_bfloat16>(x, p, u, z, pool, save_mean, save_rstd, eps, momentum, num_batches_tracked, (char*)workspace, dims, st);
         case LMNET_F16: return dw_train_fwd<__half>(x, p, u, z, pool, save_mean, save_rstd, eps, momentum, num_batches_tracked, (char*)workspace, dims, st);
+        default: return LMNET_ERR_UNSUPPORTED;
+    }
+}
+
+extern "C" int lmnet_reparam_dw_train_fwd_gram(const void* x, const lmnet_dw_params* p, void* u, void* z, float* pool,
+                                               float* save_mean, float* save_rstd, float eps, float momentum,
+                                               int64_t* const* num_batches_tracked, float* save_gram, int* gram_saved,
+                                               void* workspace, size_t workspace_bytes,
+                                               const lmnet_dw_dims* dims, int dtype, void* stream) {
+    if (gram_saved != nullptr) *gram_saved = 0;
+    int rc = dw_validate(dims);
+    if (rc != LMNET_OK) return rc;
+    if (!x || !z || !save_mean || !save_rstd || !workspace || !dw_params_ok(p, true)) return LMNET_ERR_INVALID_ARG;
+    if ((save_gram == nullptr) != (gram_saved == nullptr)) return LMNET_ERR_INVALID_ARG;
+    for (int k = 0; k < 4; ++k)
+        if ((p->running_mean[k] == nullptr) != (p->running_var[k] == nullptr)) return LMNET_ERR_INVALID_ARG;
+    if (workspace_bytes < lmnet_reparam_dw_workspace_bytes(dims, dtype)) return LMNET_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (dtype) {
+        case LMNET_F32: return dw_train_fwd<float>(x, p, u, z, pool, save_mean, save_rstd, eps, momentum, num_batches_tracked, (char*)workspace, dims, st, save_gram, gram_saved);
+        case LMNET_BF16: return dw_train_fwd<__nv_bfloat16>(x, p, u, z, pool, save_mean, save_rstd, eps, momentum, num_batches_tracked, (char*)workspace, dims, st, save_gram, gram_saved);
+        case LMNET_F16: return dw_train_fwd<__half>(x, p, u, z, pool, save_mean, save_rstd, eps, momentum, num_batches_tracked, (char*)workspace, dims, st, save_gram, gram_saved);
+        default: return LMNET_ERR_UNSUPPORTED;
+    }
+}
+
+extern "C" int lmnet_reparam_dw_gram_floats(void) { return kGramFloats; }
+
+extern "C" int lmnet_reparam_dw_train_bwd_gram(const void* x, const void* u, const void* dz, const float* dpool,
+                                               const lmnet_dw_params* p, const float* save_mean, const float* save_rstd,
+                                               const float* save_gram, void* dx, const lmnet_dw_grads* g,
+                                               void* workspace, size_t workspace_bytes,
+                                               const lmnet_dw_dims* dims, int dtype, void* stream) {
+    int rc = dw_validate(dims);
+    if (rc != LMNET_OK) return rc;
+    if (!x || !u || !dz || !dx || !g || !save_mean || !save_rstd || !workspace || !dw_params_ok(p, true)) return LMNET_ERR_INVALID_ARG;
+    if (workspace_bytes < lmnet_reparam_dw_workspace_bytes(dims, dtype)) return LMNET_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (dtype) {
+        case LMNET_F32: return dw_train_bwd<float>(x, u, dz, dpool, p, save_mean, save_rstd, dx, g, (char*)workspace, dims, st, save_gram);
+        case LMNET_BF16: return dw_train_bwd<__nv_bfloat16>(x, u, dz, dpool, p, save_mean, save_rstd, dx, g, (char*)workspace, dims, st, save_gram);
+        case LMNET_F16: return dw_train_bwd<__half>(x, u, dz, dpool, p, save_mean, save_rstd, dx, g, (char*)workspace, dims, st, save_gram);
         default: return LMNET_ERR_UNSUPPORTED;
     }
 }

@@ -411,13 +411,21 @@ dw_apply_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
 constexpr int kReduceStages = 3;
 constexpr int kReduceSlotBytes = kXSlotBytes + 2 * kRTileBytes;          // x | u | dz
 constexpr size_t kReduceSmem = 128 + (size_t)kReduceStages * kReduceSlotBytes + kRTileBytes /* du */ +
-                               kDwWarps * 5 * 128 * 4 /* G fragments */ + 2 * kReduceStages * 8 + 64;
+                               kDwWarps * 5 * 128 * 4 /* G fragments */ + 2 * kReduceStages * 8 + 64 + kDwWarps * 25 * 4;
+constexpr int kReducePartS = 52;       // partial record with the x lag sums: P [25] | sum du | S [25] | pad
 
-template <typename T>
+template <typename T> __device__ __forceinline__ uint32_t ones_pair();
+template <> __device__ __forceinline__ uint32_t ones_pair<__nv_bfloat16>() { return 0x3F803F80u; }
+template <> __device__ __forceinline__ uint32_t ones_pair<__half>() { return 0x3C003C00u; }
+
+// WITH_S: additionally S[a][b] = sum_p x(p + (a-2, b-2)) over the pixels p of the image (an all-ones Gram product on
+// the A fragments the P products load anyway) for the composite backward of reparam_dw_tma2.cuh; record stride
+// kReducePartS instead of 26.
+template <typename T, bool WITH_S>
 __global__ void __launch_bounds__(kTmaThreads, 3)
 dw_bwd_reduce_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_u,
                          const __grid_constant__ CUtensorMap tm_dz, const float* __restrict__ dpool, T* __restrict__ du_out,
-                         float* __restrict__ part /* [E][ncta][26] */, DwGeom g) {
+                         float* __restrict__ part /* [E][ncta][26 | kReducePartS] */, DwGeom g) {
     constexpr int S = kReduceStages;
     extern __shared__ unsigned char dw_smem_raw[];
     unsigned char* smem = align128(dw_smem_raw);
@@ -426,6 +434,8 @@ dw_bwd_reduce_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_
     uint64_t* full = reinterpret_cast<uint64_t*>(s_G + kDwWarps * 5 * 128);
     uint64_t* empty = full + S;
     float* s_sdu = reinterpret_cast<float*>(empty + S);                                      // [4]
+    float* s_S = s_sdu + 16;                                                                 // [4 warps][25]
+    constexpr int STRIDE = WITH_S ? kReducePartS : 26;
     const int e = blockIdx.z, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int c0 = blockIdx.x * kMmaTW - kFwdShift;
     const int band0 = blockIdx.y * g.rows_per_band, band1 = min(band0 + g.rows_per_band, g.H);
@@ -454,9 +464,11 @@ dw_bwd_reduce_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_
     } else {
         const int wr = warp >> 1, wc = warp & 1;
         const float inv_hw = 1.f / ((float)g.H * (float)g.W);
-        float G[5][4];
+        float G[5][4], G1[WITH_S ? 5 : 1][4];
 #pragma unroll
         for (int a = 0; a < 5; ++a) G[a][0] = G[a][1] = G[a][2] = G[a][3] = 0.f;
+#pragma unroll
+        for (int a = 0; a < (WITH_S ? 5 : 1); ++a) G1[a][0] = G1[a][1] = G1[a][2] = G1[a][3] = 0.f;
         float sdu = 0.f;
         // du mapping inside the warp's block: half-warps take rows 4 apart (conflict-free at the 72-element pitch),
         // 16 lanes x one 32-bit pair = 64 contiguous bytes of one image row
@@ -496,16 +508,32 @@ dw_bwd_reduce_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_
                 *reinterpret_cast<uint32_t*>(s_du + trow * kMmaPitch + bcol) = packed;
             }
             __syncwarp();
+            // ones operand in B-fragment layout: block rows 2tq, 2tq+1 (+8) at column gq, masked to the image / band
+            uint32_t onesr[2] = {0u, 0u};
+            if constexpr (WITH_S) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int r = tr + 16 * wr + 2 * (lane & 3) + 8 * h;
+                    onesr[h] = ones_pair<T>() & ((r < band1 ? 0x0000ffffu : 0u) | (r + 1 < band1 ? 0xffff0000u : 0u));
+                }
+            }
 #pragma unroll
             for (int cb = 0; cb < 4; ++cb) {
                 const int tcol = 32 * wc + 8 * cb;
-                uint32_t Bf[2];
+                uint32_t Bf[2], B1[2] = {0u, 0u};
                 load_b_trans(s_du, 16 * wr, tcol, lane, Bf);
+                if constexpr (WITH_S) {
+                    const int col = c0 + tcol + (lane >> 2);
+                    const uint32_t cmask = (col >= 0 && col < g.W) ? 0xffffffffu : 0u;
+                    B1[0] = onesr[0] & cmask;
+                    B1[1] = onesr[1] & cmask;
+                }
 #pragma unroll
                 for (int a = 0; a < 5; ++a) {
                     uint32_t A[4];
                     load_a_trans(s_x, 16 * wr + a, tcol, lane, A);
                     MmaOp<T>::run(G[a], A, Bf);
+                    if constexpr (WITH_S) MmaOp<T>::run(G1[a], A, B1);
                 }
             }
             __syncwarp();
@@ -523,8 +551,27 @@ dw_bwd_reduce_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_
             }
         sdu = warp_sum(sdu);
         if (lane == 0) s_sdu[warp] = sdu;
+        if constexpr (WITH_S) {
+            // entry (i, j) of a fragment belongs to column lag bb = i - j (this lane: i = gq, gq + 8; j = 2tq, 2tq + 1)
+            const int gq = lane >> 2, tq = lane & 3;
+#pragma unroll
+            for (int a = 0; a < 5; ++a)
+#pragma unroll
+                for (int bb = 0; bb < 5; ++bb) {
+                    float v = 0.f;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (gq + (k >> 1) * 8 - (2 * tq + (k & 1)) == bb) v += G1[a][k];
+                    v = warp_sum(v);
+                    if (lane == 0) s_S[warp * 25 + a * 5 + bb] = v;
+                }
+        }
     }
     __syncthreads();
+    if (WITH_S && threadIdx.x >= 32 && threadIdx.x < 57) {
+        const int ncta = gridDim.x * gridDim.y, cta = blockIdx.y * gridDim.x + blockIdx.x, t = threadIdx.x - 32;
+        part[((int64_t)e * ncta + cta) * STRIDE + 26 + t] = (s_S[t] + s_S[25 + t]) + (s_S[50 + t] + s_S[75 + t]);
+    }
     if (threadIdx.x < 26) {
         const int ncta = gridDim.x * gridDim.y, cta = blockIdx.y * gridDim.x + blockIdx.x;
         float acc = 0.f;
@@ -536,7 +583,7 @@ dw_bwd_reduce_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_
 #pragma unroll
                 for (int j = 0; j < 8; ++j) acc += s_G[(w * 5 + a) * 128 + (j + bb) * 8 + j];
         }
-        part[((int64_t)e * ncta + cta) * 26 + threadIdx.x] = acc;
+        part[((int64_t)e * ncta + cta) * STRIDE + threadIdx.x] = acc;
     }
 }
 

@@ -119,6 +119,11 @@ def lib():
                                              pg, c_void_p, c_size_t, pdd, c_int, c_void_p]
     L.lmnet_reparam_dw_eval_fwd.argtypes = [c_void_p, pp, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_size_t,
                                             pdd, c_int, c_void_p]
+    L.lmnet_reparam_dw_train_fwd_gram.argtypes = [c_void_p, pp, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
+                                                  c_float, POINTER(c_void_p), c_void_p, POINTER(c_int), c_void_p, c_size_t,
+                                                  pdd, c_int, c_void_p]
+    L.lmnet_reparam_dw_train_bwd_gram.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, pp, c_void_p, c_void_p, c_void_p,
+                                                  c_void_p, pg, c_void_p, c_size_t, pdd, c_int, c_void_p]
     pbd = POINTER(BnDims)
     L.lmnet_bn_act_workspace_bytes.restype = c_size_t
     L.lmnet_bn_act_workspace_bytes.argtypes = [pbd]

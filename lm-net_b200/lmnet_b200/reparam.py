@@ -68,12 +68,18 @@ class _FusedDwTrain(torch.autograd.Function):
         if nbt is not None:
             nbt_arr = (ctypes.c_void_p * 4)(*[None if t is None else t.data_ptr() for t in nbt])
         ws = _ws(dims, x)
-        rc = L.lib().lmnet_reparam_dw_train_fwd(
+        # lag sums of the branch outputs taken by the statistics pass: with them the backward is one composite stencil
+        # pass instead of a recomputation of the four branches (csrc/reparam_dw_tma2.cuh); the library says whether
+        # this shape / dtype / alignment has that path
+        gram = torch.empty(E, L.lib().lmnet_reparam_dw_gram_floats(), dtype=torch.float32, device=x.device)
+        gram_saved = ctypes.c_int(0)
+        rc = L.lib().lmnet_reparam_dw_train_fwd_gram(
             L.ptr(x), L.byref(params), L.ptr(u), L.ptr(z), L.ptr(pool), L.ptr(save_mean), L.ptr(save_rstd),
-            float(eps), float(momentum), nbt_arr, L.ptr(ws), ws.numel(), L.byref(dims), L.dtype_code(x),
-            L.stream_ptr())
-        L.check(rc, "reparam_dw_train_fwd")
-        ctx.save_for_backward(x, u, save_mean, save_rstd, *ws_f, *gam)
+            float(eps), float(momentum), nbt_arr, L.ptr(gram), ctypes.byref(gram_saved), L.ptr(ws), ws.numel(),
+            L.byref(dims), L.dtype_code(x), L.stream_ptr())
+        L.check(rc, "reparam_dw_train_fwd_gram")
+        ctx.has_gram = bool(gram_saved.value)
+        ctx.save_for_backward(x, u, save_mean, save_rstd, *ws_f, *gam, *([gram] if ctx.has_gram else []))
         ctx.param_meta = [(t.shape, t.dtype) for t in (w5, w3, w31, w13, g0, b0, g1, b1, g2, b2, g3, b3)]
         ctx.set_materialize_grads(False)
         return z, pool
@@ -81,7 +87,8 @@ class _FusedDwTrain(torch.autograd.Function):
     @staticmethod
     @custom_bwd(device_type="cuda")
     def backward(ctx, dz, dpool):
-        x, u, save_mean, save_rstd, w5, w3, w31, w13, g0, g1, g2, g3 = ctx.saved_tensors
+        x, u, save_mean, save_rstd, w5, w3, w31, w13, g0, g1, g2, g3 = ctx.saved_tensors[:12]
+        gram = ctx.saved_tensors[12] if ctx.has_gram else None
         B, E, H, W = x.shape
         dims = _dims(x)
         dz = torch.zeros_like(x) if dz is None else dz.to(x.dtype).contiguous()
@@ -95,10 +102,10 @@ class _FusedDwTrain(torch.autograd.Function):
         params = L.dw_params([w5, w3, w31, w13], [g0, g1, g2, g3], zeros)
         grads = L.dw_grads(dws, dgs, dbs)
         ws = _ws(dims, x)
-        rc = L.lib().lmnet_reparam_dw_train_bwd(
+        rc = L.lib().lmnet_reparam_dw_train_bwd_gram(
             L.ptr(x), L.ptr(u), L.ptr(dz), L.ptr(dpool), L.byref(params), L.ptr(save_mean), L.ptr(save_rstd),
-            L.ptr(dx), L.byref(grads), L.ptr(ws), ws.numel(), L.byref(dims), L.dtype_code(x), L.stream_ptr())
-        L.check(rc, "reparam_dw_train_bwd")
+            L.ptr(gram), L.ptr(dx), L.byref(grads), L.ptr(ws), ws.numel(), L.byref(dims), L.dtype_code(x), L.stream_ptr())
+        L.check(rc, "reparam_dw_train_bwd_gram")
         meta = ctx.param_meta
         outs = [dx]
         for i, t in enumerate(dws):

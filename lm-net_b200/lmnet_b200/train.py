@@ -315,6 +315,9 @@ class ConfusionMetrics:
                 "iou": float(tp / (tp + fp + fn).clamp_min(1))}
 
 
+_PREFETCH_STATE = {}
+
+
 class _Prefetcher:
     """Copies the next host batch to the device on a side stream while the current step computes.
 
@@ -327,8 +330,17 @@ class _Prefetcher:
         self.it, self.device = iter(loader), torch.device(device)
         if self.device.type == "cuda" and self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
-        self.stream = torch.cuda.Stream(self.device) if self.device.type == "cuda" else None
-        self.bufs, self.free_ev, self.slot = [None, None], [None, None], 0
+        # the side stream and the two staging buffers persist across epochs (per device): a fresh stream per epoch
+        # draws from a different allocator pool, i.e. two cudaMalloc calls of a batch each at the start of every epoch
+        # (a 20-40 ms stall in the first step, tools/e2e_probe.py) and memory that is only returned at the next GC
+        state = _PREFETCH_STATE.get(self.device) if self.device.type == "cuda" else None
+        if state is None and self.device.type == "cuda":
+            state = _PREFETCH_STATE[self.device] = {"stream": torch.cuda.Stream(self.device), "bufs": [None, None],
+                                                    "free_ev": [None, None]}
+        self.stream = state["stream"] if state is not None else None
+        self.bufs = state["bufs"] if state is not None else [None, None]
+        self.free_ev = state["free_ev"] if state is not None else [None, None]
+        self.slot = 0
         self.next, self.ready, self.in_use = None, None, None
         self._load()
 

@@ -196,6 +196,10 @@ TMA_SHAPES = [
     (2, 24, 88, 88),      # LM-Net level-3 map
     (3, 4, 64, 128),      # tiles align exactly with the image (no masks anywhere)
     (1, 5, 120, 56),      # several row tiles per band, one dx stripe exactly
+    (2, 4, 3, 16),        # every pixel is on the 2-pixel frame of the composite backward
+    (1, 8, 2, 8),         # two rows (with one row the 3x1 branch is a single tap under BatchNorm: its weight
+                          # gradient is exactly zero and only rounding noise could be compared)
+    (1, 8, 352, 352),     # LM-Net level-1 plane: 6 stripes, 11 row tiles
 ]
 
 
@@ -237,6 +241,10 @@ def test_tma_pipeline_kernels_vs_oracle(shape, dtype):
     assert rel_err(z.float().cpu(), zr) < tol
     assert rel_err(p.cpu(), pr) < tol
     assert rel_err(xc.grad.float().cpu(), xr.grad) < tol * 2
+    # the 2-pixel frame of every plane is patched by a separate kernel in the composite backward: check it on its own
+    fm = torch.zeros(H, W, dtype=torch.bool)
+    fm[:2], fm[-2:], fm[:, :2], fm[:, -2:] = True, True, True, True
+    assert rel_err(xc.grad.float().cpu()[:, :, fm], xr.grad[:, :, fm]) < tol * 2
     names = ("large_conv", "square_conv", "ver_conv", "hor_conv")
     for n in names:
         a, b = getattr(m, n), getattr(ref, n)
@@ -245,6 +253,17 @@ def test_tma_pipeline_kernels_vs_oracle(shape, dtype):
         assert rel_err(a.bn.bias.grad.cpu(), b.bn.bias.grad) < tol * 3, n
         assert torch.allclose(a.bn.running_mean.double().cpu(), b.bn.running_mean, rtol=5 * tol, atol=tol), n
         assert torch.allclose(a.bn.running_var.double().cpu(), b.bn.running_var, rtol=5 * tol, atol=tol), n
+    # composite backward (Gram by-product of the forward) vs the recomputing TMA backward on the same inputs
+    os.environ["LMNET_DW_NO_GRAM"] = "1"
+    try:
+        m1, xc1, z1, p1 = run(False)
+    finally:
+        os.environ.pop("LMNET_DW_NO_GRAM", None)
+    assert rel_err(z.float(), z1.float()) < 1e-2 and rel_err(p, p1) < 1e-3
+    assert rel_err(xc.grad.float(), xc1.grad.float()) < 2e-2
+    for n in names:
+        assert rel_err(getattr(m, n).conv.weight.grad, getattr(m1, n).conv.weight.grad) < 2e-2, n
+        assert rel_err(getattr(m, n).bn.weight.grad, getattr(m1, n).bn.weight.grad) < 1e-4, n
     m0, xc0, z0, p0 = run(True)
     assert rel_err(z.float(), z0.float()) < 1e-2 and rel_err(p, p0) < 1e-3
     assert rel_err(xc.grad.float(), xc0.grad.float()) < 2e-2

@@ -33,6 +33,22 @@ t0 = time.perf_counter()
 for i in range(N): g.graph.replay()
 t1 = time.perf_counter(); torch.cuda.synchronize()
 print(f"{'host time of graph.replay() alone':55s} {(t1-t0)/N*1e3:7.2f} ms/call")
+if os.environ.get("E2E_TRACE"):
+    # per-step host timestamps of the first end-to-end epoch after the resident loop (bench.py's order of events)
+    class TLoader(Loader):
+        def __iter__(self):
+            for i in range(self.n):
+                stamps.append(time.perf_counter())
+                yield self.src[i % 2]
+    for rep in range(2):
+        stamps = []
+        m = ConfusionMetrics(2)
+        train_one_epoch(net, opt, m, 2, Loader(host, 3), dev, crit, object(), dice, step_fn=g)
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        train_one_epoch(net, opt, m, 2, TLoader(host, 10), dev, crit, object(), dice, step_fn=g)
+        t1 = time.perf_counter(); torch.cuda.synchronize(); t2 = time.perf_counter()
+        print(f"trace rep {rep}: 10 steps {1e3*(t2-t0):.1f} ms (host loop {1e3*(t1-t0):.1f}); loader calls at",
+              " ".join(f"{1e3*(s-t0):.1f}" for s in stamps))
 run("e2e default (pinned host, prefetch, device metrics)", host)
 run("e2e, device-resident loader (no H2D)", res)
 run("e2e, no metrics", host, ) if False else None
