@@ -836,18 +836,37 @@ static int dw_validate(const lmnet_dw_dims* d) {
     return LMNET_OK;
 }
 
-// CTA grid for a kernel with tile (th x tw): enough CTAs for ~4 waves of 148 SMs, bands aligned to th
+// CTA grid for a kernel with tile (th x tw).  A CTA owns one channel, one column stripe and one band of row tiles (and
+// loops over the batch); `ctas_per_sm` x 148 CTAs are resident at once.  The band count minimises the makespan
+// waves(bands) x tiles_per_band(bands): rounding the band count UP to fill the machine once (the first rule) put 576 CTAs
+// on 444 slots at level 1 for the 3-CTA kernels — a second, 30 % full wave of whole bands (ncu: 190 us where 4 row
+// tiles per CTA in ONE wave need ~130).
 static DwGeom dw_geom(const lmnet_dw_dims* d, int th, int tw, int ctas_per_sm = 4, int shift = 0) {
     DwGeom g;
     g.B = d->B; g.E = d->E; g.H = d->H; g.W = d->W;
     g.stripes = (d->W + shift + tw - 1) / tw;          // TMA kernels: stripe s starts at s*tw - shift
     const int row_tiles = (d->H + th - 1) / th;
     static const int kCtaOverride = getenv("LMNET_DW_CTAS") ? atoi(getenv("LMNET_DW_CTAS")) : 0;
-    const int kCtaTarget = kCtaOverride > 0 ? kCtaOverride : ctas_per_sm * 148;     // one wave of resident CTAs
-    int bands = (kCtaTarget + g.E * g.stripes - 1) / (g.E * g.stripes);
-    bands = bands < 1 ? 1 : bands > row_tiles ? row_tiles : bands;
-    const int tiles_per_band = (row_tiles + bands - 1) / bands;
-    g.rows_per_band = tiles_per_band * th;
+    const int64_t capacity = kCtaOverride > 0 ? kCtaOverride : ctas_per_sm * 148;     // resident CTAs
+    const int64_t per_band = (int64_t)g.E * g.stripes;
+    // Ties (B200, tools/bench_dw.py with LMNET_DW_TPB=1..6): a grid that fills < 90 % of the first wave loses 15 % at
+    // level 3 (384 CTAs x 2 tiles against 576 x 1 on 444 slots), beyond that the smaller grid wins or is within 5 %.
+    int best_tpb = row_tiles;
+    int64_t best_cost = -1, best_ctas = 0;
+    bool best_full = false;
+    for (int bands = 1; bands <= row_tiles; ++bands) {
+        const int tpb = (row_tiles + bands - 1) / bands;
+        const int nb = (row_tiles + tpb - 1) / tpb;
+        const int64_t ctas = per_band * nb, waves = (ctas + capacity - 1) / capacity;
+        const int64_t cost = waves * tpb;
+        const bool full = 10 * ctas >= 9 * capacity;
+        const bool better = best_cost < 0 || cost < best_cost ||
+                            (cost == best_cost && (full != best_full ? full : (full ? ctas < best_ctas : ctas > best_ctas)));
+        if (better) { best_cost = cost; best_ctas = ctas; best_tpb = tpb; best_full = full; }
+    }
+    static const int kTpbOverride = getenv("LMNET_DW_TPB") ? atoi(getenv("LMNET_DW_TPB")) : 0;      // experiments
+    if (kTpbOverride > 0) best_tpb = std::min(kTpbOverride, row_tiles);
+    g.rows_per_band = best_tpb * th;
     g.bands = (d->H + g.rows_per_band - 1) / g.rows_per_band;
     return g;
 }

@@ -461,19 +461,63 @@ dw_bwd_dx2_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
 // a rectangle R of frame pixels (top / bottom: 2 rows x segment; left / right: segment x 2 columns, between the top and
 // bottom rows).  Two phases through shared memory:
 //   1. v_br(p) = c2_br y~_br(p) + c0_br for every position p OUTSIDE the image within 2 pixels of R (one float4 = four
-//      branches per position; only the taps that reach into the image are visited);
-//   2. every pixel q of R gathers w_br[s] v_br(q - s) over the s whose q - s lies outside the image.
-// The kernel is latency-bound (a few hundred loads per CTA), so the dependent chain is kept short: the per-channel
-// record wrec (25 x float4 embedded branch taps | c2 | c0, written by dw_fin_bwd2_kernel) is read through the
-// read-only path without a prologue barrier, and the dx values a thread patches are fetched before phase 1.
+//      branches per position), ONE position per thread: the two outside lines next to R (2 x (segment + 4) = 128
+//      positions), plus — only in the CTAs that touch a corner of the plane — the <= 16 positions beside R's rows;
+//   2. every pixel q of R (one per thread) gathers w_br[s] v_br(q - s) over the s whose q - s lies outside the image:
+//      whole window rows / columns selected by two 5-bit masks, so a non-corner pixel visits 5 or 10 taps.
+// ncu on the first version (window scan, 25-tap loops per pixel): 36.6 M warp instructions per level-1 launch, issue-
+// bound at 64 us; the per-channel record wrec (25 x float4 embedded branch taps | c2 | c0, written by
+// dw_fin_bwd2_kernel) is read through the read-only path, no prologue barrier.
 // ---------------------------------------------------------------------------------------------------
 constexpr int kFrameThreads = 128;
-constexpr int kFrameSeg = 128;
-constexpr int kFrameLocal = (kFrameSeg + 4) * 6;       // positions of the local window: (2 + 4) x (segment + 4)
-constexpr int kWrecStride = 27;                        // float4 per channel
+constexpr int kFrameSeg = 60;                           // 2 x (60 + 4) outside positions = one per thread
+constexpr int kFrameLocal = (kFrameSeg + 4) * 6;        // positions of the local window: (2 + 4) x (segment + 4)
+constexpr int kWrecStride = 27;                         // float4 per channel
+
+// v(p) for one outside position: `rows` = the taps that reach into the image form rows of the 5 x 5 window (p above /
+// below the image), else columns (p left / right of it).  Two lines (10 predicated loads) are fetched together before
+// any FMA consumes them: one memory latency per position except at corners and on tiny planes.
+template <typename T>
+__device__ __forceinline__ float4 dw_frame_value(const T* __restrict__ xp, const float4* __restrict__ wr, int pr, int pc, int H, int W,
+                                                 bool rows, const float4& c2, const float4& c0v) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int l0 = rows ? max(0, 2 - pr) : max(0, 2 - pc), l1 = rows ? min(4, H + 1 - pr) : min(4, W + 1 - pc);
+#pragma unroll 1
+    for (int l = l0; l <= l1; l += 2) {
+        const bool two = l + 1 <= l1;
+        const int lb = min(l + 1, 4);
+        float xa[5], xb[5];
+        if (rows) {
+            const T* row = xp + (int64_t)(pr + l - 2) * W + pc - 2;
+#pragma unroll
+            for (int t = 0; t < 5; ++t) {
+                const bool ok = (unsigned)(pc + t - 2) < (unsigned)W;
+                xa[t] = ok ? to_f(row[t]) : 0.f;
+                xb[t] = (ok && two) ? to_f(row[W + t]) : 0.f;
+            }
+        } else {
+            const T* col = xp + (int64_t)(pr - 2) * W + pc + l - 2;
+#pragma unroll
+            for (int t = 0; t < 5; ++t) {
+                const bool ok = (unsigned)(pr + t - 2) < (unsigned)H;
+                xa[t] = ok ? to_f(col[(int64_t)t * W]) : 0.f;
+                xb[t] = (ok && two) ? to_f(col[(int64_t)t * W + 1]) : 0.f;
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < 5; ++t) {
+            const float4 wa = __ldg(wr + (rows ? l * 5 + t : t * 5 + l)), wb = __ldg(wr + (rows ? lb * 5 + t : t * 5 + lb));
+            v.x = fmaf(wa.x, xa[t], fmaf(wb.x, xb[t], v.x)); v.y = fmaf(wa.y, xa[t], fmaf(wb.y, xb[t], v.y));
+            v.z = fmaf(wa.z, xa[t], fmaf(wb.z, xb[t], v.z)); v.w = fmaf(wa.w, xa[t], fmaf(wb.w, xb[t], v.w));
+        }
+    }
+    v.x = fmaf(c2.x, v.x, c0v.x); v.y = fmaf(c2.y, v.y, c0v.y);
+    v.z = fmaf(c2.z, v.z, c0v.z); v.w = fmaf(c2.w, v.w, c0v.w);
+    return v;
+}
 
 template <typename T>
-__global__ void __launch_bounds__(kFrameThreads, 6)
+__global__ void __launch_bounds__(kFrameThreads, 8)
 dw_bwd_frame_kernel(const T* __restrict__ x, T* __restrict__ dx, const float4* __restrict__ wrec, DwGeom g) {
     __shared__ float4 s_v[kFrameLocal];
     const int plane = blockIdx.x, e = plane % g.E;
@@ -493,87 +537,85 @@ dw_bwd_frame_kernel(const T* __restrict__ x, T* __restrict__ dx, const float4* _
     const float4* wr = wrec + (int64_t)e * kWrecStride;
     const T* xp = x + (int64_t)plane * H * W;
     T* dxp = dx + (int64_t)plane * H * W;
-    // the (at most two) pixels this thread patches in phase 2: fetch their dx now
-    const int rw = c1 - c0, count = (r1 - r0) * rw;       // <= 2 * kFrameSeg
-    float dx_old[2] = {0.f, 0.f};
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-        const int i = threadIdx.x + j * kFrameThreads;
-        if (i < count) {
-            const int qlr = i / rw, qlc = i - qlr * rw;
-            dx_old[j] = to_f(dxp[(int64_t)(r0 + qlr) * W + c0 + qlc]);
-        }
-    }
-    // ---- phase 1: outside positions of the window [r0 - 2, r1 + 2) x [c0 - 2, c1 + 2)
+    const int t = threadIdx.x;
+    // the pixel this thread patches in phase 2: fetch its dx now
+    const int rw = c1 - c0, count = (r1 - r0) * rw;       // <= 2 * kFrameSeg <= kFrameThreads
+    const int qlr = t / rw, qlc = t - qlr * rw;
+    const int qr = r0 + qlr, qc = c0 + qlc;
+    float dx_old = 0.f;
+    if (t < count) dx_old = to_f(dxp[(int64_t)qr * W + qc]);
+    // ---- phase 1: outside positions of the window [r0 - 2, r1 + 2) x [c0 - 2, c1 + 2), index (lr, lc) -> lr * lw + lc
     const float4 c2 = __ldg(wr + 25), c0v = __ldg(wr + 26);
     const int lw = c1 - c0 + 4, lh = r1 - r0 + 4;
-    for (int i = threadIdx.x; i < lw * lh; i += kFrameThreads) {
-        const int lr = i / lw, lc = i - lr * lw;
-        const int pr = r0 - 2 + lr, pc = c0 - 2 + lc;
-        if ((unsigned)pr < (unsigned)H && (unsigned)pc < (unsigned)W) continue;       // inside the image: never read
-        // The taps that reach into the image form at most 2 rows (top / bottom sides) or 2 columns (left / right sides)
-        // of the 5 x 5 window, except at the corners: walk that short direction in a rolled loop that skips the
-        // out-of-image lines, with the 5 loads of a line unrolled and predicated (in flight together).
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (side < 2) {
-#pragma unroll 1
-            for (int ta = 0; ta < 5; ++ta) {
-                const int rr = pr + ta - 2;
-                if ((unsigned)rr >= (unsigned)H) continue;
-                const T* row = xp + (int64_t)rr * W + pc - 2;
-                float xv[5];
-#pragma unroll
-                for (int tb = 0; tb < 5; ++tb) xv[tb] = (unsigned)(pc + tb - 2) < (unsigned)W ? to_f(row[tb]) : 0.f;
-#pragma unroll
-                for (int tb = 0; tb < 5; ++tb) {
-                    const float4 w = __ldg(wr + ta * 5 + tb);
-                    v.x = fmaf(w.x, xv[tb], v.x); v.y = fmaf(w.y, xv[tb], v.y); v.z = fmaf(w.z, xv[tb], v.z); v.w = fmaf(w.w, xv[tb], v.w);
-                }
-            }
-        } else {
-#pragma unroll 1
-            for (int tb = 0; tb < 5; ++tb) {
-                const int cc = pc + tb - 2;
-                if ((unsigned)cc >= (unsigned)W) continue;
-                const T* col = xp + (int64_t)(pr - 2) * W + cc;
-                float xv[5];
-#pragma unroll
-                for (int ta = 0; ta < 5; ++ta) xv[ta] = (unsigned)(pr + ta - 2) < (unsigned)H ? to_f(col[(int64_t)ta * W]) : 0.f;
-#pragma unroll
-                for (int ta = 0; ta < 5; ++ta) {
-                    const float4 w = __ldg(wr + ta * 5 + tb);
-                    v.x = fmaf(w.x, xv[ta], v.x); v.y = fmaf(w.y, xv[ta], v.y); v.z = fmaf(w.z, xv[ta], v.z); v.w = fmaf(w.w, xv[ta], v.w);
-                }
+    if (side < 2) {
+        // rows above (top side) or below (bottom side) the image: window rows 0, 1 resp. lh - 2, lh - 1
+        const int k = t / lw, lc = t - k * lw;
+        if (k < 2) {
+            const int lr = side == 0 ? k : lh - 2 + k;
+            s_v[lr * lw + lc] = dw_frame_value(xp, wr, r0 - 2 + lr, c0 - 2 + lc, H, W, true, c2, c0v);
+        }
+        // on planes shorter than the window the other vertical side is within reach as well
+        if (side == 0 ? r1 + 2 > H : r0 - 2 < 0) {
+            for (int i = t; i < lw * lh; i += kFrameThreads) {
+                const int lr = i / lw, pr = r0 - 2 + lr;
+                if (side == 0 ? pr >= H : pr < 0) s_v[i] = dw_frame_value(xp, wr, pr, c0 - 2 + (i - lr * lw), H, W, true, c2, c0v);
             }
         }
-        v.x = fmaf(c2.x, v.x, c0v.x); v.y = fmaf(c2.y, v.y, c0v.y);
-        v.z = fmaf(c2.z, v.z, c0v.z); v.w = fmaf(c2.w, v.w, c0v.w);
-        s_v[i] = v;
+        // positions beside the rows of the window that lie inside the image: only where R touches a corner of the plane
+        if (c0 < 2 || c1 + 2 > W) {
+            for (int i = t; i < lh * 4; i += kFrameThreads) {
+                const int lr = i >> 2, j = i & 3;
+                const int lc = j < 2 ? j : lw - 4 + j;                      // window columns 0, 1, lw - 2, lw - 1
+                const int pr = r0 - 2 + lr, pc = c0 - 2 + lc;
+                if ((unsigned)pr < (unsigned)H && (unsigned)pc >= (unsigned)W)
+                    s_v[lr * lw + lc] = dw_frame_value(xp, wr, pr, pc, H, W, false, c2, c0v);
+            }
+        }
+    } else {
+        // columns left (side 2) or right (side 3) of the image: window columns 0, 1 resp. lw - 2, lw - 1; every window
+        // row lies inside the image (R excludes the top and bottom frame rows)
+        const int k = t / lh, lr = t - k * lh;
+        if (k < 2) {
+            const int lc = side == 2 ? k : lw - 2 + k;
+            s_v[lr * lw + lc] = dw_frame_value(xp, wr, r0 - 2 + lr, c0 - 2 + lc, H, W, false, c2, c0v);
+        }
+        // planes narrower than the window: the other horizontal side is within reach as well
+        if (side == 2 ? c1 + 2 > W : c0 - 2 < 0) {
+            for (int i = t; i < lw * lh; i += kFrameThreads) {
+                const int lr2 = i / lw, lc2 = i - lr2 * lw, pc = c0 - 2 + lc2;
+                if (side == 2 ? pc >= W : pc < 0) s_v[i] = dw_frame_value(xp, wr, r0 - 2 + lr2, pc, H, W, false, c2, c0v);
+            }
+        }
     }
     __syncthreads();
-    // ---- phase 2: the pixels of R
+    // ---- phase 2: one pixel of R per thread
+    if (t >= count) return;
+    uint32_t rmask = 0u, cmask = 0u;                      // bit sa / sb: window row / column of q - s outside the image
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-        const int i = threadIdx.x + j * kFrameThreads;
-        if (i >= count) break;
-        const int qlr = i / rw, qlc = i - qlr * rw;
-        const int qr = r0 + qlr, qc = c0 + qlc;
-        float acc = 0.f;
-#pragma unroll 1
-        for (int sa = 0; sa < 5; ++sa) {
-            const int pr = qr - (sa - 2);
-            const bool rin = (unsigned)pr < (unsigned)H;
+    for (int k = 0; k < 5; ++k) {
+        rmask |= ((unsigned)(qr - (k - 2)) >= (unsigned)H ? 1u : 0u) << k;
+        cmask |= ((unsigned)(qc - (k - 2)) >= (unsigned)W ? 1u : 0u) << k;
+    }
+    float acc = 0.f;
+#pragma unroll
+    for (int sa = 0; sa < 5; ++sa) {
+        const float4* vrow = s_v + (qlr + 4 - sa) * lw + qlc + 4;
+        if ((rmask >> sa) & 1u) {
 #pragma unroll
             for (int sb = 0; sb < 5; ++sb) {
-                const int pc = qc - (sb - 2);
-                if (rin && (unsigned)pc < (unsigned)W) continue;
-                const float4 v = s_v[(qlr + 4 - sa) * lw + (qlc + 4 - sb)];
-                const float4 w = __ldg(wr + sa * 5 + sb);
+                const float4 v = vrow[-sb], w = __ldg(wr + sa * 5 + sb);
                 acc = fmaf(w.x, v.x, fmaf(w.y, v.y, fmaf(w.z, v.z, fmaf(w.w, v.w, acc))));
             }
+        } else if (cmask != 0u) {
+#pragma unroll
+            for (int sb = 0; sb < 5; ++sb)
+                if ((cmask >> sb) & 1u) {
+                    const float4 v = vrow[-sb], w = __ldg(wr + sa * 5 + sb);
+                    acc = fmaf(w.x, v.x, fmaf(w.y, v.y, fmaf(w.z, v.z, fmaf(w.w, v.w, acc))));
+                }
         }
-        dxp[(int64_t)qr * W + qc] = from_f<T>(dx_old[j] + acc);
     }
+    dxp[(int64_t)qr * W + qc] = from_f<T>(dx_old + acc);
 }
 
 }  // namespace lmnet
