@@ -187,6 +187,23 @@ int lmnet_reparam_dw_eval_fwd(const void* x, const lmnet_dw_params* p, const flo
                               void* z, float* pool, void* workspace, size_t workspace_bytes,
                               const lmnet_dw_dims* dims, int dtype, void* stream);
 
+/* ---- training loss of the reference loop in one pass per direction (widening step f4) -------------
+ * loss = CrossEntropyLoss(weight = ce_weight, label_smoothing)(logits, labels)      /root/reference/train.py:157
+ *      + DiceLoss(C)(logits, labels, weight = dice_weight, softmax = True)           /root/reference/utils/loss.py:170-206
+ * as summed in /root/reference/utils/train_eval_utils.py:141-142.  logits [B,C,H,W] contiguous of `dtype`, labels int64
+ * [B,H,W] with values in [0,C), weights fp32 [C]; fp32 arithmetic, fixed-order reductions, no host synchronisation.
+ * stats: fp32 [lmnet_seg_loss_stats_floats(C)], stats[0] = the loss, the rest feeds the backward.
+ * dloss: device pointer to the upstream gradient of the scalar (fp32).  C in {2, 3, 4, 8}. */
+int lmnet_seg_loss_supported(int C, int dtype);
+size_t lmnet_seg_loss_workspace_bytes(int C);
+int lmnet_seg_loss_stats_floats(int C);
+int lmnet_seg_loss_fwd(const void* logits, const int64_t* labels, const float* ce_weight, const float* dice_weight,
+                       float label_smoothing, float* stats, void* workspace, size_t workspace_bytes, int64_t B, int C,
+                       int64_t HW, int dtype, void* stream);
+int lmnet_seg_loss_bwd(const void* logits, const int64_t* labels, const float* ce_weight, const float* dice_weight,
+                       float label_smoothing, const float* stats, const float* dloss, void* dlogits, int64_t B, int C,
+                       int64_t HW, int dtype, void* stream);
+
 /* ---- fused BatchNorm2d + activation on NCHW tensors (widening step f1/f3, SURVEY.md §8 f) -------
  * Replaces nn.BatchNorm2d followed by an activation where the reference applies them back to back:
  * expand_conv's BN + Hardswish (/root/reference/core/modules.py:537-539) and the skip blocks'

@@ -27,7 +27,7 @@ enum KernelId : int {
     KID_BN_STATS, KID_BN_FIN_FWD, KID_BN_APPLY, KID_BN_BWD_REDUCE, KID_BN_FIN_BWD, KID_BN_BWD_APPLY,
     KID_LN_FWD, KID_LN_BWD, KID_LN_BWD_PARAMS,
     KID_WGRAD_1X1, KID_WGRAD_REDUCE, KID_UPSAMPLE_FWD, KID_UPSAMPLE_BWD,
-    KID_NA_STREAM_FWD, KID_NA_STREAM_BWD, KID_PIXEL_GEMM, KID_CONV3X3, KID_CONV3X3_WGRAD, KID_CONV3X3_REDUCE, KID_SE_GATE_FWD, KID_SE_GATE_BWD, KID_AVGPOOL_FWD, KID_AVGPOOL_BWD, KID_DW_BWD_FRAME,
+    KID_NA_STREAM_FWD, KID_NA_STREAM_BWD, KID_PIXEL_GEMM, KID_CONV3X3, KID_CONV3X3_WGRAD, KID_CONV3X3_REDUCE, KID_SE_GATE_FWD, KID_SE_GATE_BWD, KID_AVGPOOL_FWD, KID_AVGPOOL_BWD, KID_DW_BWD_FRAME, KID_SEG_LOSS,
     KID_COUNT
 };
 extern bool g_profile_on;

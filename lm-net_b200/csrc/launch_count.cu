@@ -38,7 +38,7 @@ static const char* kKernelNames[KID_COUNT] = {
     "bn_stats", "bn_fin_fwd", "bn_apply", "bn_bwd_reduce", "bn_fin_bwd", "bn_bwd_apply",
     "ln_fwd", "ln_bwd", "ln_bwd_params",
     "wgrad_1x1", "wgrad_reduce", "upsample2x_fwd", "upsample2x_bwd",
-    "na2d_stream_fwd", "na2d_stream_bwd", "pixel_gemm", "conv3x3", "conv3x3_wgrad", "conv3x3_wgrad_reduce", "se_gate_fwd", "se_gate_bwd", "avgpool_fwd", "avgpool_bwd", "dw_bwd_frame"};
+    "na2d_stream_fwd", "na2d_stream_bwd", "pixel_gemm", "conv3x3", "conv3x3_wgrad", "conv3x3_wgrad_reduce", "se_gate_fwd", "se_gate_bwd", "avgpool_fwd", "avgpool_bwd", "dw_bwd_frame", "seg_loss"};
 }  // namespace lmnet
 
 extern "C" int lmnet_profile_enable(int on) {

@@ -124,6 +124,14 @@ def lib():
                                                   pdd, c_int, c_void_p]
     L.lmnet_reparam_dw_train_bwd_gram.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, pp, c_void_p, c_void_p, c_void_p,
                                                   c_void_p, pg, c_void_p, c_size_t, pdd, c_int, c_void_p]
+    L.lmnet_seg_loss_workspace_bytes.restype = c_size_t
+    L.lmnet_seg_loss_workspace_bytes.argtypes = [c_int]
+    L.lmnet_seg_loss_supported.argtypes = [c_int, c_int]
+    L.lmnet_seg_loss_stats_floats.argtypes = [c_int]
+    L.lmnet_seg_loss_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_size_t, c_int64, c_int,
+                                     c_int64, c_int, c_void_p]
+    L.lmnet_seg_loss_bwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_int64, c_int,
+                                     c_int64, c_int, c_void_p]
     pbd = POINTER(BnDims)
     L.lmnet_bn_act_workspace_bytes.restype = c_size_t
     L.lmnet_bn_act_workspace_bytes.argtypes = [pbd]
