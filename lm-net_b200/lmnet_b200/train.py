@@ -76,8 +76,31 @@ def build_training(model: nn.Module, device, lr=1e-3, weight_decay=1e-4, smoothi
     return optimizer, criterion, criterion_dice
 
 
+_DICE_WEIGHT = (1.0, 4.0)          # utils/train_eval_utils.py:142
+
+
+def _fused_loss_args(output, labels, criterion, criterion_dice):
+    """(ce_weight, label_smoothing) when the two criteria are the reference's pair and the fused kernel applies."""
+    if not (output.is_cuda and isinstance(criterion_dice, DiceLoss) and criterion_dice.n_classes == output.shape[1]):
+        return None
+    if isinstance(criterion, WeightedSmoothedCE):
+        w, eps = criterion.weight, criterion.eps
+    elif isinstance(criterion, nn.CrossEntropyLoss) and criterion.reduction == "mean" and criterion.weight is not None:
+        w, eps = criterion.weight, criterion.label_smoothing
+    else:
+        return None
+    from .segloss import seg_loss_supported
+    return (w, eps) if seg_loss_supported(output, labels) else None
+
+
 def loss_fn(output, labels, criterion, criterion_dice):
-    return criterion(output, labels) + criterion_dice(output, labels.unsqueeze(1).float(), weight=[1.0, 4.0])
+    """criterion(output, labels) + criterion_dice(output, labels.unsqueeze(1).float(), weight=[1, 4])
+    (utils/train_eval_utils.py:141-142); on a CUDA device one fused op (csrc/seg_loss.cu)."""
+    fused = _fused_loss_args(output, labels, criterion, criterion_dice)
+    if fused is not None:
+        from .segloss import seg_loss
+        return seg_loss(output, labels, fused[0], fused[1], _DICE_WEIGHT)
+    return criterion(output, labels) + criterion_dice(output, labels.unsqueeze(1).float(), weight=list(_DICE_WEIGHT))
 
 
 def train_step(model, optimizer, images, labels, criterion, criterion_dice, amp_dtype=torch.bfloat16):
