@@ -20,7 +20,8 @@
 //       Q_br[t] = sum_p y_br(p) x~(p+t)                        (a function of x and w only: taken in the FORWARD
 //                                                              statistics pass, where y_br exists anyway)
 //
-// So the backward tile kernel is ONE phase of Toeplitz MMAs (5 rows of du, hi + lo taps; 9 rows of x) into one
+// So the backward tile kernel is ONE phase of Toeplitz MMAs (5 rows of du, 9 rows of x; taps rounded to the storage
+// type like the reference's own 16-bit convolution weights, -DLMNET_DX2_SPLIT_TAPS adds the rounding remainder) into one
 // accumulator set — no dy tiles, no CTA barrier, no Gram accumulators, the apply kernel's register budget (4 CTAs per
 // SM) — and the forward statistics kernel gains the Gram products of its own y_br fragments (through a 1 KB per-warp
 // shared-memory transpose).
@@ -411,7 +412,9 @@ dw_bwd_dx2_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                 uint32_t A[4];
                 load_a(s_du, 16 * wr + a, 32 * wc + 8 * cbk, lane, A);
                 MmaOp<T>::run(acc[cbk], A, Fhi[a]);
+#if defined(LMNET_DX2_SPLIT_TAPS)
                 MmaOp<T>::run(acc[cbk], A, Flo[a]);
+#endif
             }
         __syncwarp();
         if (lane == 0) {

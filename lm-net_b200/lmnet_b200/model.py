@@ -205,8 +205,8 @@ class GlobalAttention(nn.Module):
 
     def forward(self, x):
         B, N, C = x.shape
-        q, k, v = self.qkv(x).reshape(B, N, 3, self.num_heads, self.head_dim).permute(2, 0, 3, 1, 4)
-        if q.is_cuda and q.dtype in (torch.bfloat16, torch.float16) and (self.attn_drop.p == 0.0 or not self.training):
+        qkv = self.qkv(x).reshape(B, N, 3, self.num_heads, self.head_dim)
+        if qkv.is_cuda and qkv.dtype in (torch.bfloat16, torch.float16) and (self.attn_drop.p == 0.0 or not self.training):
             # 16-bit storage: one fused attention kernel per direction (PyTorch's flash SDPA) instead of materialising
             # the [B, heads, 484, 484] attention matrix — with autocast the explicit form also round-trips it through
             # fp32 for the softmax: 4 cast kernels + 2 softmax + 6 small GEMMs, 1.2 ms of the step
@@ -214,11 +214,13 @@ class GlobalAttention(nn.Module):
             # zeros change neither q.k nor the kept output columns.  fp32 storage keeps the explicit form (1e-4 parity).
             pad = (-self.head_dim) % 8
             if pad:
-                q, k, v = (F.pad(t, (0, pad)) for t in (q, k, v))
+                qkv = F.pad(qkv, (0, pad))                    # one copy of the packed tensor (and one slice in the backward)
+            q, k, v = qkv.permute(2, 0, 3, 1, 4)
             o = F.scaled_dot_product_attention(q, k, v, scale=self.scale)
             if pad:
                 o = o[..., :self.head_dim]
             return self.proj_drop(self.proj(o.transpose(1, 2).reshape(B, N, C)))
+        q, k, v = qkv.permute(2, 0, 3, 1, 4)
         attn = self.attn_drop(((q @ k.transpose(-2, -1)) * self.scale).softmax(dim=-1))
         return self.proj_drop(self.proj((attn @ v).transpose(1, 2).reshape(B, N, C)))
 

@@ -37,7 +37,8 @@ def main():
     for _ in range(3):
         train_step(net, opt, img, msk, crit, dice)
     torch.cuda.synchronize()
-    with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=True, with_stack=True) as prof:
+    with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=True, with_stack=True,
+                 experimental_config=torch._C._profiler._ExperimentalConfig(verbose=True)) as prof:
         train_step(net, opt, img, msk, crit, dice)
         torch.cuda.synchronize()
     agg = collections.defaultdict(lambda: [0, 0.0])
@@ -51,9 +52,11 @@ def main():
             continue
         where = "?"
         for fr in (e.stack or []):
-            if "/lm-net_b200/" in fr or "/tools/" in fr or "bench.py" in fr:
+            if ("/lm-net_b200/" in fr or "/tools/" in fr or "bench.py" in fr) and "train.py" not in fr:
                 where = fr.split("/repo/")[-1][:90]
                 break
+        if where == "?" and e.stack:
+            where = "bwd/" + e.stack[0][-60:]
         key = (e.name, str(e.input_shapes)[:70], where)
         agg[key][0] += 1
         agg[key][1] += t
