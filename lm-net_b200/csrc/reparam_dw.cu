@@ -370,34 +370,45 @@ dw_stats_kernel(const T* __restrict__ x, lmnet_dw_params p, float* __restrict__ 
 
 // per-channel finalize of the forward statistics: mean / rstd, running-stat update, merged 5x5 kernel
 // coef[e][0..24] = merged taps, coef[e][25] = bias
-__global__ void dw_fin_fwd_kernel(const float* __restrict__ part, int ncta, int part_stride, lmnet_dw_params p,
-                                  float* __restrict__ save_mean, float* __restrict__ save_rstd, float* __restrict__ coef,
-                                  float* __restrict__ gram /* [E][40] or null */, float eps, float momentum,
-                                  int64_t* nbt0, int64_t* nbt1, int64_t* nbt2, int64_t* nbt3, DwGeom g) {
-    // warp 0: lanes 0..7 each reduce one of the 8 partial sums over the CTAs, lane 0 finishes; with `gram` (launched
-    // with 64 threads) threads 8..47 reduce the 40 lag sums of the statistics + Gram pass (reparam_dw_tma2.cuh)
-    const int e = blockIdx.x;
+// Sum of n floats, `stride` apart, by ONE warp: lane l takes c = l, l + 32, ... (independent loads), then a fixed-order
+// shuffle tree in double => deterministic.  A single thread walking the per-CTA partials is a chain of dependent loads:
+// 36 partials x ~0.4 us made the finalize kernels 10-15 us each (48 launches per step, tools/bench_dw.py).
+__device__ __forceinline__ double warp_sum_strided(const float* __restrict__ p, int n, int64_t stride, int lane) {
+    double a = 0;
+    for (int c = lane; c < n; c += 32) a += (double)p[(int64_t)c * stride];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_down_sync(0xffffffffu, a, o);
+    return a;
+}
+
+constexpr int kFinThreads = 256;
+
+__global__ void __launch_bounds__(kFinThreads)
+dw_fin_fwd_kernel(const float* __restrict__ part, int ncta, int part_stride, lmnet_dw_params p,
+                  float* __restrict__ save_mean, float* __restrict__ save_rstd, float* __restrict__ coef,
+                  float* __restrict__ gram /* [E][40] or null */, float eps, float momentum,
+                  int64_t* nbt0, int64_t* nbt1, int64_t* nbt2, int64_t* nbt3, DwGeom g) {
+    // one CTA per channel; every warp reduces some of the 8 (+ 40 with `gram`: the lag sums of the statistics + Gram
+    // pass, reparam_dw_tma2.cuh) per-CTA partial sums, thread 0 finishes
+    const int e = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     __shared__ double s_tot[8];
-    if (threadIdx.x < 8) {
-        double a = 0;
-        for (int c = 0; c < ncta; ++c) a += part[((int64_t)e * ncta + c) * part_stride + threadIdx.x];
-        s_tot[threadIdx.x] = a;
-    } else if (gram != nullptr && threadIdx.x < 48) {
-        double a = 0;
-        for (int c = 0; c < ncta; ++c) a += part[((int64_t)e * ncta + c) * part_stride + threadIdx.x];
-        gram[e * 40 + (threadIdx.x - 8)] = (float)a;
+    const int nq = gram != nullptr ? 48 : 8;
+    for (int q = warp; q < nq; q += kFinThreads / 32) {
+        const double a = warp_sum_strided(part + (int64_t)e * ncta * part_stride + q, ncta, part_stride, lane);
+        if (lane == 0) {
+            if (q < 8) s_tot[q] = a;
+            else gram[e * 40 + (q - 8)] = (float)a;
+        }
     }
-    __syncwarp();
-    if (threadIdx.x != 0) return;
-    const double n = (double)g.B * g.H * g.W;
-    double sum[4], sq[4];
-    for (int k = 0; k < 4; ++k) { sum[k] = s_tot[k]; sq[k] = s_tot[4 + k]; }
-    float m5[25];
-    for (int t = 0; t < 25; ++t) m5[t] = 0.f;
-    float bias = 0.f;
-    for (int k = 0; k < 4; ++k) {
-        const double mean = sum[k] / n;
-        double var = sq[k] / n - mean * mean;
+    __syncthreads();
+    // four threads finish one branch each; 25 threads merge one tap each (a single thread walking 4 branches x 40
+    // dependent parameter loads made this launch 10-15 us)
+    __shared__ float s_a[4], s_b[4];
+    if (threadIdx.x < 4) {
+        const int k = threadIdx.x;
+        const double n = (double)g.B * g.H * g.W;
+        const double mean = s_tot[k] / n;
+        double var = s_tot[4 + k] / n - mean * mean;
         if (var < 0) var = 0;
         const float rstd = (float)(1.0 / sqrt(var + (double)eps));
         save_mean[k * g.E + e] = (float)mean;
@@ -408,19 +419,26 @@ __global__ void dw_fin_fwd_kernel(const float* __restrict__ part, int ncta, int 
             p.running_var[k][e] = (1.f - momentum) * p.running_var[k][e] + momentum * (float)unbiased;
         }
         const float a = p.gamma[k][e] * rstd;
-        bias += p.beta[k][e] - a * (float)mean;
-        if (k == 0) for (int t = 0; t < 25; ++t) m5[t] += a * p.w[0][e * 25 + t];
-        if (k == 1) for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) m5[(i + 1) * 5 + j + 1] += a * p.w[1][e * 9 + i * 3 + j];
-        if (k == 2) for (int i = 0; i < 3; ++i) m5[(i + 1) * 5 + 2] += a * p.w[2][e * 3 + i];
-        if (k == 3) for (int j = 0; j < 3; ++j) m5[2 * 5 + j + 1] += a * p.w[3][e * 3 + j];
+        s_a[k] = a;
+        s_b[k] = p.beta[k][e] - a * (float)mean;
     }
-    for (int t = 0; t < 25; ++t) coef[e * 26 + t] = m5[t];
-    coef[e * 26 + 25] = bias;
-    if (e == 0) {
-        if (nbt0) *nbt0 += 1;
-        if (nbt1) *nbt1 += 1;
-        if (nbt2) *nbt2 += 1;
-        if (nbt3) *nbt3 += 1;
+    __syncthreads();
+    if (threadIdx.x < 25) {
+        const int t = threadIdx.x, i = t / 5, j = t % 5;
+        float m = s_a[0] * p.w[0][e * 25 + t];                 // same accumulation order as the single-thread version
+        if (i >= 1 && i <= 3 && j >= 1 && j <= 3) m += s_a[1] * p.w[1][e * 9 + (i - 1) * 3 + (j - 1)];
+        if (i >= 1 && i <= 3 && j == 2) m += s_a[2] * p.w[2][e * 3 + (i - 1)];
+        if (i == 2 && j >= 1 && j <= 3) m += s_a[3] * p.w[3][e * 3 + (j - 1)];
+        coef[e * 26 + t] = m;
+    }
+    if (threadIdx.x == 32) {
+        coef[e * 26 + 25] = ((s_b[0] + s_b[1]) + s_b[2]) + s_b[3];
+        if (e == 0) {
+            if (nbt0) *nbt0 += 1;
+            if (nbt1) *nbt1 += 1;
+            if (nbt2) *nbt2 += 1;
+            if (nbt3) *nbt3 += 1;
+        }
     }
 }
 
@@ -505,11 +523,11 @@ dw_apply_kernel(const T* __restrict__ x, const float* __restrict__ coef, T* __re
 }
 
 __global__ void dw_pool_fin_kernel(const float* __restrict__ pool_part, int ncta, float inv_hw, float* __restrict__ pool, int n) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    // one warp per (image, channel)
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (i >= n) return;
-    float a = 0.f;
-    for (int c = 0; c < ncta; ++c) a += pool_part[(int64_t)i * ncta + c];
-    pool[i] = a * inv_hw;
+    const double a = warp_sum_strided(pool_part + (int64_t)i * ncta, ncta, 1, lane);
+    if (lane == 0) pool[i] = (float)a * inv_hw;
 }
 
 // =================================================================================================
@@ -966,13 +984,13 @@ static int dw_train_fwd(const void* x, const lmnet_dw_params* p, void* u, void* 
                 const DwGeom gg = dw_geom(d, kMmaTH, kMmaTW, kStatsGramOcc, kFwdShift);
                 const dim3 grid_g(gg.stripes, gg.bands, gg.E);
                 LMNET_LAUNCH(KID_DW_STATS, st, 1 * t_bytes, (dw_stats_gram_tma_kernel<T><<<grid_g, kTmaThreads, kStatsGramSmem, st>>>(tm_x, *p, part, gg)));
-                LMNET_LAUNCH(KID_DW_FIN_FWD, st, 0, (dw_fin_fwd_kernel<<<g.E, 64, 0, st>>>(part, gg.stripes * gg.bands, kGramPartStride, *p, save_mean, save_rstd, coef, save_gram, eps, momentum,
+                LMNET_LAUNCH(KID_DW_FIN_FWD, st, 0, (dw_fin_fwd_kernel<<<g.E, kFinThreads, 0, st>>>(part, gg.stripes * gg.bands, kGramPartStride, *p, save_mean, save_rstd, coef, save_gram, eps, momentum,
                                                                  nbt ? nbt[0] : nullptr, nbt ? nbt[1] : nullptr,
                                                                  nbt ? nbt[2] : nullptr, nbt ? nbt[3] : nullptr, g)));
                 *gram_saved = 1;
             } else {
                 LMNET_LAUNCH(KID_DW_STATS, st, 1 * t_bytes, (dw_stats_tma_kernel<T><<<grid_s, kTmaThreads, kStatsSmem, st>>>(tm_x, *p, part, gs)));
-                LMNET_LAUNCH(KID_DW_FIN_FWD, st, 0, (dw_fin_fwd_kernel<<<g.E, 32, 0, st>>>(part, ncta_s, 8, *p, save_mean, save_rstd, coef, nullptr, eps, momentum,
+                LMNET_LAUNCH(KID_DW_FIN_FWD, st, 0, (dw_fin_fwd_kernel<<<g.E, kFinThreads, 0, st>>>(part, ncta_s, 8, *p, save_mean, save_rstd, coef, nullptr, eps, momentum,
                                                                  nbt ? nbt[0] : nullptr, nbt ? nbt[1] : nullptr,
                                                                  nbt ? nbt[2] : nullptr, nbt ? nbt[3] : nullptr, g)));
             }
@@ -983,7 +1001,7 @@ static int dw_train_fwd(const void* x, const lmnet_dw_params* p, void* u, void* 
             LMNET_LAUNCH(KID_DW_APPLY, st, 2 * t_bytes, (dw_apply_tma_kernel<T><<<grid_s, kTmaThreads, kApplySmem, st>>>(tm_x, tm_u, tm_z, coef, (T*)u, (T*)z, pool ? pool_part : nullptr, gs)));
             if (pool) {
                 const int n = g.B * g.E;
-                LMNET_LAUNCH(KID_DW_POOL_FIN, st, 0, (dw_pool_fin_kernel<<<(n + 127) / 128, 128, 0, st>>>(pool_part, ncta_s * kDwWarps, 1.f / ((float)g.H * g.W), pool, n)));
+                LMNET_LAUNCH(KID_DW_POOL_FIN, st, 0, (dw_pool_fin_kernel<<<(n + 3) / 4, 128, 0, st>>>(pool_part, ncta_s * kDwWarps, 1.f / ((float)g.H * g.W), pool, n)));
             }
             return LMNET_OK;
         }
@@ -995,7 +1013,7 @@ static int dw_train_fwd(const void* x, const lmnet_dw_params* p, void* u, void* 
         return LMNET_OK;
     });
     if (rc != LMNET_OK) return rc;
-    LMNET_LAUNCH(KID_DW_FIN_FWD, st, 0, (dw_fin_fwd_kernel<<<g.E, 32, 0, st>>>(part, ncta, 8, *p, save_mean, save_rstd, coef, nullptr, eps, momentum,
+    LMNET_LAUNCH(KID_DW_FIN_FWD, st, 0, (dw_fin_fwd_kernel<<<g.E, kFinThreads, 0, st>>>(part, ncta, 8, *p, save_mean, save_rstd, coef, nullptr, eps, momentum,
                                                      nbt ? nbt[0] : nullptr, nbt ? nbt[1] : nullptr,
                                                      nbt ? nbt[2] : nullptr, nbt ? nbt[3] : nullptr, g)));
     if constexpr (sizeof(T) == 2) {
@@ -1009,7 +1027,7 @@ static int dw_train_fwd(const void* x, const lmnet_dw_params* p, void* u, void* 
     if (rc != LMNET_OK) return rc;
     if (pool) {
         const int n = g.B * g.E;
-        LMNET_LAUNCH(KID_DW_POOL_FIN, st, 0, (dw_pool_fin_kernel<<<(n + 127) / 128, 128, 0, st>>>(pool_part, ncta, 1.f / ((float)g.H * g.W), pool, n)));
+        LMNET_LAUNCH(KID_DW_POOL_FIN, st, 0, (dw_pool_fin_kernel<<<(n + 3) / 4, 128, 0, st>>>(pool_part, ncta, 1.f / ((float)g.H * g.W), pool, n)));
     }
     return LMNET_OK;
 }
@@ -1044,7 +1062,7 @@ static int dw_eval_fwd(const void* x, const lmnet_dw_params* p, const float* bia
             LMNET_LAUNCH(KID_DW_APPLY, st, 2 * t_bytes, (dw_apply_tma_kernel<T><<<grid_s, kTmaThreads, kApplySmem, st>>>(tm_x, tm_z, tm_z, coef, (T*)nullptr, (T*)z, pool ? pool_part : nullptr, gs)));
             if (pool) {
                 const int n = g.B * g.E;
-                LMNET_LAUNCH(KID_DW_POOL_FIN, st, 0, (dw_pool_fin_kernel<<<(n + 127) / 128, 128, 0, st>>>(pool_part, ncta_s * kDwWarps, 1.f / ((float)g.H * g.W), pool, n)));
+                LMNET_LAUNCH(KID_DW_POOL_FIN, st, 0, (dw_pool_fin_kernel<<<(n + 3) / 4, 128, 0, st>>>(pool_part, ncta_s * kDwWarps, 1.f / ((float)g.H * g.W), pool, n)));
             }
             return LMNET_OK;
         }
@@ -1058,7 +1076,7 @@ static int dw_eval_fwd(const void* x, const lmnet_dw_params* p, const float* bia
     if (rc != LMNET_OK) return rc;
     if (pool) {
         const int n = g.B * g.E;
-        LMNET_LAUNCH(KID_DW_POOL_FIN, st, 0, (dw_pool_fin_kernel<<<(n + 127) / 128, 128, 0, st>>>(pool_part, ncta, 1.f / ((float)g.H * g.W), pool, n)));
+        LMNET_LAUNCH(KID_DW_POOL_FIN, st, 0, (dw_pool_fin_kernel<<<(n + 3) / 4, 128, 0, st>>>(pool_part, ncta, 1.f / ((float)g.H * g.W), pool, n)));
     }
     return LMNET_OK;
 }
@@ -1111,7 +1129,7 @@ static int dw_train_bwd(const void* x, const void* u, const void* dz, const floa
                 if (!dw_tma_smem(dw_bwd_dx2_tma_kernel<T>, kDx2Smem, granted_x2)) return LMNET_ERR_LAUNCH;
                 float* coef2 = (float*)(ws + L.coef2);
                 float4* wrec = (float4*)(ws + L.wrec);
-                LMNET_LAUNCH(KID_DW_FIN_BWD, st, 0, (dw_fin_bwd2_kernel<<<g.E, 128, 0, st>>>(part, gr_.stripes * gr_.bands, *p, save_mean, save_rstd, gram, *gr, cb, coef2, wrec, g)));
+                LMNET_LAUNCH(KID_DW_FIN_BWD, st, 0, (dw_fin_bwd2_kernel<<<g.E, kFinThreads, 0, st>>>(part, gr_.stripes * gr_.bands, *p, save_mean, save_rstd, gram, *gr, cb, coef2, wrec, g)));
                 const DwGeom gx = dw_geom(d, kMmaTH, kMmaTW, kDx2Occ, kDx2Shift);
                 const dim3 grid_x(gx.stripes, gx.bands, gx.E);
                 LMNET_LAUNCH(KID_DW_BWD_DX, st, 3 * t_bytes, (dw_bwd_dx2_tma_kernel<T><<<grid_x, kTmaThreads, kDx2Smem, st>>>(tm_x2, tm_du, tm_dx, coef2, (T*)dx, gx)));

@@ -215,7 +215,7 @@ __device__ __forceinline__ float dw_tap5(const lmnet_dw_params& p, int k, int e,
     return (a == 2 && b >= 1 && b <= 3) ? p.w[3][e * 3 + (b - 1)] : 0.f;
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(kFinThreads)
 dw_fin_bwd2_kernel(const float* __restrict__ part, int ncta, lmnet_dw_params p, const float* __restrict__ save_mean,
                    const float* __restrict__ save_rstd, const float* __restrict__ gram /* [E][kGramFloats] */, lmnet_dw_grads gr,
                    float* __restrict__ cb /* [E][12] */, float* __restrict__ coef2 /* [E][kCoef2Stride] */,
@@ -224,10 +224,9 @@ dw_fin_bwd2_kernel(const float* __restrict__ part, int ncta, lmnet_dw_params p, 
     __shared__ double s_P[kReducePartS];                     // P [25] | sum du | S [25]
     __shared__ float s_w[4][25];
     __shared__ double s_c[4][3];
-    if (t < 51) {
-        double a = 0;
-        for (int c = 0; c < ncta; ++c) a += part[((int64_t)e * ncta + c) * kReducePartS + t];
-        s_P[t] = a;
+    for (int q = t >> 5; q < 51; q += kFinThreads / 32) {          // one warp per partial sum (see warp_sum_strided)
+        const double a = warp_sum_strided(part + (int64_t)e * ncta * kReducePartS + q, ncta, kReducePartS, t & 31);
+        if ((t & 31) == 0) s_P[q] = a;
     }
     if (t >= 64 && t < 89) {
         const int i = t - 64;
@@ -286,22 +285,21 @@ dw_fin_bwd2_kernel(const float* __restrict__ part, int ncta, lmnet_dw_params p, 
         }
     }
     if (t >= 32 && t < 32 + 81) {
+        // fp32 is plenty for taps that are rounded to the storage type (and FP64 runs at 1/64 rate on this part: the
+        // double-precision version of this loop was most of the launch's 10 us)
         const int d = t - 32, da = d / 9 - 4, db = d % 9 - 4;
-        double v = 0;
+        float v = 0.f;
         for (int k = 0; k < 4; ++k) {
-            double acc = 0;
-            for (int sa = 0; sa < 5; ++sa) {
-                const int ta = sa + da;
-                if (ta < 0 || ta > 4) continue;
+            float acc = 0.f;
+            for (int sa = max(0, -da); sa <= min(4, 4 - da); ++sa)
+#pragma unroll
                 for (int sb = 0; sb < 5; ++sb) {
                     const int tb = sb + db;
-                    if (tb < 0 || tb > 4) continue;
-                    acc += (double)s_w[k][sa * 5 + sb] * (double)s_w[k][ta * 5 + tb];
+                    if (tb >= 0 && tb <= 4) acc = fmaf(s_w[k][sa * 5 + sb], s_w[k][(sa + da) * 5 + tb], acc);
                 }
-            }
-            v += s_c[k][1] * acc;
+            v = fmaf((float)s_c[k][1], acc, v);
         }
-        out[25 + d] = (float)(-v);
+        out[25 + d] = -v;
     }
 }
 

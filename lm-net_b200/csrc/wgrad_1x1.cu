@@ -730,6 +730,7 @@ pointwise_grads_kernel(const float* __restrict__ dW, const float* __restrict__ d
     if (i < n_wpw) {
         const int m = i / E, e = i - m * E;
         float a = 0.f;
+#pragma unroll 8                       // loads of 8 iterations in flight together instead of one dependent load -> FMA chain
         for (int b = 0; b < B; ++b) a = fmaf(dW[((int64_t)b * M + m) * N + e], gate[(int64_t)b * E + e], a);
         dwpw[i] = a;
         return;
@@ -738,6 +739,7 @@ pointwise_grads_kernel(const float* __restrict__ dW, const float* __restrict__ d
     if (i < n_gate) {
         const int b = i / E, e = i - b * E;
         float a = 0.f;
+#pragma unroll 8
         for (int m = 0; m < M; ++m) a = fmaf(dW[((int64_t)b * M + m) * N + e], __ldg(wpw + m * wpw_sm + e * wpw_se), a);
         dgate[i] = a;
         return;
@@ -746,6 +748,7 @@ pointwise_grads_kernel(const float* __restrict__ dW, const float* __restrict__ d
     if (i < n_wsc) {
         const int m = i / Cin, c = i - m * Cin;
         float a = 0.f;
+#pragma unroll 8
         for (int b = 0; b < B; ++b) a += dW[((int64_t)b * M + m) * N + E + c];
         dwsc[i] = a;
         return;
@@ -753,6 +756,7 @@ pointwise_grads_kernel(const float* __restrict__ dW, const float* __restrict__ d
     i -= n_wsc;
     if (i < M) {
         float a = 0.f;
+#pragma unroll 8
         for (int b = 0; b < B; ++b) a += drow[(int64_t)b * M + i];
         dbias[i] = a;
     }

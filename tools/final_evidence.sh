@@ -15,11 +15,14 @@ LMNET_NCU_RANGE=1 timeout 900 ncu --profile-from-start off --metrics gpu__time_d
   --clock-control none --csv --log-file /tmp/launches.csv \
   python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-profile --no-graph > gpurun_out/${R}_launches.log 2>&1
 python tools/launch_list_summary.py /tmp/launches.csv gpurun_out/${R}_launches_bench.txt gpurun_out/${R}_traffic.json | head -5
-for spec in "reparam 1 dw_|pixel_gemm|wgrad|bnact|se_gate 26" "reparam 3 dw_bwd_dx|dw_apply 4" "conv 1 conv3x3 4" "natt 1 na2d_stream|ln_|pixel_gemm 12"; do
+for spec in "reparam 1 dw_|pixel_gemm|wgrad|bnact|se_gate 28" "reparam 3 dw_bwd_dx|dw_apply|dw_stats|dw_bwd_reduce 4" "conv 1 conv3x3 4" "natt 1 na2d_stream|ln_|pixel_gemm 12" "na 1 na2d_stream 2"; do
   set -- $spec
   timeout 600 ncu --set full --clock-control none -k regex:"$3" -c $4 -o /tmp/ncu_$1_l$2 python tools/run_block.py --unit $1 --level $2 --iters 1 > gpurun_out/${R}_ncu_$1_l$2.log 2>&1
   ncu -i /tmp/ncu_$1_l$2.ncu-rep --page raw --csv > gpurun_out/${R}_ncu_$1_l$2_raw.csv 2>/dev/null
   rm -f /tmp/ncu_$1_l$2.ncu-rep
 done
-timeout 300 python tools/profile_step.py --rows 120 --out gpurun_out/${R}_step_profile_final.txt | head -4 | cut -c1-200
+timeout 300 python tools/profile_step.py --rows 130 --out gpurun_out/${R}_step_profile_final.txt | head -4 | cut -c1-200
+timeout 200 python tools/bench_dw.py --iters 5 > gpurun_out/${R}_bench_dw.txt 2>&1
+timeout 200 python tools/profile_ops.py --out gpurun_out/${R}_glue_ops.txt > /dev/null 2>&1
+timeout 100 python tools/e2e_probe.py > gpurun_out/${R}_e2e_probe.txt 2>&1
 ls -la gpurun_out | head -40
