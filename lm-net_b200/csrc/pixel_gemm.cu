@@ -466,35 +466,44 @@ static bool pg_plan(const lmnet_pgemm_dims* d, bool in1_cl, bool out_cl, bool st
         if (d->N % nchunks != 0 || (d->N / nchunks) % 4 != 0) return false;
         g.NC = d->N / nchunks;
         pl.TB = (g.NC + 7) / 8;                                  // n-tiles of 8 channels
-        if (pl.TB > kPgMaxAcc) return false;
-        pl.TA = kPgMaxAcc / pl.TB;
-        if (pl.TA > 4) pl.TA = 4;
-        if (pl.TA == 3) pl.TA = 2;
-        g.PT = kPgWarps * pl.TA * 16;
-        g.in1_pitch = in1_cl ? pg_pitch(g.K1p) : pg_pitch(g.PT);
-        g.in2_pitch = d->K2 > 0 ? pg_pitch(g.K2p) : 0;
-        g.out_pitch = pg_pitch(pl.TB * 8);
     } else {
         pl.TB = (d->N + 15) / 16;                                // m-tiles of 16 channels
-        if (pl.TB > kPgMaxAcc) return false;
-        pl.TA = kPgMaxAcc / pl.TB;
-        if (pl.TA > 4) pl.TA = 4;
-        if (pl.TA == 3) pl.TA = 2;
-        g.PT = kPgWarps * pl.TA * 8;
-        g.in1_pitch = pg_pitch(g.K1p);
-        g.in2_pitch = 0;
-        g.out_pitch = pg_pitch(g.PT);
     }
-    g.pt_shift = 0;
-    while ((8 << g.pt_shift) < g.PT) ++g.pt_shift;
-    if ((8 << g.pt_shift) != g.PT) return false;
-    const int n_pad = out_cl ? pl.TB * 8 : pl.TB * 16;
-    const size_t in1_elems = in1_cl ? (size_t)g.PT * g.in1_pitch : (size_t)g.K1p * g.in1_pitch;
-    const size_t in2_elems = d->K2 > 0 ? (size_t)g.PT * g.in2_pitch : 0;
-    const size_t out_elems = (size_t)(out_cl ? g.PT : n_pad) * g.out_pitch;
-    pl.smem = ((size_t)n_pad * g.w_pitch + 2 * (in1_elems + in2_elems) + out_elems) * 2 + (size_t)n_pad * 4 +
-              (stats ? (size_t)kPgWarps * n_pad * 2 * 4 : 0) + 16;
-    if (pl.smem > 200 * 1024) return false;
+    if (pl.TB > kPgMaxAcc) return false;
+    pl.TA = kPgMaxAcc / pl.TB;
+    if (pl.TA > 4) pl.TA = 4;
+    if (pl.TA == 3) pl.TA = 2;
+    // The pixel tile (PT = warps x TA x 16 | 8 pixels) shrinks until the double-buffered operand tiles fit: the SE-gated
+    // pointwise + shortcut GEMM of level 2 (48 planes + 24 channels-last inputs) needs 230 KB at TA = 4 and went to
+    // cuBLAS baddbmm with a broadcast copy of the bias per call.  Instantiated (TA, TB): see pg_dispatch_tiles.
+    for (;; pl.TA /= 2) {
+        if (out_cl) {
+            g.PT = kPgWarps * pl.TA * 16;
+            g.in1_pitch = in1_cl ? pg_pitch(g.K1p) : pg_pitch(g.PT);
+            g.in2_pitch = d->K2 > 0 ? pg_pitch(g.K2p) : 0;
+            g.out_pitch = pg_pitch(pl.TB * 8);
+        } else {
+            g.PT = kPgWarps * pl.TA * 8;
+            g.in1_pitch = pg_pitch(g.K1p);
+            g.in2_pitch = 0;
+            g.out_pitch = pg_pitch(g.PT);
+        }
+        g.pt_shift = 0;
+        while ((8 << g.pt_shift) < g.PT) ++g.pt_shift;
+        if ((8 << g.pt_shift) != g.PT) return false;
+        const int n_pad = out_cl ? pl.TB * 8 : pl.TB * 16;
+        const size_t in1_elems = in1_cl ? (size_t)g.PT * g.in1_pitch : (size_t)g.K1p * g.in1_pitch;
+        const size_t in2_elems = d->K2 > 0 ? (size_t)g.PT * g.in2_pitch : 0;
+        const size_t out_elems = (size_t)(out_cl ? g.PT : n_pad) * g.out_pitch;
+        pl.smem = ((size_t)n_pad * g.w_pitch + 2 * (in1_elems + in2_elems) + out_elems) * 2 + (size_t)n_pad * 4 +
+                  (stats ? (size_t)kPgWarps * n_pad * 2 * 4 : 0) + 16;
+        if (pl.smem <= 200 * 1024) break;
+        const bool smaller_exists = (pl.TA == 4 && pl.TB == 3);              // (2, 3) is the one extra instantiation
+        if (!smaller_exists) {
+            if (pl.smem <= 226 * 1024) break;                                // one CTA per SM still beats the cuBLAS detour
+            return false;
+        }
+    }
     g.tiles = (int)((d->P + g.PT - 1) / g.PT);
     int ctas_x = (2 * 148 + d->B * nchunks - 1) / (d->B * nchunks);   // ~2 CTAs per SM over the whole grid
     if (ctas_x > g.tiles) ctas_x = g.tiles;
@@ -523,7 +532,7 @@ static int pg_dispatch_tiles(const void* in1, const void* in2, const lmnet_pgemm
                              float* stats_part, const PgPlan& pl, cudaStream_t st) {
 #define PG_CASE(A, B) \
     if (pl.TA == A && pl.TB == B) return pg_launch<T, OUT_CL, IN1_CL, HAS_IN2, A, B>(in1, in2, w, bias, out, stats_part, pl, st);
-    PG_CASE(4, 1) PG_CASE(4, 2) PG_CASE(4, 3) PG_CASE(2, 4) PG_CASE(2, 5) PG_CASE(2, 6) PG_CASE(1, 7) PG_CASE(1, 8)
+    PG_CASE(4, 1) PG_CASE(4, 2) PG_CASE(4, 3) PG_CASE(2, 3) PG_CASE(2, 4) PG_CASE(2, 5) PG_CASE(2, 6) PG_CASE(1, 7) PG_CASE(1, 8)
     PG_CASE(1, 9) PG_CASE(1, 10) PG_CASE(1, 11) PG_CASE(1, 12)
 #undef PG_CASE
     return LMNET_ERR_UNSUPPORTED;

@@ -52,8 +52,8 @@ def main():
             continue
         where = "?"
         for fr in (e.stack or []):
-            if ("/lm-net_b200/" in fr or "/tools/" in fr or "bench.py" in fr) and "train.py" not in fr:
-                where = fr.split("/repo/")[-1][:90]
+            if ("lmnet_b200/" in fr or "natten/" in fr) and "train.py" not in fr and "_lib.py" not in fr:
+                where = fr.split("/repo/")[-1][-70:]
                 break
         if where == "?" and e.stack:
             where = "bwd/" + e.stack[0][-60:]
