@@ -369,6 +369,15 @@ int lmnet_conv3x3_wgrad_supported(const lmnet_conv3x3_dims* dims, int dtype);
 size_t lmnet_conv3x3_wgrad_workspace_bytes(const lmnet_conv3x3_dims* dims);
 int lmnet_conv3x3_wgrad(const void* x, const void* dy, float* dW, float* dbias, void* workspace, size_t workspace_bytes,
                         const lmnet_conv3x3_dims* dims, int dtype, void* stream);
+/* Same kernels with a pixel pitch (elements between consecutive pixels; 0 or the channel count = dense) on the tensor
+ * that autograd may hand over as a channel slice of a wider channels-last tensor — the gradient of a convolution whose
+ * output went into torch.cat (/root/reference/core/modules.py M2Skip / M3Skip, /root/reference/core/LM_Net.py:58-74):
+ * x of the forward kernel (= dy when it computes the stride-1 input gradient) and dy of the weight gradient are read in
+ * place instead of being densified first. */
+int lmnet_conv3x3_fwd_strided(const void* x, int x_pixel_pitch, const float* weight, int w_transposed, const float* bias, void* y,
+                              const lmnet_conv3x3_dims* dims, int dtype, void* stream);
+int lmnet_conv3x3_wgrad_strided(const void* x, const void* dy, int dy_pixel_pitch, float* dW, float* dbias, void* workspace,
+                                size_t workspace_bytes, const lmnet_conv3x3_dims* dims, int dtype, void* stream);
 
 /* ---- bilinear x2 up-sampling, align_corners=True, NCHW (widening step f3) ----------------------
  * Replaces nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True) of the decoder and skip blocks

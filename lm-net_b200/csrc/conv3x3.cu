@@ -159,14 +159,14 @@ conv3x3_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ dy, float* _
         T* sx = s_x + st * stage;
         cv_issue_x<T, kCvWgThreads>(sx, x, g, tl);
         T* sd = sx + x_elems;
-        const T* db = dy + (int64_t)tl.b * g.Ho * g.Wo * g.Cout;
+        const T* db = dy + (int64_t)tl.b * g.Ho * g.Wo * g.gd_pitch;
         if ((g.Cout & 7) == 0) {
             const int vpp = g.Cout >> 3;
             for (int i = threadIdx.x; i < g.TH * kCvTW * vpp; i += kCvWgThreads) {
                 const int pix = i / vpp, v = i - pix * vpp;
                 const int oy = tl.oy0 + (pix >> 4), ox = tl.ox0 + (pix & 15);
                 const bool ok = oy < g.Ho && ox < g.Wo;
-                cv_cp16(sd + pix * g.pitch_o + v * 8, ok ? db + ((int64_t)oy * g.Wo + ox) * g.Cout + v * 8 : dy, ok);
+                cv_cp16(sd + pix * g.pitch_o + v * 8, ok ? db + ((int64_t)oy * g.Wo + ox) * g.gd_pitch + v * 8 : dy, ok);
             }
         } else {
             const int vpp = g.Cout >> 2;
@@ -174,7 +174,7 @@ conv3x3_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ dy, float* _
                 const int pix = i / vpp, v = i - pix * vpp;
                 const int oy = tl.oy0 + (pix >> 4), ox = tl.ox0 + (pix & 15);
                 const bool ok = oy < g.Ho && ox < g.Wo;
-                cv_cp8(sd + pix * g.pitch_o + v * 4, ok ? db + ((int64_t)oy * g.Wo + ox) * g.Cout + v * 4 : dy, ok);
+                cv_cp8(sd + pix * g.pitch_o + v * 4, ok ? db + ((int64_t)oy * g.Wo + ox) * g.gd_pitch + v * 4 : dy, ok);
             }
         }
         cv_commit();
@@ -309,6 +309,7 @@ static void cv_base_geom(const lmnet_conv3x3_dims* d, int TH, CvGeom& g) {
     g.tiles_y = (g.Ho + TH - 1) / TH;
     g.tiles = g.B * g.tiles_x * g.tiles_y;
     g.ksteps = (d->Cin + 15) / 16;
+    g.gx_pitch = d->Cin; g.gd_pitch = d->Cout;
 }
 
 struct CvFwdPlan {
@@ -431,18 +432,32 @@ extern "C" int lmnet_conv3x3_fwd_supported(const lmnet_conv3x3_dims* d, int dtyp
     return cv_fwd_plan(d, pl) ? 1 : 0;
 }
 
-extern "C" int lmnet_conv3x3_fwd(const void* x, const float* weight, int w_transposed, const float* bias, void* y,
-                                 const lmnet_conv3x3_dims* d, int dtype, void* stream) {
+// x_pixel_pitch: elements between consecutive pixels of x (0 or Cin = dense; larger = a channel slice of a wider
+// channels-last tensor); vectors of 8 (Cin % 8 == 0) or 4 elements must stay aligned
+static bool cv_pitch_ok(const void* base, int pitch, int channels) {
+    if (pitch == 0 || pitch == channels) return (uintptr_t)base % 16 == 0;
+    const int vec_bytes = channels % 8 == 0 ? 16 : 8;
+    return pitch > channels && (pitch * 2) % vec_bytes == 0 && (uintptr_t)base % vec_bytes == 0;
+}
+
+extern "C" int lmnet_conv3x3_fwd_strided(const void* x, int x_pixel_pitch, const float* weight, int w_transposed, const float* bias,
+                                         void* y, const lmnet_conv3x3_dims* d, int dtype, void* stream) {
     if (!lmnet_conv3x3_fwd_supported(d, dtype)) return LMNET_ERR_UNSUPPORTED;
     if (!x || !weight || !y) return LMNET_ERR_INVALID_ARG;
-    if ((uintptr_t)x % 16 != 0 || (uintptr_t)y % 16 != 0) return LMNET_ERR_UNSUPPORTED;
+    if (!cv_pitch_ok(x, x_pixel_pitch, d->Cin) || (uintptr_t)y % 16 != 0) return LMNET_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
     const int w_t = w_transposed ? 1 : 0;
-    if (cv_fast_fwd_has(d->stride, d->Cin, d->Cout)) return cv_fast_fwd(x, weight, w_t, bias, y, d, dtype, st);
+    if (cv_fast_fwd_has(d->stride, d->Cin, d->Cout)) return cv_fast_fwd(x, weight, w_t, bias, y, d, dtype, st, x_pixel_pitch);
     CvFwdPlan pl{};
     cv_fwd_plan(d, pl);
+    if (x_pixel_pitch > 0) pl.g.gx_pitch = x_pixel_pitch;
     return dtype == LMNET_BF16 ? cv_fwd_dispatch<__nv_bfloat16>(x, weight, w_t, bias, y, pl, st)
                                : cv_fwd_dispatch<__half>(x, weight, w_t, bias, y, pl, st);
+}
+
+extern "C" int lmnet_conv3x3_fwd(const void* x, const float* weight, int w_transposed, const float* bias, void* y,
+                                 const lmnet_conv3x3_dims* d, int dtype, void* stream) {
+    return lmnet_conv3x3_fwd_strided(x, 0, weight, w_transposed, bias, y, d, dtype, stream);
 }
 
 extern "C" int lmnet_conv3x3_wgrad_supported(const lmnet_conv3x3_dims* d, int dtype) {
@@ -463,11 +478,11 @@ extern "C" size_t lmnet_conv3x3_wgrad_workspace_bytes(const lmnet_conv3x3_dims* 
     return ((size_t)pl.grid * 9 * pl.MT * 16 * pl.NTC * 8 + (size_t)pl.grid * pl.MT * 16) * sizeof(float);
 }
 
-extern "C" int lmnet_conv3x3_wgrad(const void* x, const void* dy, float* dW, float* dbias, void* workspace, size_t workspace_bytes,
-                                   const lmnet_conv3x3_dims* d, int dtype, void* stream) {
+extern "C" int lmnet_conv3x3_wgrad_strided(const void* x, const void* dy, int dy_pixel_pitch, float* dW, float* dbias, void* workspace,
+                                           size_t workspace_bytes, const lmnet_conv3x3_dims* d, int dtype, void* stream) {
     if (!lmnet_conv3x3_wgrad_supported(d, dtype)) return LMNET_ERR_UNSUPPORTED;
     if (!x || !dy || !dW || !workspace) return LMNET_ERR_INVALID_ARG;
-    if ((uintptr_t)x % 16 != 0 || (uintptr_t)dy % 16 != 0) return LMNET_ERR_UNSUPPORTED;
+    if ((uintptr_t)x % 16 != 0 || !cv_pitch_ok(dy, dy_pixel_pitch, d->Cout)) return LMNET_ERR_UNSUPPORTED;
     if (workspace_bytes < lmnet_conv3x3_wgrad_workspace_bytes(d)) return LMNET_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     const int n_out = 9 * d->Cout * d->Cin + d->Cout;
@@ -476,7 +491,7 @@ extern "C" int lmnet_conv3x3_wgrad(const void* x, const void* dy, float* dW, flo
         const int grid = cv_fast_wgrad_grid(d, &mp, &ldn);
         float* fpart = (float*)workspace;
         float* fpart_b = fpart + (size_t)grid * 9 * mp * ldn;
-        const int frc = cv_fast_wgrad(x, dy, fpart, fpart_b, d, dtype, st);
+        const int frc = cv_fast_wgrad(x, dy, fpart, fpart_b, d, dtype, st, dy_pixel_pitch);
         if (frc != LMNET_OK) return frc;
         LMNET_LAUNCH(KID_CONV3X3_REDUCE, st, 0, (conv3x3_wgrad_reduce_kernel<<<(n_out + 63) / 64, 256, 0, st>>>(
             fpart, fpart_b, dW, dbias, grid, d->Cout, d->Cin, mp, ldn)));
@@ -484,6 +499,7 @@ extern "C" int lmnet_conv3x3_wgrad(const void* x, const void* dy, float* dW, flo
     }
     CvWgPlan pl{};
     cv_wg_plan(d, pl);
+    if (dy_pixel_pitch > 0) pl.g.gd_pitch = dy_pixel_pitch;
     float* part = (float*)workspace;
     float* part_b = part + (size_t)pl.grid * 9 * pl.MT * 16 * pl.NTC * 8;
     int rc = dtype == LMNET_BF16 ? cv_wg_dispatch<__nv_bfloat16>(x, dy, part, part_b, pl, st)
@@ -493,4 +509,9 @@ extern "C" int lmnet_conv3x3_wgrad(const void* x, const void* dy, float* dW, flo
     LMNET_LAUNCH(KID_CONV3X3_REDUCE, st, 0, (conv3x3_wgrad_reduce_kernel<<<(n + 63) / 64, 256, 0, st>>>(
         part, part_b, dW, dbias, pl.grid, d->Cout, d->Cin, pl.MT * 16, pl.NTC * 8)));
     return LMNET_OK;
+}
+
+extern "C" int lmnet_conv3x3_wgrad(const void* x, const void* dy, float* dW, float* dbias, void* workspace, size_t workspace_bytes,
+                                   const lmnet_conv3x3_dims* d, int dtype, void* stream) {
+    return lmnet_conv3x3_wgrad_strided(x, dy, 0, dW, dbias, workspace, workspace_bytes, d, dtype, stream);
 }

@@ -12,6 +12,9 @@ constexpr int kCvTW = 16;              // output pixels per tile row = one MMA M
 struct CvGeom {
     int B, H, W, Ho, Wo, Cin, Cout, S;
     int pitch_x, pitch_w, pitch_o;     // element pitches: staged input pixel, weight row, staged output pixel
+    int gx_pitch, gd_pitch;            // GLOBAL pixel pitch (elements) of the input tensor and of dy in the weight gradient:
+                                       // Cin / Cout for dense tensors, larger for a channel slice of a wider channels-last
+                                       // tensor (the gradient slices autograd hands a convolution whose output was concatenated)
     int TH, IH, IW;                    // output rows per tile; staged input rows / pixels per row
     int tiles_x, tiles_y, tiles;
     int ksteps;                        // ceil(Cin / 16)
@@ -87,7 +90,7 @@ __device__ __forceinline__ CvTile cv_tile(const CvGeom& g, int t) {
 template <typename T, int NTHREADS>
 __device__ __forceinline__ void cv_issue_x(T* s, const T* __restrict__ x, const CvGeom& g, const CvTile& tl) {
     const int iy0 = tl.oy0 * g.S - 1, ix0 = tl.ox0 * g.S - 1;
-    const T* xb = x + (int64_t)tl.b * g.H * g.W * g.Cin;
+    const T* xb = x + (int64_t)tl.b * g.H * g.W * g.gx_pitch;
     const int npix = g.IH * g.IW;
     if ((g.Cin & 7) == 0) {
         const int vpp = g.Cin >> 3;
@@ -96,7 +99,7 @@ __device__ __forceinline__ void cv_issue_x(T* s, const T* __restrict__ x, const 
             const int r = pix / g.IW, c = pix - r * g.IW;
             const int iy = iy0 + r, ix = ix0 + c;
             const bool ok = iy >= 0 && iy < g.H && ix >= 0 && ix < g.W;
-            cv_cp16(s + pix * g.pitch_x + v * 8, ok ? xb + ((int64_t)iy * g.W + ix) * g.Cin + v * 8 : x, ok);
+            cv_cp16(s + pix * g.pitch_x + v * 8, ok ? xb + ((int64_t)iy * g.W + ix) * g.gx_pitch + v * 8 : x, ok);
         }
     } else {
         const int vpp = g.Cin >> 2;
@@ -105,7 +108,7 @@ __device__ __forceinline__ void cv_issue_x(T* s, const T* __restrict__ x, const 
             const int r = pix / g.IW, c = pix - r * g.IW;
             const int iy = iy0 + r, ix = ix0 + c;
             const bool ok = iy >= 0 && iy < g.H && ix >= 0 && ix < g.W;
-            cv_cp8(s + pix * g.pitch_x + v * 4, ok ? xb + ((int64_t)iy * g.W + ix) * g.Cin + v * 4 : x, ok);
+            cv_cp8(s + pix * g.pitch_x + v * 4, ok ? xb + ((int64_t)iy * g.W + ix) * g.gx_pitch + v * 4 : x, ok);
         }
     }
 }
@@ -143,8 +146,10 @@ __device__ __forceinline__ void cv_stage_weights(T* s_w, const float* __restrict
 // channel-specialised kernels (conv3x3_fast.cu): LMNET_ERR_UNSUPPORTED when (stride, Cin, Cout) is not in their list
 bool cv_fast_fwd_has(int S, int Cin, int Cout);
 bool cv_fast_wgrad_has(int S, int Cin, int Cout);
-int cv_fast_fwd(const void* x, const float* w, int w_t, const float* bias, void* y, const lmnet_conv3x3_dims* d, int dtype, cudaStream_t st);
+int cv_fast_fwd(const void* x, const float* w, int w_t, const float* bias, void* y, const lmnet_conv3x3_dims* d, int dtype, cudaStream_t st,
+                int x_pitch = 0);
 int cv_fast_wgrad_grid(const lmnet_conv3x3_dims* d, int* mp, int* ldn);     // CTAs (= partials), padded Cout, padded Cin
-int cv_fast_wgrad(const void* x, const void* dy, float* part, float* part_b, const lmnet_conv3x3_dims* d, int dtype, cudaStream_t st);
+int cv_fast_wgrad(const void* x, const void* dy, float* part, float* part_b, const lmnet_conv3x3_dims* d, int dtype, cudaStream_t st,
+                  int dy_pitch = 0);
 
 }  // namespace lmnet

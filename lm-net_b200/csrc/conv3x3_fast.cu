@@ -55,14 +55,14 @@ template <typename T, int NTHREADS, int S, int CIN, int IHT, int IW, int PX>
 __device__ __forceinline__ void cvf_issue_x(uint32_t s, const T* __restrict__ x, const CvGeom& g, const CvTile& tl) {
     constexpr int VIN = CIN % 8 == 0 ? 8 : 4, VPP = CIN / VIN, TOTAL = IHT * IW * VPP;
     const int iy0 = tl.oy0 * S - 1, ix0 = tl.ox0 * S - 1;
-    const T* xb = x + (int64_t)tl.b * g.H * g.W * CIN;
+    const T* xb = x + (int64_t)tl.b * g.H * g.W * g.gx_pitch;
 #pragma unroll 4
     for (int i = threadIdx.x; i < TOTAL; i += NTHREADS) {
         const int pix = i / VPP, v = i - pix * VPP;
         const int r = pix / IW, c = pix - r * IW;
         const int iy = iy0 + r, ix = ix0 + c;
         const bool ok = (unsigned)iy < (unsigned)g.H && (unsigned)ix < (unsigned)g.W;
-        cv_cp_a(s + (pix * PX + v * VIN) * 2, ok ? xb + ((int64_t)iy * g.W + ix) * CIN + v * VIN : x, ok, VIN == 8);
+        cv_cp_a(s + (pix * PX + v * VIN) * 2, ok ? xb + ((int64_t)iy * g.W + ix) * g.gx_pitch + v * VIN : x, ok, VIN == 8);
     }
 }
 
@@ -197,14 +197,14 @@ conv3x3_wgrad_fast_kernel(const T* __restrict__ x, const T* __restrict__ dy, flo
         const uint32_t sx = s_base + st * STAGE * 2;
         cvf_issue_x<T, kCvWgThreads, S, CIN, C::WIH, IW, PX>(sx, x, g, tl);
         const uint32_t sd = sx + C::WX_ELEMS * 2;
-        const T* db = dy + (int64_t)tl.b * g.Ho * g.Wo * COUT;
+        const T* db = dy + (int64_t)tl.b * g.Ho * g.Wo * g.gd_pitch;
         constexpr int VOUT = C::VOUT, VPP = C::VPP_OUT, TOTAL = TH * kCvTW * VPP;
 #pragma unroll 2
         for (int i = threadIdx.x; i < TOTAL; i += kCvWgThreads) {
             const int pix = i / VPP, v = i - pix * VPP;
             const int oy = tl.oy0 + (pix >> 4), ox = tl.ox0 + (pix & 15);
             const bool ok = oy < g.Ho && ox < g.Wo;
-            cv_cp_a(sd + (pix * PD + v * VOUT) * 2, ok ? db + ((int64_t)oy * g.Wo + ox) * COUT + v * VOUT : dy, ok, VOUT == 8);
+            cv_cp_a(sd + (pix * PD + v * VOUT) * 2, ok ? db + ((int64_t)oy * g.Wo + ox) * g.gd_pitch + v * VOUT : dy, ok, VOUT == 8);
         }
         cv_commit();
     };
@@ -320,6 +320,7 @@ static void cvf_geom(const lmnet_conv3x3_dims* d, int TH, CvGeom& g) {
     g.tiles = g.B * g.tiles_x * g.tiles_y;
     g.ksteps = (d->Cin + 15) / 16;
     g.pitch_x = g.pitch_w = g.pitch_o = 0;
+    g.gx_pitch = d->Cin; g.gd_pitch = d->Cout;
 }
 
 static int cvf_grid(int tiles, size_t smem, int cap) {
@@ -330,24 +331,27 @@ static int cvf_grid(int tiles, size_t smem, int cap) {
 }
 
 template <typename T, int S, int CIN, int COUT>
-static int cvf_fwd_launch(const void* x, const float* w, int w_t, const float* bias, void* y, const lmnet_conv3x3_dims* d, cudaStream_t st) {
+static int cvf_fwd_launch(const void* x, const float* w, int w_t, const float* bias, void* y, const lmnet_conv3x3_dims* d, cudaStream_t st,
+                          int x_pitch) {
     using C = CvCfg<S, CIN, COUT>;
     auto kern = conv3x3_fwd_fast_kernel<T, S, CIN, COUT>;
     static std::atomic<size_t> granted[kMaxDevices];
     if (!ensure_smem(kern, C::SMEM, granted)) return LMNET_ERR_LAUNCH;
     CvGeom g;
     cvf_geom(d, C::TH, g);
+    if (x_pitch > 0) g.gx_pitch = x_pitch;
     g.ncta = cvf_grid(g.tiles, C::SMEM, 4);
     const double bytes = ((double)g.B * g.H * g.W * g.Cin + (double)g.B * g.Ho * g.Wo * g.Cout) * sizeof(T);
     LMNET_LAUNCH(KID_CONV3X3, st, bytes, (kern<<<g.ncta, kCvThreads, C::SMEM, st>>>((const T*)x, w, w_t, bias, (T*)y, g)));
     return LMNET_OK;
 }
 
-int cv_fast_fwd(const void* x, const float* w, int w_t, const float* bias, void* y, const lmnet_conv3x3_dims* d, int dtype, cudaStream_t st) {
+int cv_fast_fwd(const void* x, const float* w, int w_t, const float* bias, void* y, const lmnet_conv3x3_dims* d, int dtype, cudaStream_t st,
+                int x_pitch) {
 #define X(SS, CI, CO)                                                                                              \
     if (d->stride == SS && d->Cin == CI && d->Cout == CO)                                                          \
-        return dtype == LMNET_BF16 ? cvf_fwd_launch<__nv_bfloat16, SS, CI, CO>(x, w, w_t, bias, y, d, st)         \
-                                   : cvf_fwd_launch<__half, SS, CI, CO>(x, w, w_t, bias, y, d, st);
+        return dtype == LMNET_BF16 ? cvf_fwd_launch<__nv_bfloat16, SS, CI, CO>(x, w, w_t, bias, y, d, st, x_pitch) \
+                                   : cvf_fwd_launch<__half, SS, CI, CO>(x, w, w_t, bias, y, d, st, x_pitch);
     CV_FAST_FWD_LIST(X)
 #undef X
     return LMNET_ERR_UNSUPPORTED;
@@ -371,24 +375,27 @@ int cv_fast_wgrad_grid(const lmnet_conv3x3_dims* d, int* mp, int* ldn) {
 }
 
 template <typename T, int S, int CIN, int COUT>
-static int cvf_wg_launch(const void* x, const void* dy, float* part, float* part_b, const lmnet_conv3x3_dims* d, cudaStream_t st) {
+static int cvf_wg_launch(const void* x, const void* dy, float* part, float* part_b, const lmnet_conv3x3_dims* d, cudaStream_t st,
+                         int dy_pitch) {
     using C = CvCfg<S, CIN, COUT>;
     auto kern = conv3x3_wgrad_fast_kernel<T, S, CIN, COUT>;
     static std::atomic<size_t> granted[kMaxDevices];
     if (!ensure_smem(kern, C::WSMEM, granted)) return LMNET_ERR_LAUNCH;
     CvGeom g;
     cvf_geom(d, C::WTH, g);
+    if (dy_pitch > 0) g.gd_pitch = dy_pitch;
     g.ncta = cvf_grid(g.tiles, C::WSMEM, 2);
     const double bytes = ((double)g.B * g.H * g.W * g.Cin + (double)g.B * g.Ho * g.Wo * g.Cout) * sizeof(T);
     LMNET_LAUNCH(KID_CONV3X3_WGRAD, st, bytes, (kern<<<g.ncta, kCvWgThreads, C::WSMEM, st>>>((const T*)x, (const T*)dy, part, part_b, g)));
     return LMNET_OK;
 }
 
-int cv_fast_wgrad(const void* x, const void* dy, float* part, float* part_b, const lmnet_conv3x3_dims* d, int dtype, cudaStream_t st) {
+int cv_fast_wgrad(const void* x, const void* dy, float* part, float* part_b, const lmnet_conv3x3_dims* d, int dtype, cudaStream_t st,
+                  int dy_pitch) {
 #define X(SS, CI, CO)                                                                                              \
     if (d->stride == SS && d->Cin == CI && d->Cout == CO)                                                          \
-        return dtype == LMNET_BF16 ? cvf_wg_launch<__nv_bfloat16, SS, CI, CO>(x, dy, part, part_b, d, st)          \
-                                   : cvf_wg_launch<__half, SS, CI, CO>(x, dy, part, part_b, d, st);
+        return dtype == LMNET_BF16 ? cvf_wg_launch<__nv_bfloat16, SS, CI, CO>(x, dy, part, part_b, d, st, dy_pitch) \
+                                   : cvf_wg_launch<__half, SS, CI, CO>(x, dy, part, part_b, d, st, dy_pitch);
     CV_FAST_WG_LIST(X)
 #undef X
     return LMNET_ERR_UNSUPPORTED;

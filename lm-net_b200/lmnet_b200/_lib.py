@@ -170,6 +170,9 @@ def lib():
     L.lmnet_conv3x3_wgrad_workspace_bytes.restype = c_size_t
     L.lmnet_conv3x3_wgrad_workspace_bytes.argtypes = [pcv]
     L.lmnet_conv3x3_wgrad.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, pcv, c_int, c_void_p]
+    L.lmnet_conv3x3_fwd_strided.argtypes = [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, pcv, c_int, c_void_p]
+    L.lmnet_conv3x3_wgrad_strided.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t, pcv, c_int,
+                                              c_void_p]
     L.lmnet_avgpool_cl_fwd.argtypes = [c_void_p, c_void_p, POINTER(PoolDims), c_int, c_void_p]
     L.lmnet_avgpool_cl_bwd.argtypes = [c_void_p, c_void_p, POINTER(PoolDims), c_int, c_void_p]
     L.lmnet_se_gate_supported.argtypes = [c_int, c_int, c_int]

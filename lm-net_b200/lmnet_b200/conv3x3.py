@@ -38,15 +38,30 @@ def wgrad_supported(B, H, W, Cin, Cout, stride, dtype) -> bool:
     return bool(L.lib().lmnet_conv3x3_wgrad_supported(L.byref(_dims(B, H, W, Cin, Cout, stride)), L._DTYPES[dtype]))
 
 
-def _launch_fwd(x, w, transposed, bias, Cout, stride):
-    """x: logical [B,Cin,H,W] in channels-last memory; w: the layer's fp32 weight, read in place by the kernel (transposed:
-    the stride-1 input gradient uses it flipped and transposed); returns logical [B,Cout,Ho,Wo] channels-last."""
+def _pixel_pitch(t):
+    """Pixel pitch (elements) of a logical [B,C,H,W] tensor that is dense channels-last (-> C) or a channel slice of a wider
+    channels-last tensor (-> the wider tensor's channel count, e.g. the gradient slices torch.cat's backward hands out),
+    such that the kernels' 16- / 8-byte vectors stay aligned; None for any other layout."""
+    B, C, H, W = t.shape
+    sb, sc, sh, sw = t.stride()
+    if sc != 1 or sw < C or sh != W * sw or (sb != H * W * sw and B > 1):
+        return None
+    vec = 16 if C % 8 == 0 else 8
+    if (sw * t.element_size()) % vec != 0 or t.data_ptr() % vec != 0:
+        return None
+    return sw
+
+
+def _launch_fwd(x, w, transposed, bias, Cout, stride, pitch=0):
+    """x: logical [B,Cin,H,W] in channels-last memory with pixel pitch `pitch` (0 = dense); w: the layer's fp32 weight, read
+    in place by the kernel (transposed: the stride-1 input gradient uses it flipped and transposed); returns logical
+    [B,Cout,Ho,Wo] channels-last."""
     B, Cin, H, W = x.shape
     Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
     y = torch.empty((B, Cout, Ho, Wo), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
     dims = _dims(B, H, W, Cin, Cout, stride)
-    rc = L.lib().lmnet_conv3x3_fwd(L.ptr(x), L.ptr(w), int(transposed), L.ptr(bias), L.ptr(y), L.byref(dims), L.dtype_code(x),
-                                   L.stream_ptr())
+    rc = L.lib().lmnet_conv3x3_fwd_strided(L.ptr(x), int(pitch), L.ptr(w), int(transposed), L.ptr(bias), L.ptr(y), L.byref(dims),
+                                           L.dtype_code(x), L.stream_ptr())
     L.check(rc, "conv3x3_fwd")
     return y
 
@@ -80,18 +95,33 @@ class _Conv3x3(torch.autograd.Function):
         B, Cin, H, W = x.shape
         Cout = w.shape[0]
         dt = x.dtype
-        dy = _cl(dy.to(dt))
+        dy = dy.to(dt)
+        # the gradient of a convolution whose output was concatenated arrives as a channel slice of the concatenation's
+        # channels-last gradient: the kernels read it in place (pixel pitch); any other layout is densified once
+        pitch = _pixel_pitch(dy) if dy.dim() == 4 else None
+        if pitch is None:
+            dy = _cl(dy)
+            pitch = 0
+        elif pitch == dy.shape[1]:
+            pitch = 0
         has_bias = ctx.bias_dtype is not None
         dx = dw = db = None
+        dy_dense = None
+
+        def dense():
+            nonlocal dy_dense
+            if dy_dense is None:
+                dy_dense = dy if pitch == 0 else _cl(dy)
+            return dy_dense
 
         def aten_bwd(mask):
-            return torch.ops.aten.convolution_backward(dy, x, w.to(dt), [Cout] if has_bias else None, [s, s], [1, 1], [1, 1],
+            return torch.ops.aten.convolution_backward(dense(), x, w.to(dt), [Cout] if has_bias else None, [s, s], [1, 1], [1, 1],
                                                        False, [0, 0], 1, mask)
 
         if ctx.needs_input_grad[0]:
             Ho, Wo = dy.shape[2], dy.shape[3]
             if s == 1 and fwd_supported(B, Ho, Wo, Cout, Cin, 1, dt):
-                dx = _launch_fwd(dy, _w32(w), True, None, Cin, 1)
+                dx = _launch_fwd(dy, _w32(w), True, None, Cin, 1, pitch)
             else:
                 dx = aten_bwd([True, False, False])[0]
         if ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2]):
@@ -101,8 +131,8 @@ class _Conv3x3(torch.autograd.Function):
                 dbias = torch.empty(Cout, dtype=torch.float32, device=x.device) if has_bias else None
                 n = L.lib().lmnet_conv3x3_wgrad_workspace_bytes(L.byref(dims))
                 ws = torch.empty(max(int(n), 16), dtype=torch.uint8, device=x.device)
-                rc = L.lib().lmnet_conv3x3_wgrad(L.ptr(x), L.ptr(dy), L.ptr(dW), L.ptr(dbias), L.ptr(ws), ws.numel(),
-                                                 L.byref(dims), L.dtype_code(x), L.stream_ptr())
+                rc = L.lib().lmnet_conv3x3_wgrad_strided(L.ptr(x), L.ptr(dy), int(pitch), L.ptr(dW), L.ptr(dbias), L.ptr(ws),
+                                                         ws.numel(), L.byref(dims), L.dtype_code(x), L.stream_ptr())
                 L.check(rc, "conv3x3_wgrad")
                 dw = dW.to(w.dtype)
                 db = dbias.to(ctx.bias_dtype) if has_bias else None

@@ -74,3 +74,51 @@ def test_conv3x3_fallbacks_match_the_stock_module():
     convert_conv3x3(seq)
     assert type(seq[0]) is Conv3x3 and type(seq[1]) is torch.nn.Conv2d and type(seq[2]) is torch.nn.Conv2d
     assert list(seq.state_dict().keys()) == keys
+
+
+@pytest.mark.parametrize("case", [(2, 40, 36, 12, 12, 1, 24, 12), (2, 24, 24, 24, 24, 1, 48, 0), (2, 33, 47, 12, 24, 2, 48, 24),
+                                  (1, 20, 28, 48, 48, 1, 144, 48), (2, 16, 16, 12, 12, 1, 36, 12)],
+                         ids=lambda s: "x".join(map(str, s)))
+def test_conv3x3_backward_reads_concatenation_gradient_slices_in_place(case):
+    """The output of a convolution that goes into torch.cat receives its gradient as a channel slice of the concatenation's
+    channels-last gradient (pixel pitch = total channels).  The kernels read that slice in place; the result must equal the
+    backward on a densified copy bit for bit, and no densifying copy may be launched."""
+    from lmnet_b200.conv3x3 import Conv3x3, _pixel_pitch
+
+    B, H, W, Cin, Cout, s, Ctot, off = case
+    torch.manual_seed(6)
+    conv = Conv3x3(Cin, Cout, 3, s, 1).cuda()
+    x = torch.randn(B, Cin, H, W, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    Ho, Wo = (H - 1) // s + 1, (W - 1) // s + 1
+    wide = torch.randn(B, Ctot, Ho, Wo, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    sl = wide[:, off:off + Cout]                                        # what torch.cat's backward produces
+    assert _pixel_pitch(sl) == Ctot
+
+    def run(go):
+        xc = x.clone().requires_grad_()
+        conv.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            y = conv(xc)
+        y.backward(go)
+        return xc.grad, conv.weight.grad.clone(), conv.bias.grad.clone()
+
+    a = run(sl)
+    b = run(sl.contiguous(memory_format=torch.channels_last))
+    for u, v in zip(a, b):
+        assert torch.equal(u, v)
+    # through autograd's own cat: the gradients of both producers match the stock module
+    conv2 = Conv3x3(Cin, Ctot - Cout, 3, s, 1).cuda() if Ctot > Cout else None
+    if conv2 is not None:
+        xc = x.clone().requires_grad_()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            z = torch.cat([conv(xc), conv2(xc)], 1)
+        conv.zero_grad(set_to_none=True)
+        z.backward(wide)
+        g_own = conv.weight.grad.clone()
+        xs = x.clone().requires_grad_()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            zs = torch.cat([F.conv2d(xs, conv.weight, conv.bias, s, 1), F.conv2d(xs, conv2.weight, conv2.bias, s, 1)], 1)
+        conv.zero_grad(set_to_none=True)
+        zs.backward(wide)
+        assert rel_err(g_own, conv.weight.grad) < 2e-2
+        assert rel_err(xc.grad.float(), xs.grad.float()) < 2e-2
