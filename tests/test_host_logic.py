@@ -266,3 +266,24 @@ def test_step_roofline_table_is_committed_and_plausible():
     spec.loader.exec_module(bench)
     r = bench.step_roofline(16, 352, 46.8)
     assert r is not None and 4.0 < r["t_roof_ms"] < 9.0 and 0 < r["frac"] < 1
+
+
+def test_conv3x3_pixel_pitch_detection():
+    """Host logic of the in-place read of torch.cat gradient slices (lmnet_b200/conv3x3.py::_pixel_pitch): a dense
+    channels-last tensor reports its channel count, a channel slice of a wider channels-last tensor the wider count,
+    anything the kernels' aligned vector loads cannot address reports None."""
+    import torch
+
+    from lmnet_b200.conv3x3 import _pixel_pitch
+
+    wide = torch.zeros(2, 48, 6, 10, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    assert _pixel_pitch(wide) == 48
+    assert _pixel_pitch(wide[:, :24]) == 48 and _pixel_pitch(wide[:, 24:]) == 48
+    assert _pixel_pitch(wide[:, 16:40]) == 48            # 32-byte offset: 16-byte vectors stay aligned
+    assert _pixel_pitch(wide[:, 4:28]) is None           # 8-byte offset breaks the 16-byte vectors of a 24-channel slice
+    assert _pixel_pitch(wide[:, 4:16]) == 48             # ... but not the 8-byte vectors of a 12-channel slice
+    assert _pixel_pitch(torch.zeros(2, 24, 6, 10, dtype=torch.bfloat16)) is None          # NCHW planes
+    assert _pixel_pitch(wide[:, :, ::2]) is None                                            # strided rows
+    assert _pixel_pitch(wide[:, :, :, 1:]) is None                                          # cropped columns
+    one = torch.zeros(1, 24, 6, 10, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    assert _pixel_pitch(one) == 24
